@@ -1,0 +1,205 @@
+/*
+ * sampleqc_cuda.h — C ABI of the B200-native SampleQC EM library (libsampleqc_cuda.so).
+ *
+ * This is the drop-in boundary for ONE path of wmacnair/SampleQC: the multi-sample
+ * Gaussian-mixture EM behind the Rcpp exports
+ *
+ *   fit_sampleqc_robust_cpp(x, init_z, groups, D, J, K, N, em_iters, mcd_alpha,
+ *                           mcd_iters, seed, track)     reference src/fit_sampleQC_robust_cpp.cpp:451
+ *   fit_sampleqc_mle_cpp(x, init_gamma_i, groups, D, J, K, N, n_iter, seed)
+ *                                                       reference src/fit_sampleQC_mle_cpp.cpp:279
+ *
+ * and the post-fit outlier arithmetic of .calc_outliers_dt (reference R/fit_sampleqc.R:419-453).
+ * The Rcpp bodies of those two exports become marshalling stubs that call the entry points
+ * below (see INTEGRATION.md and rpkg/src/); the generated src/RcppExports.cpp:16-54 and its
+ * registration table :229-252 stay untouched.
+ *
+ * Conventions
+ *   - plain C, no CUDA / torch / Rcpp types in any signature;
+ *   - every matrix is COLUMN-MAJOR exactly as R / Armadillo hold it, so the Rcpp stubs can hand
+ *     REAL() pointers straight through:  x is N x D,  alpha_j J x D,  beta_k K x D,
+ *     sigma_k D x D x K,  p_jk J x K,  gamma_i N x K,  track_* as the reference cubes;
+ *   - the caller owns every host pointer (inputs are read-only, outputs caller-allocated);
+ *     the library owns all device memory and frees it before the call returns (or at
+ *     sqc_session_destroy);
+ *   - return value: 0 = ok; >0 = a failure class the reference would also raise as an R error
+ *     (bad mcd_alpha, empty cluster, non-SPD scatter, NaN ...); <0 = CUDA / communicator
+ *     failure.  A NUL-terminated message is written to err (if err != NULL);
+ *   - there is NO CPU fallback: without a usable CUDA device every compute entry point returns
+ *     SQC_ERR_CUDA.
+ */
+#ifndef SAMPLEQC_CUDA_H
+#define SAMPLEQC_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SQC_ABI_VERSION 1
+
+/* ---- status codes --------------------------------------------------------------------- */
+enum {
+  SQC_OK                 = 0,
+  /* reference-equivalent failure classes (the reference throws / Armadillo throws) */
+  SQC_ERR_BAD_ARG        = 1,  /* e.g. mcd_alpha outside [0,1): robust_cpp.cpp:471-472        */
+  SQC_ERR_EMPTY_CLUSTER  = 2,  /* n_k == 0: x_k.rows(0,-1), robust_cpp.cpp:307                */
+  SQC_ERR_SUBSET_SIZE    = 3,  /* h_k < 1 or h_k > n_k: randperm / span failure, :72, :51     */
+  SQC_ERR_NOT_SPD        = 4,  /* chol() of a non-SPD scatter, robust_cpp.cpp:19              */
+  SQC_ERR_SINGULAR       = 5,  /* inv() of a singular matrix, :127, :153 / mle_cpp.cpp:39,60  */
+  SQC_ERR_NAN            = 6,  /* NaN distance reaching sort_index, :50                       */
+  SQC_ERR_SELECT         = 7,  /* exact selection could not be resolved (more exactly-tied
+                                  distances than the candidate store holds)                   */
+  /* infrastructure failures */
+  SQC_ERR_CUDA           = -1,
+  SQC_ERR_COMM           = -2,
+  SQC_ERR_NOMEM          = -3
+};
+
+/* rng_mode: how the random start of every FastMCD (arma::randperm, robust_cpp.cpp:72) is keyed */
+enum {
+  SQC_RNG_R_COMPAT = 0, /* R's Mersenne-Twister stream after set.seed(seed) (helpers.cpp:10-14),
+                           one unif_rand per cell per update_beta_scale_k call, consumed in
+                           cluster-then-cell order; key = (int) Rf_runif(0, RAND_MAX)          */
+  SQC_RNG_COUNTER  = 1  /* counter-based keys hashed from (seed, call, original cell index);
+                           not stream-compatible with R, identical in oracle and CUDA          */
+};
+
+/* ---- fit arguments -------------------------------------------------------------------- */
+typedef struct sqc_fit_args {
+  uint32_t abi_version;     /* SQC_ABI_VERSION                                               */
+  int32_t  D, J, K;         /* metrics, samples, mixture components                          */
+  int64_t  N;               /* cells                                                         */
+  const double*  x;         /* N x D column-major, un-centred (R matrix)                     */
+  const int32_t* groups;    /* N, 0-based sample index of every cell                         */
+  const int32_t* init_z;    /* robust: N, 0-based initial labels (R sends doubles; the Rcpp
+                               stub converts, as arma::uvec conversion does today)           */
+  const double*  init_gamma;/* mle: N x K column-major initial responsibilities              */
+  int32_t  em_iters;        /* robust: max EM iterations; mle: n_iter (fixed count)          */
+  int32_t  mcd_iters;       /* robust: max C-steps per FastMCD                               */
+  double   mcd_alpha;       /* robust: subset fraction, h_k = int((n_k + D + 1) * mcd_alpha) */
+  uint32_t seed;            /* as received by the export          */
+  int32_t  track;           /* robust: fill track_* outputs                                  */
+  int32_t  rng_mode;        /* SQC_RNG_*                                                     */
+  int32_t  device;          /* CUDA device ordinal; -1 = current device                      */
+  /* multi-GPU (cells sharded by sample, one process per GPU).  world <= 1 means single GPU. */
+  int32_t  rank, world;
+  int64_t  cell_offset;     /* index of this shard's first cell in the full data set         */
+  int64_t  N_total;         /* cells over all shards (== N when world <= 1)                  */
+  const void* peer_handles; /* world x SQC_IPC_HANDLE_BYTES: sqc_xchg_export() of every rank */
+} sqc_fit_args;
+
+/* ---- fit outputs (all caller-allocated; NULL pointers are skipped) --------------------- */
+typedef struct sqc_fit_out {
+  double*  mu_0;            /* D                                                             */
+  double*  alpha_j;         /* J x D                                                         */
+  double*  beta_k;          /* K x D, rows ordered by ascending beta_k[,0] (:527-531)        */
+  double*  sigma_k;         /* D x D x K                                                     */
+  int32_t* z;               /* N, 1-based labels after the final relabel (the list's z)      */
+  double*  p_jk;            /* J x K                                                         */
+  double*  like_1;          /* em_iters, zero padded                                         */
+  double*  like_2;          /* em_iters, zero padded                                         */
+  double*  gamma_i;         /* mle: N x K (columns NOT reordered, as in mle_cpp.cpp:350)     */
+  double*  p_k;             /* mle: K                                                        */
+  double*  track_alpha_j;   /* robust+track: J x D x em_iters                                */
+  double*  track_beta_k;    /* robust+track: K x D x em_iters                                */
+  double*  track_sigma_k;   /* robust+track: D*D x K x em_iters                              */
+  double*  track_p_jk;      /* robust+track: J x K x em_iters                                */
+  int32_t  n_iter;          /* EM iterations executed ("took %d iterations", :524)           */
+  int32_t  mcd_iters_hit;   /* times fast_mcd reached mcd_iters (:94-95)                     */
+  int32_t  n_zero_like;     /* the reference's n_zeros counter (:380-382, :392-393)          */
+  int64_t  rng_draws;       /* unif_rand draws consumed = (1 + n_iter) * N_total (robust)    */
+  int32_t  rng_state[625];  /* R's .Random.seed payload (mti, mt[624]) after those draws,
+                               R_COMPAT mode only; lets the Rcpp stub leave R's RNG where the
+                               reference would have left it                                  */
+} sqc_fit_out;
+
+/* One-shot fits with HOST buffers: upload, run the whole EM on the device, download.
+ * These are what the Rcpp stubs call.  replaces robust_cpp.cpp:451-577 / mle_cpp.cpp:279-357 */
+int sqc_fit_robust(const sqc_fit_args* args, sqc_fit_out* out, char* err, size_t errlen);
+int sqc_fit_mle   (const sqc_fit_args* args, sqc_fit_out* out, char* err, size_t errlen);
+
+/* ---- post-fit outlier arithmetic (.calc_outliers_dt, R/fit_sampleqc.R:419-453) ---------- */
+typedef struct sqc_maha_args {
+  uint32_t abi_version;
+  int32_t  D, J, K;
+  int64_t  N;
+  const double*  x;         /* N x D column-major, un-centred                                */
+  const int32_t* groups;    /* N, 0-based                                                    */
+  const double*  mu_0;      /* D       (already re-centred as in R/fit_sampleqc.R:242-246)   */
+  const double*  alpha_j;   /* J x D                                                         */
+  const double*  beta_k;    /* K x D                                                         */
+  const double*  sigma_k;   /* D x D x K                                                     */
+  double   alpha;           /* outlier level; cut = qchisq(1 - alpha, D)                     */
+  int32_t  device;
+} sqc_maha_args;
+
+/* maha: N x K column-major (may be NULL), outlier: N bytes 0/1, maha_cut: the chi-square cut */
+int sqc_outlier_maha(const sqc_maha_args* args, double* maha, uint8_t* outlier,
+                     double* maha_cut, char* err, size_t errlen);
+
+/* ---- resident sessions (benchmarks, multi-GPU drivers) --------------------------------- */
+/* A session keeps the cell matrix resident in HBM so that the EM loop can be timed without the
+ * host<->device copies, and exposes per-kernel device timings for the roofline report.       */
+typedef struct sqc_session sqc_session;
+
+enum { SQC_VARIANT_ROBUST = 0, SQC_VARIANT_MLE = 1 };
+
+/* per-kernel-family accounting of the last sqc_session_run (device times from CUDA events)   */
+#define SQC_N_KERNEL_FAMILIES 8
+enum {
+  SQC_KF_ESTEP     = 0,  /* E-step: densities, argmax / gamma, likelihood, (j,k) statistics   */
+  SQC_KF_PARTITION = 1,  /* residual partition by cluster + like_1                            */
+  SQC_KF_MCD       = 2,  /* M-step: FastMCD selection + masked moments (persistent kernel)    */
+  SQC_KF_UPDATE    = 3,  /* small parameter-update kernels                                    */
+  SQC_KF_RNG       = 4,  /* Mersenne-Twister key stream                                       */
+  SQC_KF_INIT      = 5,  /* column means, centring, initial statistics                        */
+  SQC_KF_MLE_PASS  = 6,  /* MLE fused E/M passes                                              */
+  SQC_KF_FINAL     = 7   /* relabel / gather                                                  */
+};
+
+typedef struct sqc_run_stats {
+  int32_t n_iter;                              /* EM iterations executed                      */
+  int32_t n_gpu_launches;                      /* kernels launched by the run                 */
+  double  loop_ms;                             /* device time of the EM loop (events)         */
+  double  init_ms;                             /* device time of centring / initial M-step    */
+  double  family_ms[SQC_N_KERNEL_FAMILIES];    /* summed device time per family               */
+  int64_t family_launches[SQC_N_KERNEL_FAMILIES];
+  double  family_bytes[SQC_N_KERNEL_FAMILIES]; /* algorithmic bytes moved (DESIGN.md model)   */
+  int64_t mcd_passes;                          /* streaming passes executed inside MCD        */
+  int64_t mcd_csteps;                          /* lock-step C-steps executed                  */
+} sqc_run_stats;
+
+int  sqc_session_create (const sqc_fit_args* args, int variant, sqc_session** out,
+                         char* err, size_t errlen);      /* allocates + uploads (H2D)          */
+int  sqc_session_run    (sqc_session* s, char* err, size_t errlen); /* re-runnable: resets state,
+                                                             runs init + EM loop on device     */
+int  sqc_session_fetch  (sqc_session* s, sqc_fit_out* out, char* err, size_t errlen); /* D2H   */
+int  sqc_session_stats  (const sqc_session* s, sqc_run_stats* stats);
+void sqc_session_destroy(sqc_session* s);
+
+/* ---- multi-GPU exchange bootstrap ------------------------------------------------------ */
+/* Each rank allocates its exchange window and exports an IPC handle; the host side gathers all
+ * handles (torch.distributed / MPI / files - plumbing) and passes them in sqc_fit_args.        */
+#define SQC_IPC_HANDLE_BYTES 64
+int sqc_xchg_export(int device, void* handle_out /* SQC_IPC_HANDLE_BYTES */, char* err, size_t errlen);
+int sqc_xchg_release(int device);
+
+/* ---- misc ------------------------------------------------------------------------------ */
+int         sqc_abi_version(void);
+int         sqc_device_count(void);          /* <0 on CUDA failure                            */
+const char* sqc_status_name(int status);
+/* device-side special functions exposed for tests: qchisq(p, df) evaluated by the same device
+ * routine the MCD consistency factor uses (replaces R::qchisq, robust_cpp.cpp:102)            */
+int sqc_device_qchisq(const double* p, const double* df, double* out, int32_t n, int device,
+                      char* err, size_t errlen);
+/* the R-compatible Mersenne-Twister key stream generated on the device (tests)               */
+int sqc_device_rkeys(uint32_t seed, int64_t skip, int32_t* keys_out, int64_t n, int device,
+                     char* err, size_t errlen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAMPLEQC_CUDA_H */

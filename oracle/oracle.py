@@ -1,0 +1,134 @@
+"""ctypes front-end of the CPU oracle (oracle/libsqc_oracle.so).  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
+this module.  The product package (sampleqc_b200/) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(_HERE))
+from sampleqc_b200 import _abi as A  # noqa: E402  (ABI description only)
+
+_LIB = None
+_REF = None
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "libsqc_oracle.so")
+    src = os.path.join(_HERE, "sqc_oracle.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", _HERE, "libsqc_oracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        for name in ("sqc_oracle_fit_robust", "sqc_oracle_fit_mle"):
+            f = getattr(L, name)
+            f.argtypes = [C.POINTER(A.SqcFitArgs), C.POINTER(A.SqcFitOut), C.c_char_p, C.c_size_t]
+            f.restype = C.c_int
+        L.sqc_oracle_outlier_maha.argtypes = [C.POINTER(A.SqcMahaArgs), A.c_double_p, A.c_uint8_p, A.c_double_p, C.c_char_p, C.c_size_t]
+        L.sqc_oracle_outlier_maha.restype = C.c_int
+        L.sqc_oracle_runif.argtypes = [C.c_uint32, A.c_double_p, C.c_int64]
+        L.sqc_oracle_rkeys.argtypes = [C.c_uint32, C.c_int64, A.c_int32_p, C.c_int64]
+        L.sqc_oracle_counter_key.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64]
+        L.sqc_oracle_counter_key.restype = C.c_int32
+        L.sqc_oracle_qchisq.argtypes = [C.c_double, C.c_double]
+        L.sqc_oracle_qchisq.restype = C.c_double
+        L.sqc_oracle_set_cost_faithful.argtypes = [C.c_int]
+        L.sqc_oracle_fast_mcd.argtypes = [A.c_double_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_uint32,
+                                          A.c_double_p, A.c_double_p, A.c_int32_p, A.c_double_p, C.c_char_p, C.c_size_t]
+        L.sqc_oracle_fast_mcd.restype = C.c_int
+        _LIB = L
+    return _LIB
+
+
+def _run(fn, args, bufs):
+    err = C.create_string_buffer(512)
+    st = fn(C.byref(args), C.byref(bufs.out), err, 512)
+    if st != 0:
+        raise A.SampleQCError(st, err.value.decode(errors="replace"))
+    return bufs.as_list()
+
+
+def fit_sampleqc_robust_cpp(x, init_z, groups, D, J, K, N, em_iters, mcd_alpha, mcd_iters, seed, track=False,
+                            rng_mode=A.SQC_RNG_R_COMPAT, fn=None):
+    args, keep = A.make_fit_args(x, groups, D, J, K, N, em_iters, init_z=init_z, mcd_alpha=mcd_alpha,
+                                 mcd_iters=mcd_iters, seed=seed, track=track, rng_mode=rng_mode)
+    bufs = A.FitBuffers(D, J, K, N, em_iters, A.SQC_VARIANT_ROBUST, track)
+    return _run(fn or lib().sqc_oracle_fit_robust, args, bufs)
+
+
+def fit_sampleqc_mle_cpp(x, init_gamma_i, groups, D, J, K, N, n_iter, seed, fn=None):
+    args, keep = A.make_fit_args(x, groups, D, J, K, N, n_iter, init_gamma=init_gamma_i, seed=seed)
+    bufs = A.FitBuffers(D, J, K, N, n_iter, A.SQC_VARIANT_MLE)
+    return _run(fn or lib().sqc_oracle_fit_mle, args, bufs)
+
+
+def outlier_maha(x, groups, mu_0, alpha_j, beta_k, sigma_k, alpha, fn=None):
+    xa = A.f64_colmajor(x)
+    N, D = xa.shape
+    aj, bk, sk = A.f64_colmajor(alpha_j), A.f64_colmajor(beta_k), A.f64_colmajor(sigma_k)
+    J, K = aj.shape[0], bk.shape[0]
+    ga = A.as_i32(groups)
+    m0 = np.ascontiguousarray(np.asarray(mu_0, dtype=np.float64).reshape(-1))
+    a = A.SqcMahaArgs()
+    a.abi_version, a.D, a.J, a.K, a.N = A.SQC_ABI_VERSION, D, J, K, N
+    a.x, a.groups, a.mu_0, a.alpha_j, a.beta_k, a.sigma_k = A.ptr_d(xa), A.ptr_i(ga), A.ptr_d(m0), A.ptr_d(aj), A.ptr_d(bk), A.ptr_d(sk)
+    a.alpha, a.device = float(alpha), -1
+    maha = np.zeros((N, K), order="F")
+    out = np.zeros(N, dtype=np.uint8)
+    cut = C.c_double(0)
+    err = C.create_string_buffer(512)
+    st = (fn or lib().sqc_oracle_outlier_maha)(C.byref(a), A.ptr_d(maha), out.ctypes.data_as(A.c_uint8_p), C.byref(cut), err, 512)
+    if st != 0:
+        raise A.SampleQCError(st, err.value.decode(errors="replace"))
+    return maha, out.astype(bool), cut.value
+
+
+def runif(seed: int, n: int) -> np.ndarray:
+    out = np.zeros(n)
+    lib().sqc_oracle_runif(seed, A.ptr_d(out), n)
+    return out
+
+
+def rkeys(seed: int, skip: int, n: int) -> np.ndarray:
+    out = np.zeros(n, dtype=np.int32)
+    lib().sqc_oracle_rkeys(seed, skip, A.ptr_i(out), n)
+    return out
+
+
+def counter_key(seed: int, call: int, cell: int) -> int:
+    return int(lib().sqc_oracle_counter_key(seed, call, cell))
+
+
+def qchisq(p: float, df: float) -> float:
+    return float(lib().sqc_oracle_qchisq(p, df))
+
+
+def set_cost_faithful(on: bool) -> None:
+    lib().sqc_oracle_set_cost_faithful(int(on))
+
+
+def fast_mcd(xk, h, mcd_iters, seed):
+    xk = np.ascontiguousarray(np.asarray(xk, dtype=np.float64))
+    n, D = xk.shape
+    loc = np.zeros(D)
+    scale = np.zeros((D, D), order="F")
+    iters = C.c_int32(0)
+    q = C.c_double(0)
+    err = C.create_string_buffer(512)
+    st = lib().sqc_oracle_fast_mcd(A.ptr_d(xk), n, D, h, mcd_iters, seed, A.ptr_d(loc), A.ptr_d(scale),
+                                   C.byref(iters), C.byref(q), err, 512)
+    if st != 0:
+        raise A.SampleQCError(st, err.value.decode(errors="replace"))
+    return loc, scale, iters.value, q.value
