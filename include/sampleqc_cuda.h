@@ -40,6 +40,12 @@ extern "C" {
 
 #define SQC_ABI_VERSION 1
 
+#if defined(__GNUC__)
+#define SQC_API __attribute__((visibility("default")))
+#else
+#define SQC_API
+#endif
+
 /* ---- status codes --------------------------------------------------------------------- */
 enum {
   SQC_OK                 = 0,
@@ -63,8 +69,9 @@ enum {
   SQC_RNG_R_COMPAT = 0, /* R's Mersenne-Twister stream after set.seed(seed) (helpers.cpp:10-14),
                            one unif_rand per cell per update_beta_scale_k call, consumed in
                            cluster-then-cell order; key = (int) Rf_runif(0, RAND_MAX)          */
-  SQC_RNG_COUNTER  = 1  /* counter-based keys hashed from (seed, call, original cell index);
-                           not stream-compatible with R, identical in oracle and CUDA          */
+  SQC_RNG_COUNTER  = 1  /* counter-based keys hashed from (seed, position in that same stream);
+                           random access, not stream-compatible with R, identical in oracle
+                           and CUDA                                                            */
 };
 
 /* ---- fit arguments -------------------------------------------------------------------- */
@@ -118,8 +125,8 @@ typedef struct sqc_fit_out {
 
 /* One-shot fits with HOST buffers: upload, run the whole EM on the device, download.
  * These are what the Rcpp stubs call.  replaces robust_cpp.cpp:451-577 / mle_cpp.cpp:279-357 */
-int sqc_fit_robust(const sqc_fit_args* args, sqc_fit_out* out, char* err, size_t errlen);
-int sqc_fit_mle   (const sqc_fit_args* args, sqc_fit_out* out, char* err, size_t errlen);
+SQC_API int sqc_fit_robust(const sqc_fit_args* args, sqc_fit_out* out, char* err, size_t errlen);
+SQC_API int sqc_fit_mle   (const sqc_fit_args* args, sqc_fit_out* out, char* err, size_t errlen);
 
 /* ---- post-fit outlier arithmetic (.calc_outliers_dt, R/fit_sampleqc.R:419-453) ---------- */
 typedef struct sqc_maha_args {
@@ -137,7 +144,7 @@ typedef struct sqc_maha_args {
 } sqc_maha_args;
 
 /* maha: N x K column-major (may be NULL), outlier: N bytes 0/1, maha_cut: the chi-square cut */
-int sqc_outlier_maha(const sqc_maha_args* args, double* maha, uint8_t* outlier,
+SQC_API int sqc_outlier_maha(const sqc_maha_args* args, double* maha, uint8_t* outlier,
                      double* maha_cut, char* err, size_t errlen);
 
 /* ---- resident sessions (benchmarks, multi-GPU drivers) --------------------------------- */
@@ -172,31 +179,32 @@ typedef struct sqc_run_stats {
   int64_t mcd_csteps;                          /* lock-step C-steps executed                  */
 } sqc_run_stats;
 
-int  sqc_session_create (const sqc_fit_args* args, int variant, sqc_session** out,
+SQC_API int  sqc_session_create (const sqc_fit_args* args, int variant, sqc_session** out,
                          char* err, size_t errlen);      /* allocates + uploads (H2D)          */
-int  sqc_session_run    (sqc_session* s, char* err, size_t errlen); /* re-runnable: resets state,
+SQC_API int  sqc_session_run    (sqc_session* s, char* err, size_t errlen); /* re-runnable: resets state,
                                                              runs init + EM loop on device     */
-int  sqc_session_fetch  (sqc_session* s, sqc_fit_out* out, char* err, size_t errlen); /* D2H   */
-int  sqc_session_stats  (const sqc_session* s, sqc_run_stats* stats);
-void sqc_session_destroy(sqc_session* s);
+SQC_API int  sqc_session_fetch  (sqc_session* s, sqc_fit_out* out, char* err, size_t errlen); /* D2H   */
+SQC_API int  sqc_session_stats  (const sqc_session* s, sqc_run_stats* stats);
+SQC_API int  sqc_session_profile(sqc_session* s, int on);         /* per-launch CUDA-event timing on/off */
+SQC_API void sqc_session_destroy(sqc_session* s);
 
 /* ---- multi-GPU exchange bootstrap ------------------------------------------------------ */
 /* Each rank allocates its exchange window and exports an IPC handle; the host side gathers all
  * handles (torch.distributed / MPI / files - plumbing) and passes them in sqc_fit_args.        */
 #define SQC_IPC_HANDLE_BYTES 64
-int sqc_xchg_export(int device, void* handle_out /* SQC_IPC_HANDLE_BYTES */, char* err, size_t errlen);
-int sqc_xchg_release(int device);
+SQC_API int sqc_xchg_export(int device, void* handle_out /* SQC_IPC_HANDLE_BYTES */, char* err, size_t errlen);
+SQC_API int sqc_xchg_release(int device);
 
 /* ---- misc ------------------------------------------------------------------------------ */
-int         sqc_abi_version(void);
-int         sqc_device_count(void);          /* <0 on CUDA failure                            */
-const char* sqc_status_name(int status);
+SQC_API int         sqc_abi_version(void);
+SQC_API int         sqc_device_count(void);          /* <0 on CUDA failure                            */
+SQC_API const char* sqc_status_name(int status);
 /* device-side special functions exposed for tests: qchisq(p, df) evaluated by the same device
  * routine the MCD consistency factor uses (replaces R::qchisq, robust_cpp.cpp:102)            */
-int sqc_device_qchisq(const double* p, const double* df, double* out, int32_t n, int device,
+SQC_API int sqc_device_qchisq(const double* p, const double* df, double* out, int32_t n, int device,
                       char* err, size_t errlen);
 /* the R-compatible Mersenne-Twister key stream generated on the device (tests)               */
-int sqc_device_rkeys(uint32_t seed, int64_t skip, int32_t* keys_out, int64_t n, int device,
+SQC_API int sqc_device_rkeys(uint32_t seed, int64_t skip, int32_t* keys_out, int64_t n, int device,
                      char* err, size_t errlen);
 
 #ifdef __cplusplus

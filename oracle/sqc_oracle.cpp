@@ -110,9 +110,11 @@ inline uint64_t splitmix64(uint64_t z) {
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return z ^ (z >> 31);
 }
-inline int counter_key(uint32_t seed, uint32_t call, uint64_t cell) {
+// key of the draw with 0-based index `draw` in the fit's key stream (same position as R's stream would
+// have: call * N + cluster offset + rank inside the cluster)
+inline int counter_key(uint32_t seed, uint32_t call, uint64_t draw) {
   uint64_t m = splitmix64(((uint64_t)seed << 32) ^ (uint64_t)call);
-  uint64_t v = splitmix64(m ^ (cell * 0x9E3779B97F4A7C15ull));
+  uint64_t v = splitmix64(m ^ (draw * 0x9E3779B97F4A7C15ull));
   return (int)(v >> 33);
 }
 
@@ -343,9 +345,9 @@ void sort_dists(const std::vector<double>& d, int64_t h, std::vector<int64_t>& h
 
 struct KeySource {               // the stream behind arma::randperm (Appendix A2/A3)
   int mode; RMersenne mt; uint32_t seed; uint32_t call; int64_t draws;
-  int key(int64_t original_cell) {
-    ++draws;
-    if (mode == SQC_RNG_COUNTER) return counter_key(seed, call, (uint64_t)original_cell);
+  int key(int64_t /*original_cell*/) {
+    const int64_t draw = draws++;
+    if (mode == SQC_RNG_COUNTER) return counter_key(seed, 0u, (uint64_t)draw);
     return mt.randi_key();
   }
 };

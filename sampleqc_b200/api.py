@@ -1,0 +1,148 @@
+"""Host-side mirror of the reference's Rcpp exports for the EM path, on top of the C ABI.
+
+The names, argument order and return lists are those of the reference's R closures
+(reference R/RcppExports.R:7-16 -> src/RcppExports.cpp:16-54):
+
+    fit_sampleqc_robust_cpp(x, init_z, groups, D, J, K, N, em_iters, mcd_alpha, mcd_iters, seed, track=FALSE)
+    fit_sampleqc_mle_cpp(x, init_gamma_i, groups, D, J, K, N, n_iter, seed)
+
+plus the post-fit arithmetic of .calc_outliers_dt (reference R/fit_sampleqc.R:419-453) and the
+re-centring .fit_one_sampleqc applies to the raw outputs (R/fit_sampleqc.R:242-246).  Errors that the
+reference raises as R errors (END_RCPP) surface as SampleQCError.  Everything runs in the CUDA library.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi as A
+from ._abi import SampleQCError, SQC_RNG_COUNTER, SQC_RNG_R_COMPAT, SQC_VARIANT_MLE, SQC_VARIANT_ROBUST  # noqa: F401
+from ._lib import check, lib
+
+
+def fit_sampleqc_robust_cpp(x, init_z, groups, D, J, K, N, em_iters, mcd_alpha, mcd_iters, seed, track=False,
+                            rng_mode=SQC_RNG_R_COMPAT, device=-1):
+    """reference src/fit_sampleQC_robust_cpp.cpp:451-577; returns the Rcpp list as a dict (:562-575)."""
+    args, keep = A.make_fit_args(x, groups, D, J, K, N, em_iters, init_z=init_z, mcd_alpha=mcd_alpha,
+                                 mcd_iters=mcd_iters, seed=seed, track=track, rng_mode=rng_mode, device=device)
+    bufs = A.FitBuffers(D, J, K, N, em_iters, SQC_VARIANT_ROBUST, track)
+    err = C.create_string_buffer(512)
+    check(lib().sqc_fit_robust(C.byref(args), C.byref(bufs.out), err, 512), err)
+    return bufs.as_list()
+
+
+def fit_sampleqc_mle_cpp(x, init_gamma_i, groups, D, J, K, N, n_iter, seed, device=-1):
+    """reference src/fit_sampleQC_mle_cpp.cpp:279-357; returns the Rcpp list as a dict (:341-356)."""
+    args, keep = A.make_fit_args(x, groups, D, J, K, N, n_iter, init_gamma=init_gamma_i, seed=seed, device=device)
+    bufs = A.FitBuffers(D, J, K, N, n_iter, SQC_VARIANT_MLE)
+    err = C.create_string_buffer(512)
+    check(lib().sqc_fit_mle(C.byref(args), C.byref(bufs.out), err, 512), err)
+    return bufs.as_list()
+
+
+def recentre(fit: dict) -> dict:
+    """zero-mean re-centring of mu_0 / alpha_j / beta_k, reference R/fit_sampleqc.R:242-246."""
+    out = dict(fit)
+    a_means = fit["alpha_j"].mean(axis=0)
+    b_means = fit["beta_k"].mean(axis=0)
+    out["mu_0"] = fit["mu_0"].reshape(-1) + a_means + b_means
+    out["alpha_j"] = fit["alpha_j"] - a_means[None, :]
+    out["beta_k"] = fit["beta_k"] - b_means[None, :]
+    return out
+
+
+def calc_outliers(x, groups, mu_0, alpha_j, beta_k, sigma_k, alpha=0.01, device=-1):
+    """.calc_outliers_dt (reference R/fit_sampleqc.R:419-453): (maha N x K, outlier N bool, cut)."""
+    xa = A.f64_colmajor(x)
+    N, D = xa.shape
+    aj, bk, sk = A.f64_colmajor(alpha_j), A.f64_colmajor(beta_k), A.f64_colmajor(sigma_k)
+    J, K = aj.shape[0], bk.shape[0]
+    ga = A.as_i32(groups)
+    m0 = np.ascontiguousarray(np.asarray(mu_0, dtype=np.float64).reshape(-1))
+    a = A.SqcMahaArgs()
+    a.abi_version, a.D, a.J, a.K, a.N = A.SQC_ABI_VERSION, D, J, K, N
+    a.x, a.groups, a.mu_0, a.alpha_j, a.beta_k, a.sigma_k = A.ptr_d(xa), A.ptr_i(ga), A.ptr_d(m0), A.ptr_d(aj), A.ptr_d(bk), A.ptr_d(sk)
+    a.alpha, a.device = float(alpha), int(device)
+    maha = np.zeros((N, K), order="F")
+    out = np.zeros(N, dtype=np.uint8)
+    cut = C.c_double(0)
+    err = C.create_string_buffer(512)
+    check(lib().sqc_outlier_maha(C.byref(a), A.ptr_d(maha), out.ctypes.data_as(A.c_uint8_p), C.byref(cut), err, 512), err)
+    return maha, out.astype(bool), cut.value
+
+
+class Session:
+    """A resident fit: the cell matrix stays in HBM so the EM loop can be re-run and timed without the
+    host<->device copies (sqc_session_* in include/sampleqc_cuda.h)."""
+
+    def __init__(self, x, groups, D, J, K, N, em_iters, *, variant=SQC_VARIANT_ROBUST, init_z=None, init_gamma=None,
+                 mcd_alpha=0.5, mcd_iters=50, seed=0, track=False, rng_mode=SQC_RNG_R_COMPAT, device=-1,
+                 rank=0, world=1, cell_offset=0, N_total=None, peer_handles=None, raw_pointers=None):
+        self.D, self.J, self.K, self.N, self.em_iters = D, J, K, N, em_iters
+        self.variant, self.track = variant, track
+        args, self._keep = A.make_fit_args(x, groups, D, J, K, N, em_iters, init_z=init_z, init_gamma=init_gamma,
+                                           mcd_alpha=mcd_alpha, mcd_iters=mcd_iters, seed=seed, track=track,
+                                           rng_mode=rng_mode, device=device, rank=rank, world=world,
+                                           cell_offset=cell_offset, N_total=N_total, peer_handles=peer_handles)
+        self._h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        check(lib().sqc_session_create(C.byref(args), int(variant), C.byref(self._h), err, 512), err)
+
+    def profile(self, on=True):
+        lib().sqc_session_profile(self._h, int(on))
+
+    def run(self):
+        err = C.create_string_buffer(512)
+        check(lib().sqc_session_run(self._h, err, 512), err)
+
+    def fetch(self) -> dict:
+        bufs = A.FitBuffers(self.D, self.J, self.K, self.N, self.em_iters, self.variant, self.track)
+        err = C.create_string_buffer(512)
+        check(lib().sqc_session_fetch(self._h, C.byref(bufs.out), err, 512), err)
+        return bufs.as_list()
+
+    def stats(self) -> dict:
+        st = A.SqcRunStats()
+        lib().sqc_session_stats(self._h, C.byref(st))
+        fam = A.KERNEL_FAMILIES
+        return {
+            "n_iter": st.n_iter, "n_gpu_launches": st.n_gpu_launches, "loop_ms": st.loop_ms, "init_ms": st.init_ms,
+            "family_ms": {fam[i]: st.family_ms[i] for i in range(len(fam))},
+            "family_launches": {fam[i]: st.family_launches[i] for i in range(len(fam))},
+            "family_bytes": {fam[i]: st.family_bytes[i] for i in range(len(fam))},
+            "mcd_passes": st.mcd_passes, "mcd_csteps": st.mcd_csteps,
+        }
+
+    def close(self):
+        if self._h:
+            lib().sqc_session_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def device_qchisq(p, df, device=-1):
+    p = np.ascontiguousarray(np.asarray(p, dtype=np.float64).reshape(-1))
+    df = np.ascontiguousarray(np.broadcast_to(np.asarray(df, dtype=np.float64), p.shape).copy())
+    out = np.zeros_like(p)
+    err = C.create_string_buffer(512)
+    check(lib().sqc_device_qchisq(A.ptr_d(p), A.ptr_d(df), A.ptr_d(out), p.size, device, err, 512), err)
+    return out
+
+
+def device_rkeys(seed, skip, n, device=-1):
+    out = np.zeros(n, dtype=np.int32)
+    err = C.create_string_buffer(512)
+    check(lib().sqc_device_rkeys(seed, skip, A.ptr_i(out), n, device, err, 512), err)
+    return out

@@ -1,0 +1,224 @@
+// sqc_common.cuh — device-side building blocks shared by all kernels of libsampleqc_cuda.so.
+//
+// Data layout in HBM:
+//   x      D columns of N fp64, structure-of-arrays (R's column-major matrix as is), centred in place
+//   z      N uint8 labels
+//   tiles  sample-aligned runs of <= TILE cells; a tile never crosses a sample boundary, so the sample
+//          index (and with it alpha_j, p_j.) is uniform per tile and `groups` is never streamed
+//   rs     D columns of cluster-sorted residuals r = x - alpha_j (stable partition by label)
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#define SQC_MAXD 8
+#define SQC_MAXK 16
+#define SQC_TRI(D) ((D) * ((D) + 1) / 2)
+#define SQC_NMOM(D) (1 + (D) + SQC_TRI(D))          // count, sum, upper-triangular scatter
+
+// device-side status (mirrors include/sampleqc_cuda.h)
+#define SQC_D_OK 0
+#define SQC_D_BAD_ARG 1
+#define SQC_D_EMPTY_CLUSTER 2
+#define SQC_D_SUBSET_SIZE 3
+#define SQC_D_NOT_SPD 4
+#define SQC_D_SINGULAR 5
+#define SQC_D_NAN 6
+#define SQC_D_SELECT 7
+
+namespace sqc {
+
+// ---------------------------------------------------------------------------------------------
+// streaming loads: the cell matrix is read once per pass, keep it out of L1
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double ld_stream(const double* p) {
+  double v;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double2 ld_stream2(const double* p) {          // 128-bit, 16-byte aligned
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ unsigned ld_stream_u8(const uint8_t* p) {
+  unsigned v;
+  asm volatile("ld.global.nc.L1::no_allocate.u8 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_stream_s32(const int* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ long long warp_sum_ll(long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tiny dense linear algebra on D x D column-major matrices, run by ONE thread
+// (stand-ins for arma::det / inv / chol used at robust_cpp.cpp:19,77,91,127,153)
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline double small_det(const double* m, int n) {
+  if (n == 1) return m[0];
+  if (n == 2) return m[0] * m[3] - m[2] * m[1];
+  if (n == 3)
+    return m[0] * (m[4] * m[8] - m[7] * m[5]) - m[3] * (m[1] * m[8] - m[7] * m[2]) + m[6] * (m[1] * m[5] - m[4] * m[2]);
+  double lu[SQC_MAXD * SQC_MAXD];
+  for (int i = 0; i < n * n; ++i) lu[i] = m[i];
+  double det = 1.0;
+  for (int c = 0; c < n; ++c) {
+    int piv = c; double best = fabs(lu[c + n * c]);
+    for (int r = c + 1; r < n; ++r) if (fabs(lu[r + n * c]) > best) { best = fabs(lu[r + n * c]); piv = r; }
+    if (best == 0.0) return 0.0;
+    if (piv != c) { for (int k = 0; k < n; ++k) { double t = lu[c + n * k]; lu[c + n * k] = lu[piv + n * k]; lu[piv + n * k] = t; } det = -det; }
+    det *= lu[c + n * c];
+    for (int r = c + 1; r < n; ++r) {
+      double f = lu[r + n * c] / lu[c + n * c];
+      for (int k = c + 1; k < n; ++k) lu[r + n * k] -= f * lu[c + n * k];
+    }
+  }
+  return det;
+}
+// general inverse by Gauss-Jordan with partial pivoting; false if singular
+__host__ __device__ inline bool small_inv(const double* m, int n, double* inv) {
+  double a[SQC_MAXD * SQC_MAXD];
+  for (int i = 0; i < n * n; ++i) { a[i] = m[i]; inv[i] = 0.0; }
+  for (int i = 0; i < n; ++i) inv[i + n * i] = 1.0;
+  for (int c = 0; c < n; ++c) {
+    int piv = c; double best = fabs(a[c + n * c]);
+    for (int r = c + 1; r < n; ++r) if (fabs(a[r + n * c]) > best) { best = fabs(a[r + n * c]); piv = r; }
+    if (!(best > 0.0) || !(best < __builtin_huge_val())) return false;
+    if (piv != c) for (int k = 0; k < n; ++k) {
+      double t = a[c + n * k]; a[c + n * k] = a[piv + n * k]; a[piv + n * k] = t;
+      t = inv[c + n * k]; inv[c + n * k] = inv[piv + n * k]; inv[piv + n * k] = t;
+    }
+    double d = a[c + n * c];
+    for (int k = 0; k < n; ++k) { a[c + n * k] /= d; inv[c + n * k] /= d; }
+    for (int r = 0; r < n; ++r) if (r != c) {
+      double f = a[r + n * c];
+      if (f != 0.0) for (int k = 0; k < n; ++k) { a[r + n * k] -= f * a[c + n * k]; inv[r + n * k] -= f * inv[c + n * k]; }
+    }
+  }
+  return true;
+}
+// lower Cholesky factor L (L L' = m) and its inverse Linv (lower); false if not SPD
+__host__ __device__ inline bool small_chol_inv(const double* m, int n, double* L, double* Linv) {
+  for (int i = 0; i < n * n; ++i) { L[i] = 0.0; Linv[i] = 0.0; }
+  for (int c = 0; c < n; ++c) {
+    double s = m[c + n * c];
+    for (int k = 0; k < c; ++k) s -= L[c + n * k] * L[c + n * k];
+    if (!(s > 0.0) || !(s < __builtin_huge_val())) return false;
+    double d = sqrt(s); L[c + n * c] = d;
+    for (int r = c + 1; r < n; ++r) {
+      double t = m[r + n * c];
+      for (int k = 0; k < c; ++k) t -= L[r + n * k] * L[c + n * k];
+      L[r + n * c] = t / d;
+    }
+  }
+  // forward substitution for the inverse, column by column
+  for (int c = 0; c < n; ++c) {
+    Linv[c + n * c] = 1.0 / L[c + n * c];
+    for (int r = c + 1; r < n; ++r) {
+      double t = 0.0;
+      for (int k = c; k < r; ++k) t -= L[r + n * k] * Linv[k + n * c];
+      Linv[r + n * c] = t / L[r + n * r];
+    }
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// qchisq(p, df), integer df: replaces R::qchisq (robust_cpp.cpp:102) / stats::qchisq
+// (R/fit_sampleqc.R:429).  Half-integer-shape regularised incomplete gamma in closed form
+// (lower tail by series, upper tail by the finite erfc / Poisson sums), safeguarded Newton.
+// ---------------------------------------------------------------------------------------------
+__device__ inline double gamma_p_series(double a, double y) {         // P(a, y), positive-term series
+  if (y <= 0.0) return 0.0;
+  double term = 1.0 / a, sum = term, ap = a;
+  for (int n = 0; n < 4000; ++n) { ap += 1.0; term *= y / ap; sum += term; if (term < sum * 1e-17) break; }
+  return sum * exp(-y + a * log(y) - lgamma(a));
+}
+__device__ inline double gamma_q_halfint(int df, double y) {          // Q(df/2, y), finite positive sum
+  if (y <= 0.0) return 1.0;
+  const double ey = exp(-y);
+  if ((df & 1) == 0) {
+    double term = 1.0, sum = 1.0;
+    for (int i = 1; i < df / 2; ++i) { term *= y / i; sum += term; }
+    return ey * sum;
+  }
+  const double sy = sqrt(y);
+  double q = erfc(sy);
+  double term = ey * sy * 1.1283791670955125738961589031215;         // y^(1/2) e^-y / Gamma(3/2)
+  for (int i = 0; i < df / 2; ++i) { q += term; term *= y / (1.5 + i); }
+  return q;
+}
+__device__ inline double dev_qchisq(double p, int df) {
+  if (!(p >= 0.0) || !(p <= 1.0) || df < 1) return CUDART_NAN;
+  if (p == 0.0) return 0.0;
+  if (p == 1.0) return CUDART_INF;
+  const double a = 0.5 * df;
+  const bool upper = p > 0.5;
+  const double target = upper ? 1.0 - p : p;
+  const double lg = lgamma(a);
+  // Wilson-Hilferty start
+  double zq = normcdfinv(p), c = 2.0 / (9.0 * df);
+  double w = 1.0 - c + zq * sqrt(c);
+  double y = 0.5 * df * w * w * w;
+  if (!(y > 1e-300)) y = 0.5 * exp((log(p) + lg + log(a)) / a);      // tiny-p asymptote P ~ y^a / Gamma(a+1)
+  double lo = 0.0, hi = CUDART_INF;
+  for (int it = 0; it < 100; ++it) {
+    double f = upper ? (target - gamma_q_halfint(df, y)) : (gamma_p_series(a, y) - target);
+    if (f > 0) hi = y; else lo = y;
+    double pdf = exp(-y + (a - 1.0) * log(y) - lg);
+    double yn = (pdf > 0.0) ? y - f / pdf : y;
+    if (!(yn > lo) || !(yn < hi)) yn = (hi < CUDART_INF) ? 0.5 * (lo + hi) : 2.0 * y + 1.0;
+    if (fabs(yn - y) <= 4e-16 * fabs(yn)) { y = yn; break; }
+    y = yn;
+  }
+  return 2.0 * y;
+}
+
+// ---------------------------------------------------------------------------------------------
+// random keys for the FastMCD start (arma::randperm, robust_cpp.cpp:72)
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ inline uint64_t splitmix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__host__ __device__ inline int counter_key(uint64_t call_mix, uint64_t cell) {
+  uint64_t v = splitmix64(call_mix ^ (cell * 0x9E3779B97F4A7C15ull));
+  return (int)(v >> 33);
+}
+__host__ __device__ inline uint64_t counter_call_mix(uint32_t seed, uint32_t call) {
+  return splitmix64(((uint64_t)seed << 32) ^ (uint64_t)call);
+}
+// Mersenne-Twister output word -> randperm key:  (int) Rf_runif(0, RAND_MAX) after R's fixup()
+__device__ __forceinline__ int mt_word_to_key(uint32_t y) {
+  y ^= (y >> 11);
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= (y >> 18);
+  double u = (double)y * 2.3283064365386963e-10;
+  const double i2_32m1 = 2.328306437080797e-10;
+  if (u <= 0.0) u = 0.5 * i2_32m1;
+  if ((1.0 - u) <= 0.0) u = 1.0 - 0.5 * i2_32m1;
+  return (int)(2147483647.0 * u);
+}
+
+}  // namespace sqc

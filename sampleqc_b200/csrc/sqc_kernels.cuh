@@ -1,0 +1,549 @@
+// sqc_kernels.cuh — sm_100a kernels of the robust multi-sample GMM EM (reference
+// src/fit_sampleQC_robust_cpp.cpp) and the shared streaming machinery.
+//
+// Kernel families (SQC_KF_* in include/sampleqc_cuda.h):
+//   k_estep       E-step pass  (calc_log_likelihood :400-432 + calc_expected_z :344-396 + the (j,k)
+//                 sufficient statistics that update_alpha_j :116-157 / update_p_jk :322-341 need)
+//   k_partition   like_1 pass + stable partition of residuals x - alpha_j by label
+//                 (restrict_to_x_k :265-283 for all k in one pass)
+//   k_mcd         persistent cooperative kernel: the whole update_beta_scale_k :289-318 /
+//                 fast_mcd :55-108 for all clusters in lock step — exact order-statistic selection by
+//                 histogram + candidate resolution instead of arma::sort_index, masked moments
+//   k_* (update)  alpha_j solves, p_jk, statistics reduction, control
+//   k_mt_keys     R's Mersenne-Twister stream -> randperm keys
+#pragma once
+#include <cooperative_groups.h>
+
+#include "sqc_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace sqc {
+
+constexpr int EST_THREADS = 256;     // E-step / partition CTAs: one sample-aligned tile each
+// cells per thread of a tile, by dimension (register budget)
+template <int D> struct TileCfg { static constexpr int CPT = (D <= 4) ? 4 : 2; static constexpr int TILE = EST_THREADS * CPT; };
+
+struct Control {
+  int iter;          // EM iterations completed
+  int z_delta;       // labels changed by the last E-step (robust_cpp.cpp:519)
+  int cont;          // loop condition (:490)
+  int status;        // SQC_D_*
+  int n_zero;        // n_zeros counter (:380-382)
+  int mcd_hit;       // fast_mcd reached mcd_iters (:94-95)
+  int mcd_call;      // update_beta_scale_k calls so far (RNG stream position = call * N_total)
+  int pad;
+  long long mcd_passes, mcd_csteps;
+};
+
+// everything a kernel needs, passed by value
+struct Dev {
+  int D, J, K, T;             // T = number of tiles
+  long long N;                // local cells
+  long long N_total;
+  long long cell_offset;
+  // data
+  double* x; uint8_t* z;
+  const int* tile_start; const int* tile_len; const int* tile_sample; const int* sample_tile_begin; const int* sample_n;
+  // parameters
+  double* mu0; double* alpha; double* beta; double* sigma; double* linv; double* ainv; double* logP; double* Pk;
+  double* p_jk; double* logp_jk;
+  // tile partials / reduced statistics
+  double* t_ll1; double* t_ll2; int* t_nk; double* t_sk; int* t_base; double* t_col;
+  int* n_jk; double* s_jk;
+  long long* clu_n; long long* clu_off;        // local cells per cluster, segment offsets in rs
+  long long* clu_n_glob; long long* clu_prefix; // cells per cluster over all shards; key-stream offset of the local segment
+  // cluster-sorted residuals
+  double* rs; long long rs_stride;
+  // outputs / control
+  double* like1; double* like2; Control* ctl;
+  double* track_alpha; double* track_beta; double* track_sigma; double* track_p;
+  // fit parameters
+  int em_iters, mcd_iters, rng_mode, track; double mcd_alpha; unsigned int seed;
+};
+
+// ---------------------------------------------------------------------------------------------
+// block-level helpers
+// ---------------------------------------------------------------------------------------------
+template <int NT> __device__ __forceinline__ double block_sum(double v, double* sh /* NT/32 */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0) for (int i = 0; i < NT / 32; ++i) r += sh[i];     // fixed order: deterministic
+  return r;                                                                // valid in thread 0
+}
+// exclusive scan of one long long per thread; returns the exclusive prefix, *total = block sum (all threads)
+template <int NT> __device__ __forceinline__ long long block_excl_scan(long long v, long long* sh /* NT/32 + 1 */, long long* total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  long long inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  __syncthreads();
+  if (lane == 31) sh[w] = inc;
+  __syncthreads();
+  if (threadIdx.x == 0) { long long run = 0; for (int i = 0; i < NT / 32; ++i) { long long t = sh[i]; sh[i] = run; run += t; } sh[NT / 32] = run; }
+  __syncthreads();
+  *total = sh[NT / 32];
+  return sh[w] + inc - v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-(tile, component) density constants staged in shared memory
+//   mean = alpha_j + beta_k (the reference forms mu_ik first: robust_cpp.cpp:363,423), inverse Cholesky
+//   rows, log p_jk, log-normaliser, p_jk, normaliser  (RcppDist::dmvnorm)
+// ---------------------------------------------------------------------------------------------
+template <int D> struct ParK { static constexpr int SZ = D + SQC_TRI(D) + 4; };
+
+template <int D> __device__ __forceinline__ void stage_params(const Dev& s, int j, double* sh /* K * SZ */) {
+  constexpr int SZ = ParK<D>::SZ;
+  for (int idx = threadIdx.x; idx < s.K * SZ; idx += blockDim.x) {
+    const int k = idx / SZ, e = idx % SZ;
+    double v;
+    if (e < D) v = s.alpha[j * D + e] + s.beta[k * D + e];
+    else if (e < D + SQC_TRI(D)) {
+      int t = e - D, r = 0;
+      while ((r + 1) * (r + 2) / 2 <= t) ++r;
+      int c = t - r * (r + 1) / 2;
+      v = s.linv[k * D * D + r + D * c];
+    } else if (e == D + SQC_TRI(D)) v = s.logp_jk[j * s.K + k];
+    else if (e == D + SQC_TRI(D) + 1) v = s.logP[k];
+    else if (e == D + SQC_TRI(D) + 2) v = s.p_jk[j * s.K + k];
+    else v = s.Pk[k];
+    sh[idx] = v;
+  }
+}
+// squared Mahalanobis norm |Linv v|^2 with Linv packed lower-triangular row-major
+template <int D> __device__ __forceinline__ double maha_tri(const double (&v)[D], const double* lt) {
+  double q = 0.0;
+#pragma unroll
+  for (int r = 0; r < D; ++r) {
+    double y = 0.0;
+#pragma unroll
+    for (int c = 0; c <= r; ++c) y = fma(lt[r * (r + 1) / 2 + c], v[c], y);
+    q = fma(y, y, q);
+  }
+  return q;
+}
+
+// ---------------------------------------------------------------------------------------------
+// E-step pass.  One CTA per sample-aligned tile.
+//   MODE 0: like_2 + new labels + z_delta + statistics of the NEW labels   (:506, :509, :519)
+//   MODE 1: statistics of the current labels only (initial labelling)
+// Statistics per tile: n_k (int) and sum_k x (D doubles) -> reduced per sample by k_post_stats.
+// ---------------------------------------------------------------------------------------------
+template <int D, int MODE>
+__global__ void __launch_bounds__(EST_THREADS) k_estep(Dev s) {
+  constexpr int CPT = TileCfg<D>::CPT, SZ = ParK<D>::SZ, NW = EST_THREADS / 32;
+  extern __shared__ double sh_dyn[];
+  double* sh_par = sh_dyn;                                   // K * SZ
+  double* sh_red = sh_par + s.K * SZ;                        // NW * K * (D + 1)
+  __shared__ double sh_w[NW];
+  __shared__ int sh_i[NW * 2];
+  if (!s.ctl->cont) return;
+  const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int j = s.tile_sample[t], start = s.tile_start[t], len = s.tile_len[t];
+  if (MODE == 0) stage_params<D>(s, j, sh_par);
+  double xv[CPT][D]; int zo[CPT]; bool valid[CPT];
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) {
+    const int i = c * EST_THREADS + tid;
+    valid[c] = i < len;
+    const long long gi = (long long)start + (valid[c] ? i : 0);
+#pragma unroll
+    for (int d = 0; d < D; ++d) xv[c][d] = ld_stream(s.x + (long long)d * s.N + gi);
+    zo[c] = (int)ld_stream_u8(s.z + gi);
+  }
+  int zn[CPT];
+  double ll = 0.0; int delta = 0, nzero = 0;
+  if (MODE == 0) {
+    __syncthreads();
+    double best[CPT], like[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) { best[c] = -CUDART_INF; like[c] = 0.0; zn[c] = 0; }
+    for (int k = 0; k < s.K; ++k) {
+      const double* pk = sh_par + k * SZ;
+      double m[D], lt[SQC_TRI(D)];
+#pragma unroll
+      for (int d = 0; d < D; ++d) m[d] = pk[d];
+#pragma unroll
+      for (int e = 0; e < SQC_TRI(D); ++e) lt[e] = pk[D + e];
+      const double logp = pk[D + SQC_TRI(D)], logP = pk[D + SQC_TRI(D) + 1], p = pk[D + SQC_TRI(D) + 2], P = pk[D + SQC_TRI(D) + 3];
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        double v[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) v[d] = xv[c][d] - m[d];
+        const double q = maha_tri<D>(v, lt);
+        const double l = logp + (logP - 0.5 * q);            // log(p_jk) + dmvnorm(log=TRUE), :364
+        if (l > best[c]) { best[c] = l; zn[c] = k; }         // strict >, first max, :375-378
+        if (valid[c] && best[c] == -CUDART_INF) ++nzero;     // :380-382
+        like[c] += p * (P * exp(-0.5 * q));                  // p_jk * dmvnorm(log=FALSE), :424
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) if (valid[c]) {
+      ll += log(like[c]);                                    // :428
+      delta += (zn[c] != zo[c]);
+      s.z[(long long)start + c * EST_THREADS + tid] = (uint8_t)zn[c];
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) zn[c] = zo[c];
+  }
+  // statistics of the labels zn: per component count and sum of x, reduced over the tile
+  for (int k = 0; k < s.K; ++k) {
+    int cnt = 0; double sx[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) sx[d] = 0.0;
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const bool in = valid[c] && zn[c] == k;
+      cnt += in;
+#pragma unroll
+      for (int d = 0; d < D; ++d) sx[d] += in ? xv[c][d] : 0.0;
+    }
+    cnt = warp_sum_i(cnt);
+#pragma unroll
+    for (int d = 0; d < D; ++d) sx[d] = warp_sum(sx[d]);
+    if (lane == 0) {
+      double* r = sh_red + (w * s.K + k) * (D + 1);
+      r[0] = (double)cnt;
+#pragma unroll
+      for (int d = 0; d < D; ++d) r[1 + d] = sx[d];
+    }
+  }
+  ll = warp_sum(ll); delta = warp_sum_i(delta); nzero = warp_sum_i(nzero);
+  if (lane == 0) { sh_w[w] = ll; sh_i[w] = delta; sh_i[NW + w] = nzero; }
+  __syncthreads();
+  for (int idx = tid; idx < s.K * (D + 1); idx += EST_THREADS) {
+    const int k = idx / (D + 1), e = idx % (D + 1);
+    double acc = 0.0;
+#pragma unroll
+    for (int ww = 0; ww < NW; ++ww) acc += sh_red[(ww * s.K + k) * (D + 1) + e];
+    if (e == 0) s.t_nk[t * s.K + k] = (int)acc;
+    else s.t_sk[((long long)t * s.K + k) * D + (e - 1)] = acc;
+  }
+  if (MODE == 0 && tid == 0) {
+    double a = 0.0; int dl = 0, nz = 0;
+#pragma unroll
+    for (int ww = 0; ww < NW; ++ww) { a += sh_w[ww]; dl += sh_i[ww]; nz += sh_i[NW + ww]; }
+    s.t_ll2[t] = a;
+    if (dl) atomicAdd(&s.ctl->z_delta, dl);
+    if (nz) atomicAdd(&s.ctl->n_zero, nz);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// like_1 + stable partition by label.  One CTA per tile.
+//   r_i = x_i - alpha_{j}  written to rs[d][clu_off[z] + t_base[tile][z] + rank in tile]
+//   (restrict_to_x_k :265-283 keeps original cell order inside each cluster; so does this).
+//   LIKE = 1: also the log-likelihood with the new alpha_j and the previous beta/Sigma/p_jk (:499).
+// ---------------------------------------------------------------------------------------------
+template <int D, int LIKE>
+__global__ void __launch_bounds__(EST_THREADS) k_partition(Dev s) {
+  constexpr int CPT = TileCfg<D>::CPT, SZ = ParK<D>::SZ, NW = EST_THREADS / 32;
+  extern __shared__ double sh_dyn[];
+  double* sh_par = sh_dyn;                                   // K * SZ
+  int* sh_cnt = (int*)(sh_par + s.K * SZ);                   // CPT * NW * K exclusive prefixes
+  __shared__ double sh_w[NW];
+  if (!s.ctl->cont) return;
+  const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int j = s.tile_sample[t], start = s.tile_start[t], len = s.tile_len[t];
+  if (LIKE) stage_params<D>(s, j, sh_par);
+  double xv[CPT][D]; int zo[CPT]; bool valid[CPT];
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) {
+    const int i = c * EST_THREADS + tid;
+    valid[c] = i < len;
+    const long long gi = (long long)start + (valid[c] ? i : 0);
+#pragma unroll
+    for (int d = 0; d < D; ++d) xv[c][d] = ld_stream(s.x + (long long)d * s.N + gi);
+    zo[c] = valid[c] ? (int)ld_stream_u8(s.z + gi) : -1;
+  }
+  // per (iteration c, warp, component) counts -> exclusive prefix in tile order (c, warp, lane)
+  int myrank[CPT];
+  for (int k = 0; k < s.K; ++k) {
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const unsigned b = __ballot_sync(0xffffffffu, zo[c] == k);
+      if (zo[c] == k) myrank[c] = __popc(b & ((1u << lane) - 1u));
+      if (lane == 0) sh_cnt[(c * NW + w) * s.K + k] = __popc(b);
+    }
+  }
+  __syncthreads();
+  if (tid < s.K) {                                           // tiny serial scan per component
+    int run = s.t_base[t * s.K + tid];
+    for (int e = 0; e < CPT * NW; ++e) { int v = sh_cnt[e * s.K + tid]; sh_cnt[e * s.K + tid] = run; run += v; }
+  }
+  __syncthreads();
+  double aj[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) aj[d] = s.alpha[j * D + d];
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) if (valid[c]) {
+    const long long pos = s.clu_off[zo[c]] + sh_cnt[(c * NW + w) * s.K + zo[c]] + myrank[c];
+#pragma unroll
+    for (int d = 0; d < D; ++d) s.rs[(long long)d * s.rs_stride + pos] = xv[c][d] - aj[d];   // :274
+  }
+  if (LIKE) {
+    double like[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) like[c] = 0.0;
+    for (int k = 0; k < s.K; ++k) {
+      const double* pk = sh_par + k * SZ;
+      double m[D], lt[SQC_TRI(D)];
+#pragma unroll
+      for (int d = 0; d < D; ++d) m[d] = pk[d];
+#pragma unroll
+      for (int e = 0; e < SQC_TRI(D); ++e) lt[e] = pk[D + e];
+      const double p = pk[D + SQC_TRI(D) + 2], P = pk[D + SQC_TRI(D) + 3];
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        double v[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) v[d] = xv[c][d] - m[d];
+        like[c] += p * (P * exp(-0.5 * maha_tri<D>(v, lt)));
+      }
+    }
+    double ll = 0.0;
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) if (valid[c]) ll += log(like[c]);
+    ll = warp_sum(ll);
+    if (lane == 0) sh_w[w] = ll;
+    __syncthreads();
+    if (tid == 0) { double a = 0.0; for (int ww = 0; ww < NW; ++ww) a += sh_w[ww]; s.t_ll1[t] = a; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// initialisation passes: column sums (arma::mean :478), centring (centre_x helpers.cpp:105-115)
+// fused with the per-sample sums of the centred data (init_alpha_j helpers.cpp:117-140)
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(EST_THREADS) k_colsum(Dev s) {
+  constexpr int CPT = TileCfg<D>::CPT, NW = EST_THREADS / 32;
+  __shared__ double sh[NW * D];
+  const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int start = s.tile_start[t], len = s.tile_len[t];
+  double acc[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) acc[d] = 0.0;
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) {
+    const int i = c * EST_THREADS + tid;
+    if (i < len) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) acc[d] += ld_stream(s.x + (long long)d * s.N + start + i);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d) { acc[d] = warp_sum(acc[d]); if (lane == 0) sh[w * D + d] = acc[d]; }
+  __syncthreads();
+  if (tid < D) { double a = 0.0; for (int ww = 0; ww < NW; ++ww) a += sh[ww * D + tid]; s.t_col[(long long)t * D + tid] = a; }
+}
+// mu0[d] = sum over tiles (fixed order) / N_total ; single block
+__global__ void __launch_bounds__(1024) k_colmean(Dev s) {
+  __shared__ double sh[32];
+  for (int d = 0; d < s.D; ++d) {
+    double a = 0.0;
+    for (int t = threadIdx.x; t < s.T; t += 1024) a += s.t_col[(long long)t * s.D + d];
+    double r = block_sum<1024>(a, sh);
+    if (threadIdx.x == 0) s.mu0[d] = r;       // sum; divided after the (optional) cross-GPU reduction
+    __syncthreads();
+  }
+}
+__global__ void k_colmean_finish(Dev s) { if (threadIdx.x < s.D) s.mu0[threadIdx.x] /= (double)s.N_total; }
+
+template <int D>
+__global__ void __launch_bounds__(EST_THREADS) k_centre(Dev s) {
+  constexpr int CPT = TileCfg<D>::CPT, NW = EST_THREADS / 32;
+  __shared__ double sh[NW * D];
+  const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int start = s.tile_start[t], len = s.tile_len[t];
+  double acc[D], mu[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) { acc[d] = 0.0; mu[d] = s.mu0[d]; }
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) {
+    const int i = c * EST_THREADS + tid;
+    if (i < len) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        double* p = s.x + (long long)d * s.N + start + i;
+        const double v = *p - mu[d];
+        *p = v; acc[d] += v;
+      }
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d) { acc[d] = warp_sum(acc[d]); if (lane == 0) sh[w * D + d] = acc[d]; }
+  __syncthreads();
+  if (tid < D) { double a = 0.0; for (int ww = 0; ww < NW; ++ww) a += sh[ww * D + tid]; s.t_col[(long long)t * D + tid] = a; }
+}
+// alpha_j = per-sample mean of the centred data; one warp per sample
+__global__ void k_init_alpha(Dev s) {
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (j >= s.J) return;
+  if (lane < s.D) {
+    double a = 0.0;
+    for (int t = s.sample_tile_begin[j]; t < s.sample_tile_begin[j + 1]; ++t) a += s.t_col[(long long)t * s.D + lane];
+    s.alpha[j * s.D + lane] = a / (double)s.sample_n[j];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// statistics reduction after an E-step / stats pass:
+//   blocks 0 .. : one warp per sample sums its tiles' partials -> n_jk, s_jk
+//   last block  : per-component exclusive scan of tile counts (partition bases), cluster sizes/offsets
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_post_stats(Dev s, int n_sample_blocks) {
+  __shared__ long long sh_scan[33];
+  if (!s.ctl->cont) return;
+  const int tid = threadIdx.x, lane = tid & 31;
+  if ((int)blockIdx.x < n_sample_blocks) {
+    const int j = blockIdx.x * 32 + (tid >> 5);
+    if (j >= s.J) return;
+    const int t0 = s.sample_tile_begin[j], t1 = s.sample_tile_begin[j + 1];
+    const int ne = s.K * (s.D + 1);
+    for (int e = lane; e < ne; e += 32) {
+      const int k = e / (s.D + 1), c = e % (s.D + 1);
+      if (c == 0) { int a = 0; for (int t = t0; t < t1; ++t) a += s.t_nk[t * s.K + k]; s.n_jk[j * s.K + k] = a; }
+      else { double a = 0.0; for (int t = t0; t < t1; ++t) a += s.t_sk[((long long)t * s.K + k) * s.D + (c - 1)]; s.s_jk[((long long)j * s.K + k) * s.D + (c - 1)] = a; }
+    }
+    return;
+  }
+  const int per = (s.T + 1023) / 1024;
+  const int b0 = min(tid * per, s.T), b1 = min(b0 + per, s.T);
+  long long off_run = 0;
+  for (int k = 0; k < s.K; ++k) {
+    long long mine = 0;
+    for (int t = b0; t < b1; ++t) mine += s.t_nk[t * s.K + k];
+    long long total;
+    long long run = block_excl_scan<1024>(mine, sh_scan, &total);
+    for (int t = b0; t < b1; ++t) { s.t_base[t * s.K + k] = (int)run; run += s.t_nk[t * s.K + k]; }
+    if (tid == 0) { s.clu_n[k] = total; s.clu_off[k] = off_run; }
+    off_run += (total + 31) & ~31ll;        // 256-byte aligned cluster segments
+    __syncthreads();
+  }
+  // single GPU: the key stream of one update_beta_scale_k call runs over the clusters in order
+  // (SURVEY Appendix A3); the multi-GPU exchange overwrites these with the global values
+  if (tid == 0) { long long run = 0; for (int k = 0; k < s.K; ++k) { s.clu_n_glob[k] = s.clu_n[k]; s.clu_prefix[k] = run; run += s.clu_n[k]; } }
+}
+
+// alpha_j from the (j,k) statistics: update_alpha_j :116-157 with the per-cell sums factored out
+//   denom_j = sum_k n_jk A_k,  numer_j = sum_k A_k (s_jk - n_jk beta_k),  alpha_j = inv(denom_j) numer_j
+__global__ void k_update_alpha(Dev s) {
+  if (!s.ctl->cont) return;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= s.J) return;
+  const int D = s.D, K = s.K;
+  double denom[SQC_MAXD * SQC_MAXD], numer[SQC_MAXD], inv[SQC_MAXD * SQC_MAXD];
+  for (int e = 0; e < D * D; ++e) denom[e] = 0.0;
+  for (int d = 0; d < D; ++d) numer[d] = 0.0;
+  for (int k = 0; k < K; ++k) {
+    const double n = (double)s.n_jk[j * K + k];
+    const double* A = s.ainv + k * D * D;
+    double v[SQC_MAXD];
+    for (int d = 0; d < D; ++d) v[d] = s.s_jk[((long long)j * K + k) * D + d] - n * s.beta[k * D + d];
+    for (int r = 0; r < D; ++r) { double a = 0.0; for (int c = 0; c < D; ++c) a += A[r + D * c] * v[c]; numer[r] += a; }
+    for (int e = 0; e < D * D; ++e) denom[e] += n * A[e];
+  }
+  if (!small_inv(denom, D, inv)) { atomicCAS(&s.ctl->status, 0, SQC_D_SINGULAR); return; }   // arma::inv throws, :153
+  for (int r = 0; r < D; ++r) { double a = 0.0; for (int c = 0; c < D; ++c) a += inv[r + D * c] * numer[c]; s.alpha[j * D + r] = a; }
+}
+// p_jk = (1 + n_jk) / (K + n_j), update_p_jk :322-341
+__global__ void k_update_p(Dev s) {
+  if (!s.ctl->cont) return;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= s.J) return;
+  long long nj = s.K;
+  for (int k = 0; k < s.K; ++k) nj += s.n_jk[j * s.K + k];
+  for (int k = 0; k < s.K; ++k) {
+    const double p = (1.0 + (double)s.n_jk[j * s.K + k]) / (double)nj;
+    s.p_jk[j * s.K + k] = p; s.logp_jk[j * s.K + k] = log(p);
+  }
+}
+
+// end-of-iteration bookkeeping (:499,:506,:511-521): deterministic sums of the tile log-likelihoods,
+// loop condition, optional tracking.  single block.
+__global__ void __launch_bounds__(1024) k_em_control(Dev s) {
+  __shared__ double sh[32];
+  Control* c = s.ctl;
+  if (!c->cont) return;
+  const int it = c->iter;
+  double a1 = 0.0, a2 = 0.0;
+  for (int t = threadIdx.x; t < s.T; t += 1024) { a1 += s.t_ll1[t]; a2 += s.t_ll2[t]; }
+  double r1 = block_sum<1024>(a1, sh);
+  double r2 = block_sum<1024>(a2, sh);
+  if (s.track && it < s.em_iters) {
+    for (int e = threadIdx.x; e < s.J * s.D; e += 1024) { int j = e / s.D, d = e % s.D; s.track_alpha[(long long)it * s.J * s.D + j + s.J * d] = s.alpha[e]; }
+    for (int e = threadIdx.x; e < s.K * s.D; e += 1024) { int k = e / s.D, d = e % s.D; s.track_beta[(long long)it * s.K * s.D + k + s.K * d] = s.beta[e]; }
+    for (int e = threadIdx.x; e < s.K * s.D * s.D; e += 1024) s.track_sigma[(long long)it * s.K * s.D * s.D + e] = s.sigma[e];
+    for (int e = threadIdx.x; e < s.J * s.K; e += 1024) { int j = e / s.K, k = e % s.K; s.track_p[(long long)it * s.J * s.K + j + s.J * k] = s.p_jk[e]; }
+  }
+  if (threadIdx.x == 0) {
+    // multi-GPU: like sums and z_delta are made global by the host-side exchange before this kernel
+    s.like1[it] = r1; s.like2[it] = r2;
+    c->iter = it + 1;
+    __threadfence();
+    c->cont = (c->z_delta > 0) && (it + 1 < s.em_iters) && (c->status == 0);    // :490
+    c->z_delta = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// R's Mersenne-Twister on one CTA: 227-wide wavefronts of the recurrence,
+// ping-pong state in shared memory.  st = 624 state words + position.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mt_twist(uint32_t a, uint32_t b) {
+  uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+  return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+__global__ void __launch_bounds__(256) k_mt_keys(uint32_t* st, int* out, long long n, long long skip, const Control* ctl) {
+  __shared__ uint32_t bufA[624], bufB[624];
+  if (ctl && !ctl->cont) return;
+  uint32_t* cur = bufA; uint32_t* nxt = bufB;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 624; i += 256) cur[i] = st[i];
+  int mti = (int)st[624];
+  __syncthreads();
+  long long produced = -skip;          // skip draws first (tests)
+  while (produced < n) {
+    if (mti >= 624) {
+      if (tid < 227) nxt[tid] = cur[tid + 397] ^ mt_twist(cur[tid], cur[tid + 1]);
+      __syncthreads();
+      if (tid < 227) nxt[227 + tid] = nxt[tid] ^ mt_twist(cur[227 + tid], cur[228 + tid]);
+      __syncthreads();
+      if (tid < 169) nxt[454 + tid] = nxt[227 + tid] ^ mt_twist(cur[454 + tid], cur[455 + tid]);
+      if (tid == 169) nxt[623] = nxt[396] ^ mt_twist(cur[623], nxt[0]);
+      __syncthreads();
+      uint32_t* tmp = cur; cur = nxt; nxt = tmp;
+      mti = 0;
+    }
+    const long long room = n - produced;
+    const int m = (int)((room < (long long)(624 - mti)) ? room : (long long)(624 - mti));
+    for (int i = tid; i < m; i += 256) {
+      const long long o = produced + i;
+      if (o >= 0) out[o] = mt_word_to_key(cur[mti + i]);
+    }
+    produced += m; mti += m;
+  }
+  __syncthreads();
+  for (int i = tid; i < 624; i += 256) st[i] = cur[i];
+  if (tid == 0) st[624] = (uint32_t)mti;
+}
+// R set.seed(seed) state initialisation (Appendix A1)
+__global__ void k_mt_seed(uint32_t* st, uint32_t seed) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    uint32_t v = seed;
+    for (int j = 0; j < 50; ++j) v = 69069u * v + 1u;
+    v = 69069u * v + 1u;                        // i_seed[0] (overwritten by mti = 624)
+    for (int j = 0; j < 624; ++j) { v = 69069u * v + 1u; st[j] = v; }
+    st[624] = 624u;
+  }
+}
+
+}  // namespace sqc

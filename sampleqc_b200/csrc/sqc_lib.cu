@@ -1,0 +1,715 @@
+// sqc_lib.cu — host side of libsampleqc_cuda.so: the C ABI of include/sampleqc_cuda.h.
+//
+// Replaces the bodies of fit_sampleqc_robust_cpp (reference src/fit_sampleQC_robust_cpp.cpp:451-577)
+// and fit_sampleqc_mle_cpp (src/fit_sampleQC_mle_cpp.cpp:279-357).  The host only validates, lays the
+// data out in HBM, enqueues the whole EM (every kernel is predicated on the device-side loop flag, so
+// nothing returns to the host until convergence) and copies the results back.  There is no CPU
+// fallback: without a CUDA device every compute entry point returns SQC_ERR_CUDA.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/sampleqc_cuda.h"
+#include "sqc_mcd.cuh"
+#include "sqc_mle.cuh"
+#include "sqc_xchg.cuh"
+
+#ifndef SQC_FOR_D
+#define SQC_FOR_D(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
+#endif
+
+using namespace sqc;
+
+namespace {
+
+struct SqcFail {
+  int code; std::string msg;
+};
+[[noreturn]] void fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  throw SqcFail{code, buf};
+}
+#define CK(call)                                                                                   \
+  do {                                                                                             \
+    cudaError_t e_ = (call);                                                                       \
+    if (e_ != cudaSuccess)                                                                         \
+      fail(e_ == cudaErrorMemoryAllocation ? SQC_ERR_NOMEM : SQC_ERR_CUDA, "CUDA: %s (%s) at %s:%d", \
+           cudaGetErrorString(e_), #call, __FILE__, __LINE__);                                     \
+  } while (0)
+
+const char* device_status_message(int st) {
+  switch (st) {
+    case SQC_ERR_BAD_ARG: return "'mcd_alpha' must be between 0 and 1";
+    case SQC_ERR_EMPTY_CLUSTER: return "empty cluster: x_k.rows(0, -1) out of bounds (robust_cpp.cpp:307)";
+    case SQC_ERR_SUBSET_SIZE: return "randperm(): 'M' must be less than or equal to 'N' (h-subset size out of range, robust_cpp.cpp:72)";
+    case SQC_ERR_NOT_SPD: return "chol(): decomposition failed (robust_cpp.cpp:19)";
+    case SQC_ERR_SINGULAR: return "inv(): matrix is singular";
+    case SQC_ERR_NAN: return "sort_index(): detected NaN (robust_cpp.cpp:50)";
+    case SQC_ERR_SELECT: return "exact selection could not be resolved (too many exactly tied distances)";
+    default: return "device error";
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// small kernels that only the host driver needs
+// ---------------------------------------------------------------------------------------------
+__global__ void k_ctl_reset(Dev s) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    Control* c = s.ctl;
+    c->iter = 0; c->z_delta = 0; c->cont = 1; c->status = 0; c->n_zero = 0; c->mcd_hit = 0; c->mcd_call = 0; c->pad = 0;
+    c->mcd_passes = 0; c->mcd_csteps = 0;
+  }
+}
+__global__ void k_ctl_start_loop(Dev s) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { Control* c = s.ctl; c->cont = (s.em_iters > 0) && (c->status == 0); c->z_delta = 0; }
+}
+// derived per-component constants after an M-step: inverse Cholesky factor, inverse, normalisers
+// (what RcppDist::dmvnorm recomputes on every call — SURVEY Appendix A4 — hoisted)
+__global__ void k_derive(Dev s) {
+  if (!s.ctl->cont) return;
+  const int k = threadIdx.x, D = s.D;
+  if (k >= s.K) return;
+  const double* S = s.sigma + k * D * D;
+  double L[SQC_MAXD * SQC_MAXD], Li[SQC_MAXD * SQC_MAXD], Ai[SQC_MAXD * SQC_MAXD];
+  const bool ok1 = small_inv(S, D, Ai);
+  const bool ok2 = small_chol_inv(S, D, L, Li);
+  if (!ok1) { atomicCAS(&s.ctl->status, 0, SQC_D_SINGULAR); return; }
+  if (!ok2) { atomicCAS(&s.ctl->status, 0, SQC_D_NOT_SPD); return; }
+  const double det = small_det(S, D);
+  for (int e = 0; e < D * D; ++e) { s.linv[k * D * D + e] = Li[e]; s.ainv[k * D * D + e] = Ai[e]; }
+  s.logP[k] = -1.0 * (D / 2.0) * 1.837877066409345483560659472811 - 0.5 * log(det);
+  s.Pk[k] = 1.0 / sqrt(pow(6.283185307179586476925286766559, (double)D) * det);
+}
+// final relabel by ascending beta_k[,0] (robust_cpp.cpp:527-531, reorder_z :434-445) and packing of
+// every output into the column-major shapes of the Rcpp list
+struct OutPtrs { double* mu0; double* alpha; double* beta; double* sigma; double* p_jk; int* z; int* korder; };
+__global__ void k_order_components(Dev s, OutPtrs o) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int idx[SQC_MAXK];
+    for (int k = 0; k < s.K; ++k) idx[k] = k;
+    for (int a = 1; a < s.K; ++a) {             // stable insertion sort (ties: lower index first)
+      int v = idx[a], b = a - 1;
+      while (b >= 0 && s.beta[idx[b] * s.D] > s.beta[v * s.D]) { idx[b + 1] = idx[b]; --b; }
+      idx[b + 1] = v;
+    }
+    for (int k = 0; k < s.K; ++k) o.korder[k] = idx[k];
+    for (int k = 0; k < s.K; ++k) o.korder[SQC_MAXK + idx[k]] = k;     // inverse map
+  }
+}
+__global__ void k_pack_outputs(Dev s, OutPtrs o, int zero_z) {
+  const int D = s.D, J = s.J, K = s.K;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x, gsz = (long long)gridDim.x * blockDim.x;
+  for (long long e = gid; e < (long long)J * D; e += gsz) { int j = (int)(e / D), d = (int)(e % D); o.alpha[j + (long long)J * d] = s.alpha[e]; }
+  for (long long e = gid; e < (long long)K * D; e += gsz) { int k = (int)(e / D), d = (int)(e % D); o.beta[k + K * d] = s.beta[o.korder[k] * D + d]; }
+  for (long long e = gid; e < (long long)K * D * D; e += gsz) { int k = (int)(e / (D * D)), r = (int)(e % (D * D)); o.sigma[e] = s.sigma[o.korder[k] * D * D + r]; }
+  for (long long e = gid; e < (long long)J * K; e += gsz) { int j = (int)(e / K), k = (int)(e % K); o.p_jk[j + (long long)J * k] = s.p_jk[j * K + o.korder[k]]; }
+  for (long long e = gid; e < D; e += gsz) o.mu0[e] = s.mu0[e];
+  if (o.z) for (long long i = gid; i < s.N; i += gsz) o.z[i] = zero_z ? (o.korder[SQC_MAXK + 0] + 1) : (o.korder[SQC_MAXK + s.z[i]] + 1);
+}
+__global__ void k_widen_labels(const int* in, uint8_t* out, long long n, int K, int* bad) {
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x, gsz = (long long)gridDim.x * blockDim.x;
+  for (long long i = gid; i < n; i += gsz) { int v = in[i]; if (v < 0 || v >= K) { *bad = 1; v = 0; } out[i] = (uint8_t)v; }
+}
+__global__ void k_qchisq(const double* p, const double* df, double* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = dev_qchisq(p[i], (int)df[i]);
+}
+// .calc_outliers_dt (reference R/fit_sampleqc.R:419-453): N x K squared Mahalanobis distances with
+// stats::mahalanobis' solve(cov) form, row minimum against qchisq(1 - alpha, D)
+template <int D>
+__global__ void __launch_bounds__(256) k_outlier_maha(const double* x, const int* groups, long long N, int J, int K,
+                                                      const double* mu0, const double* alpha /* J x D col-major */,
+                                                      const double* beta /* K x D col-major */, const double* ainv /* K x D x D */,
+                                                      double cut, double* maha, uint8_t* outlier) {
+  extern __shared__ double sh[];                 // K * (D + D*D)
+  for (int e = threadIdx.x; e < K * D; e += blockDim.x) { int k = e / D, d = e % D; sh[k * (D + D * D) + d] = beta[k + K * d]; }
+  for (int e = threadIdx.x; e < K * D * D; e += blockDim.x) { int k = e / (D * D), r = e % (D * D); sh[k * (D + D * D) + D + r] = ainv[e]; }
+  __syncthreads();
+  const long long gsz = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gsz) {
+    const int j = ld_stream_s32(groups + i);
+    double xc[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) xc[d] = (ld_stream(x + (long long)d * N + i) - mu0[d]) - alpha[j + (long long)J * d];   // :432
+    double mn = CUDART_INF;
+    for (int k = 0; k < K; ++k) {
+      const double* pk = sh + k * (D + D * D);
+      double v[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) v[d] = xc[d] - pk[d];
+      double q = 0.0;
+#pragma unroll
+      for (int c = 0; c < D; ++c) {                // rowSums((x %*% cov) * x), stats::mahalanobis
+        double t = 0.0;
+#pragma unroll
+        for (int r = 0; r < D; ++r) t += v[r] * pk[D + r + D * c];
+        q += t * v[c];
+      }
+      if (maha) maha[i + N * k] = q;
+      if (q < mn) mn = q;
+    }
+    if (outlier) outlier[i] = (mn > cut) ? 1 : 0;   // :449
+  }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// session
+// ---------------------------------------------------------------------------------------------
+struct sqc_session {
+  int D = 0, J = 0, K = 0, variant = 0, device = 0, tile = 0;
+  long long N = 0, N_total = 0;
+  int em_iters = 0, mcd_iters = 0, rng_mode = 0, track = 0, rank = 0, world = 1;
+  double mcd_alpha = 0.5; unsigned seed = 0;
+  cudaStream_t st = nullptr;
+  std::vector<void*> allocs;
+  Dev dev{};
+  McdBufs mb{};
+  MleBufs ml{};
+  Xchg xc{};
+  uint8_t* z0 = nullptr; double* alpha0 = nullptr; double* gamma0 = nullptr;
+  uint32_t* mt_state = nullptr; int* keybuf = nullptr;
+  double* o_buf = nullptr; int* o_z = nullptr; int* o_korder = nullptr; OutPtrs optr{};
+  size_t o_doubles = 0;
+  int mcd_grid = 0, n_sm = 0;
+  bool sorted = true; std::vector<long long> perm;      // perm[i] = original index of the cell stored at i
+  bool profile = false;
+  struct Ev { cudaEvent_t a, b; int fam; };
+  std::vector<Ev> evs; size_t ev_used = 0;
+  cudaEvent_t ev_run0 = nullptr, ev_init = nullptr, ev_loop = nullptr;
+  sqc_run_stats stats{};
+  bool ran = false;
+  Control h_ctl{};
+
+  template <class T> T* alloc(size_t n, bool zero = true) {
+    void* p = nullptr;
+    size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    CK(cudaMalloc(&p, bytes));
+    allocs.push_back(p);
+    if (zero) CK(cudaMemsetAsync(p, 0, bytes, st));
+    return (T*)p;
+  }
+  ~sqc_session() {
+    if (device >= 0) cudaSetDevice(device);
+    xchg_close(xc);
+    for (void* p : allocs) cudaFree(p);
+    for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    if (ev_run0) cudaEventDestroy(ev_run0);
+    if (ev_init) cudaEventDestroy(ev_init);
+    if (ev_loop) cudaEventDestroy(ev_loop);
+    if (st) cudaStreamDestroy(st);
+  }
+};
+
+namespace {
+void mle_alloc(sqc_session&, const sqc_fit_args*, sqc::MleBufs&);
+void mle_run(sqc_session*);
+void mle_fetch(sqc_session*, sqc_fit_out*);
+
+// per-launch accounting: count every launch, time it with events when profiling is on
+struct Launch {
+  sqc_session* S; int fam; sqc_session::Ev* ev = nullptr;
+  Launch(sqc_session* s, int f) : S(s), fam(f) {
+    S->stats.n_gpu_launches++; S->stats.family_launches[fam]++;
+    if (S->profile) {
+      if (S->ev_used == S->evs.size()) { sqc_session::Ev e; CK(cudaEventCreate(&e.a)); CK(cudaEventCreate(&e.b)); e.fam = f; S->evs.push_back(e); }
+      ev = &S->evs[S->ev_used++]; ev->fam = f;
+      CK(cudaEventRecord(ev->a, S->st));
+    }
+  }
+  void done() { if (ev) CK(cudaEventRecord(ev->b, S->st)); CK(cudaGetLastError()); }
+};
+
+template <int D> void launch_estep(sqc_session* S, int mode) {
+  const Dev& s = S->dev;
+  const size_t sm = (size_t)(s.K * ParK<D>::SZ + (EST_THREADS / 32) * s.K * (D + 1)) * sizeof(double);
+  Launch L(S, mode == 0 ? SQC_KF_ESTEP : SQC_KF_INIT);
+  if (mode == 0) k_estep<D, 0><<<s.T, EST_THREADS, sm, S->st>>>(s);
+  else k_estep<D, 1><<<s.T, EST_THREADS, sm, S->st>>>(s);
+  L.done();
+}
+template <int D> void launch_partition(sqc_session* S, int like) {
+  const Dev& s = S->dev;
+  const size_t sm = (size_t)(s.K * ParK<D>::SZ) * sizeof(double) + (size_t)TileCfg<D>::CPT * (EST_THREADS / 32) * s.K * sizeof(int);
+  Launch L(S, SQC_KF_PARTITION);
+  if (like) k_partition<D, 1><<<s.T, EST_THREADS, sm, S->st>>>(s);
+  else k_partition<D, 0><<<s.T, EST_THREADS, sm, S->st>>>(s);
+  L.done();
+}
+template <int D> void launch_mcd(sqc_session* S) {
+  Launch L(S, SQC_KF_MCD);
+  void* args[] = {(void*)&S->dev, (void*)&S->mb};
+  CK(cudaLaunchCooperativeKernel((void*)k_mcd<D>, dim3(S->mcd_grid), dim3(MCD_THREADS), args, MCD_SMEM, S->st));
+  L.done();
+}
+template <int D> int mcd_max_grid(int n_sm) {
+  CK(cudaFuncSetAttribute(k_mcd<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MCD_SMEM));
+  int per = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_mcd<D>, MCD_THREADS, MCD_SMEM));
+  if (per < 1) fail(SQC_ERR_CUDA, "k_mcd<%d> does not fit on an SM", D);
+  return n_sm;                                   // one CTA per SM
+}
+template <int D> void launch_init_passes(sqc_session* S) {
+  const Dev& s = S->dev;
+  { Launch L(S, SQC_KF_INIT); k_colsum<D><<<s.T, EST_THREADS, 0, S->st>>>(s); L.done(); }
+  { Launch L(S, SQC_KF_INIT); k_colmean<<<1, 1024, 0, S->st>>>(s); L.done(); }
+  if (S->world > 1) xchg_allreduce_host(S->xc, S->st, s.mu0, s.D);
+  { Launch L(S, SQC_KF_INIT); k_colmean_finish<<<1, 32, 0, S->st>>>(s); L.done(); }
+  { Launch L(S, SQC_KF_INIT); k_centre<D><<<s.T, EST_THREADS, 0, S->st>>>(s); L.done(); }
+  { Launch L(S, SQC_KF_INIT); k_init_alpha<<<(s.J * 32 + 255) / 256, 256, 0, S->st>>>(s); L.done(); }
+}
+
+#define SQC_CASE_ESTEP(DD) case DD: launch_estep<DD>(S, mode); break;
+void do_estep(sqc_session* S, int mode) { switch (S->D) { SQC_FOR_D(SQC_CASE_ESTEP) default: fail(SQC_ERR_BAD_ARG, "D = %d not compiled in", S->D); } }
+#define SQC_CASE_PART(DD) case DD: launch_partition<DD>(S, like); break;
+void do_partition(sqc_session* S, int like) { switch (S->D) { SQC_FOR_D(SQC_CASE_PART) default: fail(SQC_ERR_BAD_ARG, "D = %d not compiled in", S->D); } }
+#define SQC_CASE_MCD(DD) case DD: launch_mcd<DD>(S); break;
+void do_mcd(sqc_session* S) { switch (S->D) { SQC_FOR_D(SQC_CASE_MCD) default: fail(SQC_ERR_BAD_ARG, "D = %d not compiled in", S->D); } }
+#define SQC_CASE_GRID(DD) case DD: return mcd_max_grid<DD>(n_sm);
+int do_mcd_grid(int D, int n_sm) { switch (D) { SQC_FOR_D(SQC_CASE_GRID) default: fail(SQC_ERR_BAD_ARG, "D = %d not compiled in", D); } }
+#define SQC_CASE_INIT(DD) case DD: launch_init_passes<DD>(S); break;
+void do_init_passes(sqc_session* S) { switch (S->D) { SQC_FOR_D(SQC_CASE_INIT) default: fail(SQC_ERR_BAD_ARG, "D = %d not compiled in", S->D); } }
+#define SQC_CASE_MLE(DD) case DD: mle_launch_pass<DD>(S->dev, S->ml, which, S->st); break;
+void do_mle_pass(sqc_session* S, int which) {
+  Launch L(S, SQC_KF_MLE_PASS);
+  switch (S->D) { SQC_FOR_D(SQC_CASE_MLE) default: fail(SQC_ERR_BAD_ARG, "D = %d not compiled in", S->D); }
+  L.done();
+}
+int tile_cells(int D) { return D <= 4 ? TileCfg<3>::TILE : TileCfg<6>::TILE; }
+
+void select_device(int device, int* chosen) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n < 1) fail(SQC_ERR_CUDA, "no usable CUDA device (%s): this library has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  int d = device;
+  if (d < 0) CK(cudaGetDevice(&d));
+  if (d >= n) fail(SQC_ERR_CUDA, "device %d out of range (%d visible)", d, n);
+  CK(cudaSetDevice(d));
+  *chosen = d;
+}
+
+void check_args(const sqc_fit_args* a, int variant) {
+  if (!a) fail(SQC_ERR_BAD_ARG, "null arguments");
+  if (a->abi_version != SQC_ABI_VERSION) fail(SQC_ERR_BAD_ARG, "ABI version mismatch: caller %u, library %d", a->abi_version, SQC_ABI_VERSION);
+  if (!a->x || !a->groups) fail(SQC_ERR_BAD_ARG, "null input");
+  if (a->D < 1 || a->D > SQC_MAXD) fail(SQC_ERR_BAD_ARG, "D must be in 1..%d", SQC_MAXD);
+  if (a->K < 1 || a->K > SQC_MAXK) fail(SQC_ERR_BAD_ARG, "K must be in 1..%d", SQC_MAXK);
+  if (a->J < 1 || a->N < 1) fail(SQC_ERR_BAD_ARG, "bad dimensions");
+  if (a->N > 2000000000ll) fail(SQC_ERR_BAD_ARG, "N too large for one shard");
+  if (variant == SQC_VARIANT_ROBUST) {
+    if (!a->init_z) fail(SQC_ERR_BAD_ARG, "init_z missing");
+    if ((a->mcd_alpha < 0) | (a->mcd_alpha >= 1) | !(a->mcd_alpha == a->mcd_alpha))
+      fail(SQC_ERR_BAD_ARG, "'mcd_alpha' must be between 0 and 1");                    // robust_cpp.cpp:471-472
+  } else if (!a->init_gamma) fail(SQC_ERR_BAD_ARG, "init_gamma missing");
+  if (a->rng_mode != SQC_RNG_R_COMPAT && a->rng_mode != SQC_RNG_COUNTER) fail(SQC_ERR_BAD_ARG, "unknown rng_mode");
+}
+
+sqc_session* session_create(const sqc_fit_args* a, int variant) {
+  check_args(a, variant);
+  std::unique_ptr<sqc_session> up(new sqc_session());
+  sqc_session* S = up.get();
+  select_device(a->device, &S->device);
+  CK(cudaStreamCreateWithFlags(&S->st, cudaStreamNonBlocking));
+  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, S->device));
+  S->n_sm = prop.multiProcessorCount;
+  S->D = a->D; S->J = a->J; S->K = a->K; S->N = a->N; S->variant = variant;
+  S->world = a->world > 1 ? a->world : 1; S->rank = S->world > 1 ? a->rank : 0;
+  S->N_total = S->world > 1 ? a->N_total : a->N;
+  S->em_iters = a->em_iters; S->mcd_iters = a->mcd_iters; S->mcd_alpha = a->mcd_alpha; S->seed = a->seed;
+  S->rng_mode = a->rng_mode; S->track = a->track ? 1 : 0;
+  S->profile = getenv("SQC_PROFILE") && atoi(getenv("SQC_PROFILE")) != 0;
+  const int D = S->D, J = S->J, K = S->K; const long long N = S->N;
+  const int em = std::max(S->em_iters, 0);
+
+  // ---- sample layout: cells of a sample must be contiguous; permute once if they are not -------
+  std::vector<long long> n_j(J, 0);
+  bool sorted = true;
+  for (long long i = 0; i < N; ++i) {
+    const int g = a->groups[i];
+    if (g < 0 || g >= J) fail(SQC_ERR_BAD_ARG, "groups out of range at cell %lld", i);
+    n_j[g]++;
+    if (i && g < a->groups[i - 1]) sorted = false;
+  }
+  S->sorted = sorted;
+  if (!sorted) {                                    // stable counting sort by sample
+    std::vector<long long> start(J + 1, 0);
+    for (int j = 0; j < J; ++j) start[j + 1] = start[j] + n_j[j];
+    S->perm.resize(N);
+    for (long long i = 0; i < N; ++i) S->perm[start[a->groups[i]]++] = i;
+  }
+  const int TILE = tile_cells(D);
+  S->tile = TILE;
+  std::vector<int> t_start, t_len, t_sample, s_tb(J + 1, 0), s_n(J);
+  {
+    long long pos = 0;
+    for (int j = 0; j < J; ++j) {
+      s_tb[j] = (int)t_start.size(); s_n[j] = (int)n_j[j];
+      for (long long o = 0; o < n_j[j]; o += TILE) { t_start.push_back((int)(pos + o)); t_len.push_back((int)std::min<long long>(TILE, n_j[j] - o)); t_sample.push_back(j); }
+      pos += n_j[j];
+    }
+    s_tb[J] = (int)t_start.size();
+  }
+  const int T = (int)t_start.size();
+
+  Dev& s = S->dev;
+  s.D = D; s.J = J; s.K = K; s.T = T; s.N = N; s.N_total = S->N_total; s.cell_offset = S->world > 1 ? a->cell_offset : 0;
+  s.em_iters = S->em_iters; s.mcd_iters = S->mcd_iters; s.rng_mode = S->rng_mode; s.track = S->track; s.mcd_alpha = S->mcd_alpha; s.seed = S->seed;
+  s.x = S->alloc<double>((size_t)N * D, false);
+  s.z = S->alloc<uint8_t>(N);
+  auto up_i = [&](const std::vector<int>& v) { int* p = S->alloc<int>(v.size(), false); CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, S->st)); return p; };
+  s.tile_start = up_i(t_start); s.tile_len = up_i(t_len); s.tile_sample = up_i(t_sample); s.sample_tile_begin = up_i(s_tb); s.sample_n = up_i(s_n);
+  CK(cudaStreamSynchronize(S->st));                 // the host vectors above go out of scope
+  s.mu0 = S->alloc<double>(D); s.alpha = S->alloc<double>((size_t)J * D); s.beta = S->alloc<double>((size_t)K * D);
+  s.sigma = S->alloc<double>((size_t)K * D * D); s.linv = S->alloc<double>((size_t)K * D * D); s.ainv = S->alloc<double>((size_t)K * D * D);
+  s.logP = S->alloc<double>(K); s.Pk = S->alloc<double>(K);
+  s.p_jk = S->alloc<double>((size_t)J * K); s.logp_jk = S->alloc<double>((size_t)J * K);
+  s.t_ll1 = S->alloc<double>(T); s.t_ll2 = S->alloc<double>(T);
+  s.t_nk = S->alloc<int>((size_t)T * K); s.t_sk = S->alloc<double>((size_t)T * K * D); s.t_base = S->alloc<int>((size_t)T * K);
+  s.t_col = S->alloc<double>((size_t)T * D);
+  s.n_jk = S->alloc<int>((size_t)J * K); s.s_jk = S->alloc<double>((size_t)J * K * D);
+  s.clu_n = S->alloc<long long>(K); s.clu_off = S->alloc<long long>(K); s.clu_n_glob = S->alloc<long long>(K); s.clu_prefix = S->alloc<long long>(K);
+  s.like1 = S->alloc<double>(em + 1); s.like2 = S->alloc<double>(em + 1);
+  s.ctl = S->alloc<Control>(1);
+  S->alpha0 = S->alloc<double>((size_t)J * D);
+  if (S->track && variant == SQC_VARIANT_ROBUST) {
+    s.track_alpha = S->alloc<double>((size_t)J * D * em); s.track_beta = S->alloc<double>((size_t)K * D * em);
+    s.track_sigma = S->alloc<double>((size_t)K * D * D * em); s.track_p = S->alloc<double>((size_t)J * K * em);
+  }
+  // outputs, packed: mu0 | alpha | beta | sigma | p_jk
+  S->o_doubles = (size_t)D + (size_t)J * D + (size_t)K * D + (size_t)K * D * D + (size_t)J * K;
+  S->o_buf = S->alloc<double>(S->o_doubles); S->o_z = S->alloc<int>(N, false); S->o_korder = S->alloc<int>(2 * SQC_MAXK);
+  S->optr.mu0 = S->o_buf; S->optr.alpha = S->optr.mu0 + D; S->optr.beta = S->optr.alpha + (size_t)J * D;
+  S->optr.sigma = S->optr.beta + (size_t)K * D; S->optr.p_jk = S->optr.sigma + (size_t)K * D * D; S->optr.z = S->o_z; S->optr.korder = S->o_korder;
+
+  // ---- upload ----------------------------------------------------------------------------------
+  if (sorted) {
+    CK(cudaMemcpyAsync(s.x, a->x, (size_t)N * D * sizeof(double), cudaMemcpyHostToDevice, S->st));
+  } else {
+    std::vector<double> col(N);
+    for (int d = 0; d < D; ++d) {
+      for (long long i = 0; i < N; ++i) col[i] = a->x[(size_t)d * N + S->perm[i]];
+      CK(cudaMemcpyAsync(s.x + (size_t)d * N, col.data(), (size_t)N * sizeof(double), cudaMemcpyHostToDevice, S->st));
+      CK(cudaStreamSynchronize(S->st));
+    }
+  }
+  if (S->world > 1) xchg_open(S->xc, S->device, S->rank, S->world, a->peer_handles);
+
+  if (variant == SQC_VARIANT_ROBUST) {
+    S->z0 = S->alloc<uint8_t>(N, false);
+    int* bad = S->alloc<int>(1);
+    {                                               // labels travel as int32 (the export's arma::uvec); narrow on the device
+      int* tmp = nullptr; CK(cudaMalloc((void**)&tmp, (size_t)N * sizeof(int)));
+      if (sorted) CK(cudaMemcpyAsync(tmp, a->init_z, (size_t)N * sizeof(int), cudaMemcpyHostToDevice, S->st));
+      else { std::vector<int> zz(N); for (long long i = 0; i < N; ++i) zz[i] = a->init_z[S->perm[i]]; CK(cudaMemcpy(tmp, zz.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice)); }
+      k_widen_labels<<<std::min<long long>((N + 255) / 256, 4096), 256, 0, S->st>>>(tmp, S->z0, N, K, bad);
+      int hb = 0; CK(cudaMemcpyAsync(&hb, bad, sizeof(int), cudaMemcpyDeviceToHost, S->st));
+      CK(cudaStreamSynchronize(S->st));
+      cudaFree(tmp);
+      if (hb) fail(SQC_ERR_BAD_ARG, "init_z out of range");
+    }
+    s.rs_stride = ((N + 32ll * (K + 1)) + 31) & ~31ll;
+    s.rs = S->alloc<double>((size_t)s.rs_stride * D);
+    S->mcd_grid = do_mcd_grid(D, S->n_sm);
+    McdBufs& mb = S->mb;
+    mb.work = S->alloc<McdWork>(1);
+    mb.hist = S->alloc<unsigned int>((size_t)K * MCD_NB);
+    mb.part = S->alloc<double>((size_t)S->mcd_grid * K * SQC_NMOM(D));
+    mb.cand_bits = S->alloc<unsigned long long>((size_t)K * MCD_CAND_CAP);
+    mb.cand_pos = S->alloc<unsigned int>((size_t)K * MCD_CAND_CAP);
+    if (S->rng_mode == SQC_RNG_R_COMPAT) { S->mt_state = S->alloc<uint32_t>(640); S->keybuf = S->alloc<int>(S->N_total, false); }
+  } else {
+    mle_alloc(*S, a, S->ml);
+  }
+  // ---- centring: mu_0 = colMeans(x) (:478), x <- x - mu_0 (centre_x), alpha_j = per-sample means ----
+  S->stats = sqc_run_stats{};
+  do_init_passes(S);
+  CK(cudaMemcpyAsync(S->alpha0, s.alpha, (size_t)J * D * sizeof(double), cudaMemcpyDeviceToDevice, S->st));
+  CK(cudaStreamSynchronize(S->st));
+  CK(cudaEventCreate(&S->ev_run0)); CK(cudaEventCreate(&S->ev_init)); CK(cudaEventCreate(&S->ev_loop));
+  return up.release();
+}
+
+void gen_keys(sqc_session* S, int call) {
+  // one update_beta_scale_k call consumes exactly N_total draws
+  if (S->rng_mode == SQC_RNG_R_COMPAT) {
+    Launch L(S, SQC_KF_RNG);
+    k_mt_keys<<<1, 256, 0, S->st>>>(S->mt_state, S->keybuf, S->N_total, 0, S->dev.ctl);
+    L.done();
+    S->mb.keys = S->keybuf;
+  } else {
+    S->mb.keys = nullptr;
+  }
+  S->mb.call_mix = counter_call_mix(S->seed, 0u);
+  S->mb.stream_base = (long long)call * S->N_total;
+}
+
+void run_robust(sqc_session* S) {
+  Dev& s = S->dev;
+  const int J = S->J;
+  CK(cudaEventRecord(S->ev_run0, S->st));
+  { Launch L(S, SQC_KF_UPDATE); k_ctl_reset<<<1, 32, 0, S->st>>>(s); L.done(); }
+  CK(cudaMemcpyAsync(s.z, S->z0, (size_t)S->N, cudaMemcpyDeviceToDevice, S->st));
+  CK(cudaMemcpyAsync(s.alpha, S->alpha0, (size_t)J * S->D * sizeof(double), cudaMemcpyDeviceToDevice, S->st));   // init_alpha_j, :482
+  CK(cudaMemsetAsync(s.beta, 0, (size_t)S->K * S->D * sizeof(double), S->st));
+  CK(cudaMemsetAsync(s.sigma, 0, (size_t)S->K * S->D * S->D * sizeof(double), S->st));
+  CK(cudaMemsetAsync(s.like1, 0, (size_t)(std::max(S->em_iters, 0) + 1) * sizeof(double), S->st));
+  CK(cudaMemsetAsync(s.like2, 0, (size_t)(std::max(S->em_iters, 0) + 1) * sizeof(double), S->st));
+  if (S->mt_state) { Launch L(S, SQC_KF_RNG); k_mt_seed<<<1, 32, 0, S->st>>>(S->mt_state, S->seed); L.done(); }   // set_seed_cpp, :475
+  const int nsb = (J + 31) / 32;
+  auto post_stats = [&]() {
+    Launch L(S, SQC_KF_UPDATE); k_post_stats<<<nsb + 1, 1024, 0, S->st>>>(s, nsb); L.done();
+    if (S->world > 1) xchg_cluster_layout(S, s);
+  };
+  auto m_step = [&](int call, int like) {
+    do_partition(S, like);
+    gen_keys(S, call);
+    do_mcd(S);
+    { Launch L(S, SQC_KF_UPDATE); k_derive<<<1, 32, 0, S->st>>>(s); L.done(); }
+  };
+  // initial labelling: p_jk (:481), alpha_j (:482), beta_k / Sigma_k (:483)
+  do_estep(S, 1);
+  post_stats();
+  { Launch L(S, SQC_KF_UPDATE); k_update_p<<<(J + 127) / 128, 128, 0, S->st>>>(s); L.done(); }
+  m_step(0, 0);
+  { Launch L(S, SQC_KF_UPDATE); k_ctl_start_loop<<<1, 32, 0, S->st>>>(s); L.done(); }
+  CK(cudaEventRecord(S->ev_init, S->st));
+  for (int it = 0; it < S->em_iters; ++it) {                                            // :490
+    { Launch L(S, SQC_KF_UPDATE); k_update_alpha<<<(J + 127) / 128, 128, 0, S->st>>>(s); L.done(); }   // :496
+    m_step(it + 1, 1);                                                                  // like_1 :499, M-step :502
+    { Launch L(S, SQC_KF_UPDATE); k_update_p<<<(J + 127) / 128, 128, 0, S->st>>>(s); L.done(); }       // :504
+    do_estep(S, 0);                                                                     // :506, :509, :519
+    post_stats();
+    if (S->world > 1) xchg_allreduce_like(S, s);
+    { Launch L(S, SQC_KF_UPDATE); k_em_control<<<1, 1024, 0, S->st>>>(s); L.done(); }
+  }
+  CK(cudaEventRecord(S->ev_loop, S->st));
+}
+
+void session_run(sqc_session* S) {
+  CK(cudaSetDevice(S->device));
+  S->stats = sqc_run_stats{};
+  S->ev_used = 0;
+  if (S->variant == SQC_VARIANT_ROBUST) run_robust(S);
+  else mle_run(S);
+  CK(cudaMemcpyAsync(&S->h_ctl, S->dev.ctl, sizeof(Control), cudaMemcpyDeviceToHost, S->st));
+  CK(cudaStreamSynchronize(S->st));
+  S->ran = true;
+  float ms = 0;
+  CK(cudaEventElapsedTime(&ms, S->ev_run0, S->ev_init)); S->stats.init_ms = ms;
+  CK(cudaEventElapsedTime(&ms, S->ev_init, S->ev_loop)); S->stats.loop_ms = ms;
+  S->stats.n_iter = S->h_ctl.iter;
+  S->stats.mcd_passes = S->h_ctl.mcd_passes; S->stats.mcd_csteps = S->h_ctl.mcd_csteps;
+  for (size_t i = 0; i < S->ev_used; ++i) {
+    CK(cudaEventElapsedTime(&ms, S->evs[i].a, S->evs[i].b));
+    S->stats.family_ms[S->evs[i].fam] += ms;
+  }
+  // algorithmic bytes: one pass = N (8 D + 5) bytes; E-step writes N more
+  const double pass = (double)S->N * (8.0 * S->D + 5.0);
+  const int it = S->h_ctl.iter;
+  if (S->variant == SQC_VARIANT_ROBUST) {
+    S->stats.family_bytes[SQC_KF_ESTEP] = (double)it * (pass + (double)S->N);
+    S->stats.family_bytes[SQC_KF_PARTITION] = (double)(it + 1) * (pass + 8.0 * S->D * (double)S->N);
+    S->stats.family_bytes[SQC_KF_MCD] = (double)S->h_ctl.mcd_passes * (double)S->N * (8.0 * S->D);
+  } else {
+    S->stats.family_bytes[SQC_KF_MLE_PASS] = (double)(2 * it + 1) * pass;
+  }
+  if (S->h_ctl.status != 0) fail(S->h_ctl.status, "%s", device_status_message(S->h_ctl.status));
+}
+
+void reorder_track(const sqc_session* S, sqc_fit_out* o, const int* korder) {
+  const int D = S->D, J = S->J, K = S->K, em = std::max(S->em_iters, 0);
+  std::vector<double> tmp;
+  for (int it = 0; it < em; ++it) {                 // robust_cpp.cpp:533-537
+    if (o->track_beta_k) { double* b = o->track_beta_k + (size_t)it * K * D; tmp.assign(b, b + K * D);
+      for (int k = 0; k < K; ++k) for (int d = 0; d < D; ++d) b[k + K * d] = tmp[korder[k] + K * d]; }
+    if (o->track_sigma_k) { double* g = o->track_sigma_k + (size_t)it * D * D * K; tmp.assign(g, g + D * D * K);
+      for (int k = 0; k < K; ++k) memcpy(g + (size_t)k * D * D, tmp.data() + (size_t)korder[k] * D * D, sizeof(double) * D * D); }
+    if (o->track_p_jk) { double* p = o->track_p_jk + (size_t)it * J * K; tmp.assign(p, p + J * K);
+      for (int k = 0; k < K; ++k) for (int j = 0; j < J; ++j) p[j + J * k] = tmp[j + J * korder[k]]; }
+  }
+}
+
+void session_fetch(sqc_session* S, sqc_fit_out* o) {
+  if (!o) fail(SQC_ERR_BAD_ARG, "null output");
+  if (!S->ran) fail(SQC_ERR_BAD_ARG, "sqc_session_fetch before sqc_session_run");
+  CK(cudaSetDevice(S->device));
+  Dev& s = S->dev;
+  const int D = S->D, J = S->J, K = S->K, em = std::max(S->em_iters, 0); const long long N = S->N;
+  if (S->variant == SQC_VARIANT_MLE) { mle_fetch(S, o); return; }
+  OutPtrs op = S->optr;
+  if (!o->z) op.z = nullptr;
+  k_order_components<<<1, 32, 0, S->st>>>(s, op);
+  k_pack_outputs<<<std::max(1, std::min<int>((int)((N + 255) / 256), S->n_sm * 8)), 256, 0, S->st>>>(s, op, S->em_iters <= 0 ? 1 : 0);
+  CK(cudaGetLastError());
+  std::vector<double> h(S->o_doubles);
+  int korder[2 * SQC_MAXK];
+  CK(cudaMemcpyAsync(h.data(), S->o_buf, S->o_doubles * sizeof(double), cudaMemcpyDeviceToHost, S->st));
+  CK(cudaMemcpyAsync(korder, S->o_korder, sizeof korder, cudaMemcpyDeviceToHost, S->st));
+  if (o->z) {
+    if (S->sorted) CK(cudaMemcpyAsync(o->z, S->o_z, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, S->st));
+    else { std::vector<int> zz(N); CK(cudaMemcpyAsync(zz.data(), S->o_z, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost, S->st)); CK(cudaStreamSynchronize(S->st));
+           for (long long i = 0; i < N; ++i) o->z[S->perm[i]] = zz[i]; }
+  }
+  if (o->like_1) CK(cudaMemcpyAsync(o->like_1, s.like1, (size_t)em * sizeof(double), cudaMemcpyDeviceToHost, S->st));
+  if (o->like_2) CK(cudaMemcpyAsync(o->like_2, s.like2, (size_t)em * sizeof(double), cudaMemcpyDeviceToHost, S->st));
+  if (S->track) {
+    if (o->track_alpha_j) CK(cudaMemcpyAsync(o->track_alpha_j, s.track_alpha, (size_t)J * D * em * sizeof(double), cudaMemcpyDeviceToHost, S->st));
+    if (o->track_beta_k) CK(cudaMemcpyAsync(o->track_beta_k, s.track_beta, (size_t)K * D * em * sizeof(double), cudaMemcpyDeviceToHost, S->st));
+    if (o->track_sigma_k) CK(cudaMemcpyAsync(o->track_sigma_k, s.track_sigma, (size_t)K * D * D * em * sizeof(double), cudaMemcpyDeviceToHost, S->st));
+    if (o->track_p_jk) CK(cudaMemcpyAsync(o->track_p_jk, s.track_p, (size_t)J * K * em * sizeof(double), cudaMemcpyDeviceToHost, S->st));
+  }
+  if (S->mt_state) {
+    uint32_t st[625];
+    CK(cudaMemcpyAsync(st, S->mt_state, sizeof st, cudaMemcpyDeviceToHost, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    o->rng_state[0] = (int32_t)st[624];
+    for (int i = 0; i < 624; ++i) o->rng_state[i + 1] = (int32_t)st[i];
+  } else memset(o->rng_state, 0, sizeof o->rng_state);
+  CK(cudaStreamSynchronize(S->st));
+  const double* p = h.data();
+  if (o->mu_0) memcpy(o->mu_0, p, sizeof(double) * D); p += D;
+  if (o->alpha_j) memcpy(o->alpha_j, p, sizeof(double) * J * D); p += (size_t)J * D;
+  if (o->beta_k) memcpy(o->beta_k, p, sizeof(double) * K * D); p += (size_t)K * D;
+  if (o->sigma_k) memcpy(o->sigma_k, p, sizeof(double) * K * D * D); p += (size_t)K * D * D;
+  if (o->p_jk) memcpy(o->p_jk, p, sizeof(double) * J * K);
+  if (S->track) reorder_track(S, o, korder);
+  o->n_iter = S->h_ctl.iter; o->mcd_iters_hit = S->h_ctl.mcd_hit; o->n_zero_like = S->h_ctl.n_zero;
+  o->rng_draws = (long long)(1 + S->h_ctl.iter) * S->N_total;
+}
+
+template <class F> int guarded(F&& f, char* err, size_t errlen) {
+  try { f(); if (err && errlen) err[0] = 0; return SQC_OK; }
+  catch (const SqcFail& e) { if (err && errlen) snprintf(err, errlen, "%s", e.msg.c_str()); return e.code; }
+  catch (const std::bad_alloc&) { if (err && errlen) snprintf(err, errlen, "host allocation failed"); return SQC_ERR_NOMEM; }
+  catch (const std::exception& e) { if (err && errlen) snprintf(err, errlen, "%s", e.what()); return SQC_ERR_CUDA; }
+}
+
+int one_shot(const sqc_fit_args* a, sqc_fit_out* o, int variant, char* err, size_t errlen) {
+  sqc_session* S = nullptr;
+  int st = guarded([&] {
+    if (!o) fail(SQC_ERR_BAD_ARG, "null output");
+    S = session_create(a, variant);
+    session_run(S);
+    session_fetch(S, o);
+  }, err, errlen);
+  delete S;
+  return st;
+}
+
+}  // namespace
+
+#include "sqc_mle_host.inl"
+
+extern "C" {
+
+int sqc_fit_robust(const sqc_fit_args* a, sqc_fit_out* o, char* err, size_t errlen) { return one_shot(a, o, SQC_VARIANT_ROBUST, err, errlen); }
+int sqc_fit_mle(const sqc_fit_args* a, sqc_fit_out* o, char* err, size_t errlen) { return one_shot(a, o, SQC_VARIANT_MLE, err, errlen); }
+
+int sqc_session_create(const sqc_fit_args* a, int variant, sqc_session** out, char* err, size_t errlen) {
+  if (out) *out = nullptr;
+  return guarded([&] {
+    if (!out) fail(SQC_ERR_BAD_ARG, "null session pointer");
+    if (variant != SQC_VARIANT_ROBUST && variant != SQC_VARIANT_MLE) fail(SQC_ERR_BAD_ARG, "unknown variant");
+    *out = session_create(a, variant);
+  }, err, errlen);
+}
+int sqc_session_run(sqc_session* s, char* err, size_t errlen) { return guarded([&] { if (!s) fail(SQC_ERR_BAD_ARG, "null session"); session_run(s); }, err, errlen); }
+int sqc_session_fetch(sqc_session* s, sqc_fit_out* o, char* err, size_t errlen) { return guarded([&] { if (!s) fail(SQC_ERR_BAD_ARG, "null session"); session_fetch(s, o); }, err, errlen); }
+int sqc_session_stats(const sqc_session* s, sqc_run_stats* st) { if (!s || !st) return SQC_ERR_BAD_ARG; *st = s->stats; return SQC_OK; }
+int sqc_session_profile(sqc_session* s, int on) { if (!s) return SQC_ERR_BAD_ARG; s->profile = on != 0; return SQC_OK; }
+void sqc_session_destroy(sqc_session* s) { delete s; }
+
+int sqc_outlier_maha(const sqc_maha_args* a, double* maha, uint8_t* outlier, double* maha_cut, char* err, size_t errlen) {
+  return guarded([&] {
+    if (!a || !a->x || !a->groups || !a->mu_0 || !a->alpha_j || !a->beta_k || !a->sigma_k) fail(SQC_ERR_BAD_ARG, "null input");
+    if (a->abi_version != SQC_ABI_VERSION) fail(SQC_ERR_BAD_ARG, "ABI version mismatch");
+    const int D = a->D, J = a->J, K = a->K; const long long N = a->N;
+    if (D < 1 || D > SQC_MAXD || K < 1 || K > 64 || J < 1 || N < 1) fail(SQC_ERR_BAD_ARG, "bad dimensions");
+    int dev; select_device(a->device, &dev);
+    // solve(cov) on the host: K tiny inverses (stats::mahalanobis)
+    std::vector<double> ainv((size_t)K * D * D);
+    for (int k = 0; k < K; ++k) if (!small_inv(a->sigma_k + (size_t)k * D * D, D, ainv.data() + (size_t)k * D * D)) fail(SQC_ERR_SINGULAR, "solve(): system is exactly singular");
+    double *dx = nullptr, *dpar = nullptr, *dm = nullptr; int* dg = nullptr; uint8_t* dout = nullptr; double* dq = nullptr;
+    auto cleanup = [&] { cudaFree(dx); cudaFree(dpar); cudaFree(dm); cudaFree(dg); cudaFree(dout); cudaFree(dq); };
+    try {
+      const size_t npar = (size_t)D + (size_t)J * D + (size_t)K * D + (size_t)K * D * D;
+      CK(cudaMalloc((void**)&dx, (size_t)N * D * sizeof(double))); CK(cudaMalloc((void**)&dg, (size_t)N * sizeof(int)));
+      CK(cudaMalloc((void**)&dpar, npar * sizeof(double))); CK(cudaMalloc((void**)&dq, 3 * sizeof(double)));
+      if (maha) CK(cudaMalloc((void**)&dm, (size_t)N * K * sizeof(double)));
+      if (outlier) CK(cudaMalloc((void**)&dout, (size_t)N));
+      CK(cudaMemcpy(dx, a->x, (size_t)N * D * sizeof(double), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(dg, a->groups, (size_t)N * sizeof(int), cudaMemcpyHostToDevice));
+      double* pm = dpar; double* pa = pm + D; double* pb = pa + (size_t)J * D; double* pi = pb + (size_t)K * D;
+      CK(cudaMemcpy(pm, a->mu_0, D * sizeof(double), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(pa, a->alpha_j, (size_t)J * D * sizeof(double), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(pb, a->beta_k, (size_t)K * D * sizeof(double), cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(pi, ainv.data(), (size_t)K * D * D * sizeof(double), cudaMemcpyHostToDevice));
+      double hq[3] = {1.0 - a->alpha, (double)D, 0.0};                  // qchisq(1 - alpha, df = D), :429
+      CK(cudaMemcpy(dq, hq, sizeof hq, cudaMemcpyHostToDevice));
+      k_qchisq<<<1, 32>>>(dq, dq + 1, dq + 2, 1);
+      CK(cudaMemcpy(hq, dq, sizeof hq, cudaMemcpyDeviceToHost));
+      const double cut = hq[2];
+      if (maha_cut) *maha_cut = cut;
+      for (long long i = 0; i < N; ++i) if (a->groups[i] < 0 || a->groups[i] >= J) fail(SQC_ERR_BAD_ARG, "groups out of range");
+      const int grid = (int)std::min<long long>((N + 255) / 256, 148 * 16);
+      const size_t sm = (size_t)K * (D + D * D) * sizeof(double);
+#define SQC_CASE_MAHA(DD) case DD: k_outlier_maha<DD><<<grid, 256, sm>>>(dx, dg, N, J, K, pm, pa, pb, pi, cut, dm, dout); break;
+      switch (D) { SQC_FOR_D(SQC_CASE_MAHA) default: fail(SQC_ERR_BAD_ARG, "D = %d not compiled in", D); }
+      CK(cudaGetLastError());
+      if (maha) CK(cudaMemcpy(maha, dm, (size_t)N * K * sizeof(double), cudaMemcpyDeviceToHost));
+      if (outlier) CK(cudaMemcpy(outlier, dout, (size_t)N, cudaMemcpyDeviceToHost));
+      CK(cudaDeviceSynchronize());
+    } catch (...) { cleanup(); throw; }
+    cleanup();
+  }, err, errlen);
+}
+
+int sqc_xchg_export(int device, void* handle_out, char* err, size_t errlen) { return guarded([&] { int d; select_device(device, &d); xchg_export(d, handle_out); }, err, errlen); }
+int sqc_xchg_release(int device) { return xchg_release(device); }
+
+int sqc_abi_version(void) { return SQC_ABI_VERSION; }
+int sqc_device_count(void) { int n = 0; cudaError_t e = cudaGetDeviceCount(&n); return e == cudaSuccess ? n : -1; }
+const char* sqc_status_name(int st) {
+  switch (st) {
+    case SQC_OK: return "SQC_OK"; case SQC_ERR_BAD_ARG: return "SQC_ERR_BAD_ARG"; case SQC_ERR_EMPTY_CLUSTER: return "SQC_ERR_EMPTY_CLUSTER";
+    case SQC_ERR_SUBSET_SIZE: return "SQC_ERR_SUBSET_SIZE"; case SQC_ERR_NOT_SPD: return "SQC_ERR_NOT_SPD"; case SQC_ERR_SINGULAR: return "SQC_ERR_SINGULAR";
+    case SQC_ERR_NAN: return "SQC_ERR_NAN"; case SQC_ERR_SELECT: return "SQC_ERR_SELECT"; case SQC_ERR_CUDA: return "SQC_ERR_CUDA";
+    case SQC_ERR_COMM: return "SQC_ERR_COMM"; case SQC_ERR_NOMEM: return "SQC_ERR_NOMEM"; default: return "SQC_ERR_UNKNOWN";
+  }
+}
+int sqc_device_qchisq(const double* p, const double* df, double* out, int32_t n, int device, char* err, size_t errlen) {
+  return guarded([&] {
+    if (!p || !df || !out || n < 0) fail(SQC_ERR_BAD_ARG, "bad arguments");
+    int d; select_device(device, &d);
+    double* buf = nullptr; CK(cudaMalloc((void**)&buf, (size_t)3 * std::max(n, 1) * sizeof(double)));
+    cudaMemcpy(buf, p, n * sizeof(double), cudaMemcpyHostToDevice); cudaMemcpy(buf + n, df, n * sizeof(double), cudaMemcpyHostToDevice);
+    k_qchisq<<<(n + 127) / 128, 128>>>(buf, buf + n, buf + 2 * (size_t)n, n);
+    cudaError_t e = cudaMemcpy(out, buf + 2 * (size_t)n, n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(buf); CK(e);
+  }, err, errlen);
+}
+int sqc_device_rkeys(uint32_t seed, int64_t skip, int32_t* keys_out, int64_t n, int device, char* err, size_t errlen) {
+  return guarded([&] {
+    if (!keys_out || n < 0 || skip < 0) fail(SQC_ERR_BAD_ARG, "bad arguments");
+    int d; select_device(device, &d);
+    uint32_t* st = nullptr; int* out = nullptr;
+    CK(cudaMalloc((void**)&st, 640 * sizeof(uint32_t))); CK(cudaMalloc((void**)&out, (size_t)std::max<int64_t>(n, 1) * sizeof(int)));
+    k_mt_seed<<<1, 32>>>(st, seed);
+    k_mt_keys<<<1, 256>>>(st, out, n, skip, nullptr);
+    cudaError_t e = cudaMemcpy(keys_out, out, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(st); cudaFree(out); CK(e);
+  }, err, errlen);
+}
+
+}  // extern "C"
