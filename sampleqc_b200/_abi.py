@@ -132,10 +132,11 @@ def ptr_i(a: np.ndarray | None):
 class FitBuffers:
     """Owns the caller-allocated host outputs of one fit and converts them to the Rcpp List shape."""
 
-    def __init__(self, D, J, K, N, em_iters, variant, track=False):
+    def __init__(self, D, J, K, N, em_iters, variant, track=False, alloc=None):
+        """alloc(shape, dtype=..., order=...) may hand out pinned host memory (bench.py's e2e leg)"""
         self.D, self.J, self.K, self.N, self.em_iters = D, J, K, N, max(int(em_iters), 0)
         self.variant, self.track = variant, bool(track)
-        z = np.zeros
+        z = alloc or np.zeros
         self.mu_0 = z(D)
         self.alpha_j = z((J, D), order="F")
         self.beta_k = z((K, D), order="F")

@@ -171,21 +171,23 @@ __device__ inline double dev_qchisq(double p, int df) {
   if (p == 0.0) return 0.0;
   if (p == 1.0) return CUDART_INF;
   const double a = 0.5 * df;
-  const bool upper = p > 0.5;
+  const bool upper = p > 0.5;                      // solve on the smaller tail (1 - p is exact for p >= 0.5)
   const double target = upper ? 1.0 - p : p;
   const double lg = lgamma(a);
-  // Wilson-Hilferty start
-  double zq = normcdfinv(p), c = 2.0 / (9.0 * df);
-  double w = 1.0 - c + zq * sqrt(c);
+  // residual, increasing in y = x / 2
+  auto resid = [&](double y) { return upper ? (target - gamma_q_halfint(df, y)) : (gamma_p_series(a, y) - target); };
+  // bracket, then bisection-safeguarded Newton started from Wilson-Hilferty when that lies inside
+  double lo = 0.0, hi = fmax(1.0, a);
+  while (resid(hi) < 0.0) { lo = hi; hi *= 2.0; if (hi > 1e300) break; }
+  const double zq = normcdfinv(p), c = 2.0 / (9.0 * df), w = 1.0 - c + zq * sqrt(c);
   double y = 0.5 * df * w * w * w;
-  if (!(y > 1e-300)) y = 0.5 * exp((log(p) + lg + log(a)) / a);      // tiny-p asymptote P ~ y^a / Gamma(a+1)
-  double lo = 0.0, hi = CUDART_INF;
-  for (int it = 0; it < 100; ++it) {
-    double f = upper ? (target - gamma_q_halfint(df, y)) : (gamma_p_series(a, y) - target);
-    if (f > 0) hi = y; else lo = y;
-    double pdf = exp(-y + (a - 1.0) * log(y) - lg);
-    double yn = (pdf > 0.0) ? y - f / pdf : y;
-    if (!(yn > lo) || !(yn < hi)) yn = (hi < CUDART_INF) ? 0.5 * (lo + hi) : 2.0 * y + 1.0;
+  if (!(y > lo && y < hi)) y = 0.5 * (lo + hi);
+  for (int it = 0; it < 200; ++it) {
+    const double f = resid(y);
+    if (f > 0.0) hi = y; else lo = y;
+    const double pdf = exp(-y + (a - 1.0) * log(y) - lg);
+    double yn = (pdf > 0.0) ? y - f / pdf : 0.5 * (lo + hi);
+    if (!(yn > lo && yn < hi)) yn = 0.5 * (lo + hi);
     if (fabs(yn - y) <= 4e-16 * fabs(yn)) { y = yn; break; }
     y = yn;
   }

@@ -34,6 +34,8 @@ struct Control {
   int mcd_call;      // update_beta_scale_k calls so far (RNG stream position = call * N_total)
   int pad;
   long long mcd_passes, mcd_csteps;
+  long long mcd_cells;   // sum over streaming rounds of the cells of the clusters still active
+  long long mcd_bytes;   // bytes those rounds had to read (residual columns + keys), DESIGN.md
 };
 
 // everything a kernel needs, passed by value

@@ -67,7 +67,7 @@ __global__ void k_ctl_reset(Dev s) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     Control* c = s.ctl;
     c->iter = 0; c->z_delta = 0; c->cont = 1; c->status = 0; c->n_zero = 0; c->mcd_hit = 0; c->mcd_call = 0; c->pad = 0;
-    c->mcd_passes = 0; c->mcd_csteps = 0;
+    c->mcd_passes = 0; c->mcd_csteps = 0; c->mcd_cells = 0; c->mcd_bytes = 0;
   }
 }
 __global__ void k_ctl_start_loop(Dev s) {
@@ -106,7 +106,8 @@ __global__ void k_order_components(Dev s, OutPtrs o) {
     for (int k = 0; k < s.K; ++k) o.korder[SQC_MAXK + idx[k]] = k;     // inverse map
   }
 }
-__global__ void k_pack_outputs(Dev s, OutPtrs o, int zero_z) {
+// zmode: 0 = inverse relabel (reorder_z), 1 = loop never ran (labels all zero), 2 = idx(k_max) (mle extract_z :241)
+__global__ void k_pack_outputs(Dev s, OutPtrs o, int zmode) {
   const int D = s.D, J = s.J, K = s.K;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x, gsz = (long long)gridDim.x * blockDim.x;
   for (long long e = gid; e < (long long)J * D; e += gsz) { int j = (int)(e / D), d = (int)(e % D); o.alpha[j + (long long)J * d] = s.alpha[e]; }
@@ -114,7 +115,8 @@ __global__ void k_pack_outputs(Dev s, OutPtrs o, int zero_z) {
   for (long long e = gid; e < (long long)K * D * D; e += gsz) { int k = (int)(e / (D * D)), r = (int)(e % (D * D)); o.sigma[e] = s.sigma[o.korder[k] * D * D + r]; }
   for (long long e = gid; e < (long long)J * K; e += gsz) { int j = (int)(e / K), k = (int)(e % K); o.p_jk[j + (long long)J * k] = s.p_jk[j * K + o.korder[k]]; }
   for (long long e = gid; e < D; e += gsz) o.mu0[e] = s.mu0[e];
-  if (o.z) for (long long i = gid; i < s.N; i += gsz) o.z[i] = zero_z ? (o.korder[SQC_MAXK + 0] + 1) : (o.korder[SQC_MAXK + s.z[i]] + 1);
+  if (o.z) for (long long i = gid; i < s.N; i += gsz)
+    o.z[i] = (zmode == 1) ? (o.korder[SQC_MAXK + 0] + 1) : (zmode == 2) ? (o.korder[s.z[i]] + 1) : (o.korder[SQC_MAXK + s.z[i]] + 1);
 }
 __global__ void k_widen_labels(const int* in, uint8_t* out, long long n, int K, int* bad) {
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x, gsz = (long long)gridDim.x * blockDim.x;
@@ -520,7 +522,7 @@ void session_run(sqc_session* S) {
   if (S->variant == SQC_VARIANT_ROBUST) {
     S->stats.family_bytes[SQC_KF_ESTEP] = (double)it * (pass + (double)S->N);
     S->stats.family_bytes[SQC_KF_PARTITION] = (double)(it + 1) * (pass + 8.0 * S->D * (double)S->N);
-    S->stats.family_bytes[SQC_KF_MCD] = (double)S->h_ctl.mcd_passes * (double)S->N * (8.0 * S->D);
+    S->stats.family_bytes[SQC_KF_MCD] = (double)S->h_ctl.mcd_bytes;
   } else {
     S->stats.family_bytes[SQC_KF_MLE_PASS] = (double)(2 * it + 1) * pass;
   }

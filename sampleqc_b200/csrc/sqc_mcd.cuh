@@ -220,14 +220,20 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
   for (;;) {
     // ---- active chunk map -------------------------------------------------------------------
     if (tid == 0) {
-      long long run = 0; int any = 0;
+      long long run = 0, cells = 0, bytes = 0; int any = 0;
       const bool bad = s.ctl->status != 0;
       for (int k = 0; k < K; ++k) {
         sh_cstart[k] = run;
         const int ph = W->clu[k].phase;
-        if (ph != PH_DONE && !bad) { run += (W->clu[k].n + MCD_CHUNK - 1) / MCD_CHUNK; any = 1; }
+        if (ph != PH_DONE && !bad) {
+          const long long n = W->clu[k].n;
+          run += (n + MCD_CHUNK - 1) / MCD_CHUNK; any = 1; cells += n;
+          const bool keyr = (ph == PH_KEY_HIST || ph == PH_KEY_COLLECT);
+          bytes += n * ((ph == PH_KEY_HIST ? 0 : 8 * D) + ((keyr && mb.keys) ? 4 : 0));
+        }
       }
       sh_cstart[K] = run; sh_flag[0] = any;
+      if (b == 0) { s.ctl->mcd_cells += cells; s.ctl->mcd_bytes += bytes; }
     }
     __syncthreads();
     if (!sh_flag[0]) break;

@@ -10,6 +10,8 @@ inline void xchg_close(Xchg&) {}
 inline void xchg_allreduce_host(Xchg&, cudaStream_t, double*, int) {}
 inline void xchg_cluster_layout(sqc_session*, Dev&) {}
 inline void xchg_allreduce_like(sqc_session*, Dev&) {}
+struct MleBufs;
+inline void xchg_allreduce_mle(sqc_session*, Dev&, MleBufs&, int, double*, int) {}
 inline void xchg_export(int, void*) { throw std::runtime_error("multi-GPU exchange not built"); }
 inline int xchg_release(int) { return 0; }
 }  // namespace sqc
