@@ -429,6 +429,7 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
     mb.part = S->alloc<double>((size_t)S->mcd_grid * K * SQC_NMOM(D));
     mb.cand_bits = S->alloc<unsigned long long>((size_t)K * MCD_CAND_CAP);
     mb.cand_pos = S->alloc<unsigned int>((size_t)K * MCD_CAND_CAP);
+    mb.trace = getenv("SQC_MCD_TRACE") ? S->alloc<long long>(8 * 512) : nullptr;
     if (S->rng_mode == SQC_RNG_R_COMPAT) { S->mt_state = S->alloc<uint32_t>(640); S->keybuf = S->alloc<int>(S->N_total, false); }
   } else {
     mle_alloc(*S, a, S->ml);
@@ -629,6 +630,12 @@ int sqc_session_create(const sqc_fit_args* a, int variant, sqc_session** out, ch
 int sqc_session_run(sqc_session* s, char* err, size_t errlen) { return guarded([&] { if (!s) fail(SQC_ERR_BAD_ARG, "null session"); session_run(s); }, err, errlen); }
 int sqc_session_fetch(sqc_session* s, sqc_fit_out* o, char* err, size_t errlen) { return guarded([&] { if (!s) fail(SQC_ERR_BAD_ARG, "null session"); session_fetch(s, o); }, err, errlen); }
 int sqc_session_stats(const sqc_session* s, sqc_run_stats* st) { if (!s || !st) return SQC_ERR_BAD_ARG; *st = s->stats; return SQC_OK; }
+// debug: per-round timeline of the LAST k_mcd launch (only when SQC_MCD_TRACE is set at session creation)
+SQC_API int sqc_session_mcd_trace(sqc_session* s, long long* out, int n_words) {
+  if (!s || !out || !s->mb.trace) return SQC_ERR_BAD_ARG;
+  cudaSetDevice(s->device);
+  return cudaMemcpy(out, s->mb.trace, sizeof(long long) * std::min(n_words, 8 * 512), cudaMemcpyDeviceToHost) == cudaSuccess ? SQC_OK : SQC_ERR_CUDA;
+}
 int sqc_session_profile(sqc_session* s, int on) { if (!s) return SQC_ERR_BAD_ARG; s->profile = on != 0; return SQC_OK; }
 void sqc_session_destroy(sqc_session* s) { delete s; }
 

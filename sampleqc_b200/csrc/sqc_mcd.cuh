@@ -62,7 +62,9 @@ struct McdBufs {
   const int* keys;                     // R-compatible key stream of this call (N_total ints), or null
   unsigned long long call_mix;         // counter-mode key mix for this call
   long long stream_base;               // call * N_total: index of this call's first draw
+  long long* trace;                    // optional per-round timeline (debug): 8 words per round, word 0 of the buffer = rounds
 };
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
 __device__ __forceinline__ unsigned long long dist_bits(double d) { return (unsigned long long)__double_as_longlong(d); }
 
@@ -238,6 +240,9 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
     __syncthreads();
     if (!sh_flag[0]) break;
     ++rounds;
+    const bool tr = mb.trace && b == 0 && tid == 0 && rounds < 500;
+    long long* trow = mb.trace + 8 * rounds;
+    if (tr) { trow[0] = gtimer(); int ph = 0; for (int k = 0; k < K; ++k) ph |= (W->clu[k].phase & 7) << (3 * k); trow[4] = ph; trow[5] = sh_cstart[K]; }
     for (int i = tid; i < K * NM; i += MCD_THREADS) mb.part[((long long)b * K) * NM + i] = 0.0;
     const long long total = sh_cstart[K];
     const long long c0 = total * b / G, c1 = total * (b + 1) / G;
@@ -361,8 +366,10 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
       if (lane == 0 && nn) atomicAdd(&W->cnt_nan[k], (unsigned long long)nn);
       c = cend;
     }
+    if (tr) trow[1] = gtimer();
     __threadfence();
     grid.sync();
+    if (tr) trow[2] = gtimer();
 
     // ---- leaders: per-cluster post-processing -------------------------------------------------
     if (tid == 0) sh_flag[2] = (b < K && W->clu[b].phase != PH_DONE && s.ctl->status == 0) ? 1 : 0;
@@ -512,6 +519,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         }
       }
     }
+    if (tr) { trow[3] = gtimer(); mb.trace[0] = rounds; }
     __threadfence();
     grid.sync();
   }
