@@ -429,6 +429,7 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
     mb.part = S->alloc<double>((size_t)S->mcd_grid * K * SQC_NMOM(D));
     mb.cand_bits = S->alloc<unsigned long long>((size_t)K * MCD_CAND_CAP);
     mb.cand_pos = S->alloc<unsigned int>((size_t)K * MCD_CAND_CAP);
+    mb.bar = S->alloc<GridBar>(1);
     mb.trace = getenv("SQC_MCD_TRACE") ? S->alloc<long long>(8 * 512) : nullptr;
     if (S->rng_mode == SQC_RNG_R_COMPAT) { S->mt_state = S->alloc<uint32_t>(640); S->keybuf = S->alloc<int>(S->N_total, false); }
   } else {

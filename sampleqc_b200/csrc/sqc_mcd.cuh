@@ -53,6 +53,8 @@ struct McdWork {
   unsigned int cand_cnt[SQC_MAXK];
 };
 
+struct GridBar { unsigned int count; unsigned int gen; };
+
 struct McdBufs {
   McdWork* work;
   unsigned int* hist;                  // K x MCD_NB
@@ -62,8 +64,26 @@ struct McdBufs {
   const int* keys;                     // R-compatible key stream of this call (N_total ints), or null
   unsigned long long call_mix;         // counter-mode key mix for this call
   long long stream_base;               // call * N_total: index of this call's first draw
+  GridBar* bar;                        // grid barrier words (count must be 0 at launch)
   long long* trace;                    // optional per-round timeline (debug): 8 words per round, word 0 of the buffer = rounds
 };
+// Sense-reversing grid barrier on two words of global memory (the launch is cooperative, so all CTAs are
+// co-resident).  About half the latency of cooperative_groups' grid.sync() for one CTA per SM.
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void grid_barrier(GridBar* bar, unsigned int nblocks, unsigned int& gen) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned int prev = atomicAdd(&bar->count, 1u);
+    if (prev == nblocks - 1u) { atomicExch(&bar->count, 0u); __threadfence(); atomicAdd(&bar->gen, 1u); }
+    else { while (ld_acquire_u32(&bar->gen) == gen) { } }
+    __threadfence();
+  }
+  ++gen;
+  __syncthreads();
+}
 __device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
 __device__ __forceinline__ unsigned long long dist_bits(double d) { return (unsigned long long)__double_as_longlong(d); }
@@ -155,9 +175,42 @@ __device__ inline void moments_to_loc_scale(const double* S, double h, const dou
 // Cholesky of the scale and its packed inverse (calc_maha_dists :17-21); false -> chol() throws in the reference
 template <int D>
 __device__ inline bool prepare_dist(McdClu& c) {
-  double L[SQC_MAXD * SQC_MAXD], Li[SQC_MAXD * SQC_MAXD];
-  if (!small_chol_inv(c.scale, D, L, Li)) return false;
-  for (int r = 0; r < D; ++r) for (int cc = 0; cc <= r; ++cc) c.linv[r * (r + 1) / 2 + cc] = Li[r + D * cc];
+  double m[D * D], L[D * D], Li[D * D];
+#pragma unroll
+  for (int e = 0; e < D * D; ++e) { m[e] = c.scale[e]; L[e] = 0.0; Li[e] = 0.0; }
+  bool ok = true;
+#pragma unroll
+  for (int cc = 0; cc < D; ++cc) {
+    double sdiag = m[cc + D * cc];
+#pragma unroll
+    for (int k = 0; k < cc; ++k) sdiag -= L[cc + D * k] * L[cc + D * k];
+    if (!(sdiag > 0.0) || !(sdiag < CUDART_INF)) ok = false;
+    const double dd = sqrt(sdiag); L[cc + D * cc] = dd;
+#pragma unroll
+    for (int r = cc + 1; r < D; ++r) {
+      double t = m[r + D * cc];
+#pragma unroll
+      for (int k = 0; k < cc; ++k) t -= L[r + D * k] * L[cc + D * k];
+      L[r + D * cc] = t / dd;
+    }
+  }
+  if (!ok) return false;
+#pragma unroll
+  for (int cc = 0; cc < D; ++cc) {
+    Li[cc + D * cc] = 1.0 / L[cc + D * cc];
+#pragma unroll
+    for (int r = cc + 1; r < D; ++r) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = cc; k < r; ++k) t -= L[r + D * k] * Li[k + D * cc];
+      Li[r + D * cc] = t / L[r + D * r];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < D; ++r)
+#pragma unroll
+    for (int cc = 0; cc <= r; ++cc) c.linv[r * (r + 1) / 2 + cc] = Li[r + D * cc];
+#pragma unroll
   for (int d = 0; d < D; ++d) c.cshift[d] = c.loc[d];
   return true;
 }
@@ -168,7 +221,6 @@ __device__ inline bool prepare_dist(McdClu& c) {
 template <int D>
 __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
   constexpr int NM = SQC_NMOM(D);
-  cg::grid_group grid = cg::this_grid();
   extern __shared__ __align__(16) unsigned char sh_raw[];
   unsigned long long* sh_key = (unsigned long long*)sh_raw;                  // MCD_CAND_CAP (leader sort)
   unsigned int* sh_pos = (unsigned int*)(sh_raw + (size_t)MCD_CAND_CAP * 8); // MCD_CAND_CAP
@@ -178,10 +230,13 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
   __shared__ long long sh_cstart[SQC_MAXK + 1];
   __shared__ long long sh_scan[33];
   __shared__ int sh_flag[4];
+  __shared__ int sh_ph[SQC_MAXK];
+  __shared__ long long sh_n[SQC_MAXK];
   __shared__ unsigned long long sh_u64[2];
 
-  if (!s.ctl->cont) return;                    // uniform across the grid: nobody reaches a grid.sync
+  if (!s.ctl->cont) return;                    // uniform across the grid: nobody reaches a barrier
   const int tid = threadIdx.x, lane = tid & 31, G = gridDim.x, b = blockIdx.x, K = s.K;
+  unsigned int bar_gen = ld_acquire_u32(&mb.bar->gen);
   McdWork* W = mb.work;
 
   // ---- setup: one leader CTA per cluster ----------------------------------------------------
@@ -216,19 +271,22 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
     for (int i = tid; i < MCD_NB; i += MCD_THREADS) mb.hist[k * MCD_NB + i] = 0u;
   }
   __threadfence();
-  grid.sync();
+  grid_barrier(mb.bar, (unsigned)G, bar_gen);
 
   long long rounds = 0;
   for (;;) {
     // ---- active chunk map -------------------------------------------------------------------
+    if (tid < K) { sh_ph[tid] = W->clu[tid].phase; sh_n[tid] = W->clu[tid].n; }      // parallel loads, then a tiny serial prefix
+    if (tid == 32) sh_flag[3] = s.ctl->status;
+    __syncthreads();
     if (tid == 0) {
       long long run = 0, cells = 0, bytes = 0; int any = 0;
-      const bool bad = s.ctl->status != 0;
+      const bool bad = sh_flag[3] != 0;
       for (int k = 0; k < K; ++k) {
         sh_cstart[k] = run;
-        const int ph = W->clu[k].phase;
+        const int ph = sh_ph[k];
         if (ph != PH_DONE && !bad) {
-          const long long n = W->clu[k].n;
+          const long long n = sh_n[k];
           run += (n + MCD_CHUNK - 1) / MCD_CHUNK; any = 1; cells += n;
           const bool keyr = (ph == PH_KEY_HIST || ph == PH_KEY_COLLECT);
           bytes += n * ((ph == PH_KEY_HIST ? 0 : 8 * D) + ((keyr && mb.keys) ? 4 : 0));
@@ -368,7 +426,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
     }
     if (tr) trow[1] = gtimer();
     __threadfence();
-    grid.sync();
+    grid_barrier(mb.bar, (unsigned)G, bar_gen);
     if (tr) trow[2] = gtimer();
 
     // ---- leaders: per-cluster post-processing -------------------------------------------------
@@ -436,7 +494,9 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
           else { sh_key[i] = ~0ull; sh_pos[i] = ~0u; }
         }
         __syncthreads();
+        if (tr) trow[6] = gtimer();
         bitonic_sort_pairs(sh_key, sh_pos, P);
+        if (tr) { trow[7] = gtimer(); trow[5] |= ((long long)ncand << 32); }
         const long long take = cl.h - cl.below;                     // candidates that belong to the h-subset
         const bool ok = (take >= 1 && take <= ncand && W->cand_cnt[k] <= (unsigned)MCD_CAND_CAP);
         const unsigned long long thr = ok ? sh_key[take - 1] : 0ull;
@@ -509,8 +569,10 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
               cl.is_final = go_final ? 1 : 0;
               cl.phase = PH_DIST_HIST; cl.n_hist_rounds = 0;
               if (cl.t_prev) {
+                // the trimmed scatter of the first C-step shrinks the scale (distances grow by up to
+                // 1 / c(p)); later C-steps move the threshold by little.  Wide, cheap window either way.
                 const double t = __longlong_as_double((long long)cl.t_prev);
-                set_dist_window(cl, t * 0.5, t * 2.0);
+                set_dist_window(cl, t * 0.25, t * 8.0);
               } else {
                 set_dist_window(cl, cl.q_chisq * 0.25, cl.q_chisq * 4.0);
               }
@@ -521,7 +583,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
     }
     if (tr) { trow[3] = gtimer(); mb.trace[0] = rounds; }
     __threadfence();
-    grid.sync();
+    grid_barrier(mb.bar, (unsigned)G, bar_gen);
   }
   if (b == 0 && tid == 0) { s.ctl->mcd_passes += rounds; s.ctl->mcd_call += 1; }
 }
