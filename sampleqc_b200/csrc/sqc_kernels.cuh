@@ -10,7 +10,7 @@
 //                 fast_mcd :55-108 for all clusters in lock step — exact order-statistic selection by
 //                 histogram + candidate resolution instead of arma::sort_index, masked moments
 //   k_* (update)  alpha_j solves, p_jk, statistics reduction, control
-//   k_mt_keys     R's Mersenne-Twister stream -> randperm keys
+//   (sqc_mt.cuh)  R's Mersenne-Twister stream -> randperm keys, block-parallel by GF(2) jump-ahead
 #pragma once
 #include <cooperative_groups.h>
 
@@ -503,39 +503,6 @@ __global__ void __launch_bounds__(1024) k_em_control(Dev s) {
 __device__ __forceinline__ uint32_t mt_twist(uint32_t a, uint32_t b) {
   uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
   return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-}
-__global__ void __launch_bounds__(256) k_mt_keys(uint32_t* st, int* out, long long n, long long skip, const Control* ctl) {
-  __shared__ uint32_t bufA[624], bufB[624];
-  if (ctl && !ctl->cont) return;
-  uint32_t* cur = bufA; uint32_t* nxt = bufB;
-  const int tid = threadIdx.x;
-  for (int i = tid; i < 624; i += 256) cur[i] = st[i];
-  int mti = (int)st[624];
-  __syncthreads();
-  long long produced = -skip;          // skip draws first (tests)
-  while (produced < n) {
-    if (mti >= 624) {
-      if (tid < 227) nxt[tid] = cur[tid + 397] ^ mt_twist(cur[tid], cur[tid + 1]);
-      __syncthreads();
-      if (tid < 227) nxt[227 + tid] = nxt[tid] ^ mt_twist(cur[227 + tid], cur[228 + tid]);
-      __syncthreads();
-      if (tid < 169) nxt[454 + tid] = nxt[227 + tid] ^ mt_twist(cur[454 + tid], cur[455 + tid]);
-      if (tid == 169) nxt[623] = nxt[396] ^ mt_twist(cur[623], nxt[0]);
-      __syncthreads();
-      uint32_t* tmp = cur; cur = nxt; nxt = tmp;
-      mti = 0;
-    }
-    const long long room = n - produced;
-    const int m = (int)((room < (long long)(624 - mti)) ? room : (long long)(624 - mti));
-    for (int i = tid; i < m; i += 256) {
-      const long long o = produced + i;
-      if (o >= 0) out[o] = mt_word_to_key(cur[mti + i]);
-    }
-    produced += m; mti += m;
-  }
-  __syncthreads();
-  for (int i = tid; i < 624; i += 256) st[i] = cur[i];
-  if (tid == 0) st[624] = (uint32_t)mti;
 }
 // R set.seed(seed) state initialisation (Appendix A1)
 __global__ void k_mt_seed(uint32_t* st, uint32_t seed) {

@@ -20,6 +20,7 @@
 
 #include "../../include/sampleqc_cuda.h"
 #include "sqc_mcd.cuh"
+#include "sqc_mt.cuh"
 #include "sqc_mle.cuh"
 #include "sqc_xchg.cuh"
 
@@ -174,14 +175,16 @@ struct sqc_session {
   long long N = 0, N_total = 0;
   int em_iters = 0, mcd_iters = 0, rng_mode = 0, track = 0, rank = 0, world = 1;
   double mcd_alpha = 0.5; unsigned seed = 0;
-  cudaStream_t st = nullptr;
+  cudaStream_t st = nullptr, st_rng = nullptr;
+  cudaEvent_t ev_key_ready[2] = {nullptr, nullptr}, ev_key_free[2] = {nullptr, nullptr};
   std::vector<void*> allocs;
   Dev dev{};
   McdBufs mb{};
   MleBufs ml{};
   Xchg xc{};
   uint8_t* z0 = nullptr; double* alpha0 = nullptr; double* gamma0 = nullptr;
-  uint32_t* mt_state = nullptr; int* keybuf = nullptr;
+  int mt_target_blocks = 146;
+  uint32_t* mt_state = nullptr; uint32_t* mt_seq = nullptr; uint32_t* mt_table = nullptr; int* keybuf = nullptr;
   double* o_buf = nullptr; int* o_z = nullptr; int* o_korder = nullptr; OutPtrs optr{};
   size_t o_doubles = 0;
   int mcd_grid = 0, n_sm = 0;
@@ -210,6 +213,8 @@ struct sqc_session {
     if (ev_run0) cudaEventDestroy(ev_run0);
     if (ev_init) cudaEventDestroy(ev_init);
     if (ev_loop) cudaEventDestroy(ev_loop);
+    for (int i = 0; i < 2; ++i) { if (ev_key_ready[i]) cudaEventDestroy(ev_key_ready[i]); if (ev_key_free[i]) cudaEventDestroy(ev_key_free[i]); }
+    if (st_rng && st_rng != st) cudaStreamDestroy(st_rng);
     if (st) cudaStreamDestroy(st);
   }
 };
@@ -227,10 +232,11 @@ struct Launch {
     if (S->profile) {
       if (S->ev_used == S->evs.size()) { sqc_session::Ev e; CK(cudaEventCreate(&e.a)); CK(cudaEventCreate(&e.b)); e.fam = f; S->evs.push_back(e); }
       ev = &S->evs[S->ev_used++]; ev->fam = f;
-      CK(cudaEventRecord(ev->a, S->st));
+      CK(cudaEventRecord(ev->a, stream()));
     }
   }
-  void done() { if (ev) CK(cudaEventRecord(ev->b, S->st)); CK(cudaGetLastError()); }
+  cudaStream_t stream() const { return fam == SQC_KF_RNG ? S->st_rng : S->st; }
+  void done() { if (ev) CK(cudaEventRecord(ev->b, stream())); CK(cudaGetLastError()); }
 };
 
 template <int D> void launch_estep(sqc_session* S, int mode) {
@@ -431,7 +437,17 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
     mb.cand_pos = S->alloc<unsigned int>((size_t)K * MCD_CAND_CAP);
     mb.bar = S->alloc<GridBar>(1);
     mb.trace = getenv("SQC_MCD_TRACE") ? S->alloc<long long>(8 * 512) : nullptr;
-    if (S->rng_mode == SQC_RNG_R_COMPAT) { S->mt_state = S->alloc<uint32_t>(640); S->keybuf = S->alloc<int>(S->N_total, false); }
+    if (S->rng_mode == SQC_RNG_R_COMPAT) {
+      S->mt_state = S->alloc<uint32_t>(640 * 5); S->keybuf = S->alloc<int>(2 * (size_t)S->N_total, false);
+      if (getenv("SQC_RNG_INLINE") && atoi(getenv("SQC_RNG_INLINE"))) S->st_rng = S->st;      // debug: no side stream
+      else CK(cudaStreamCreateWithFlags(&S->st_rng, cudaStreamNonBlocking));
+      if (getenv("SQC_MT_BLOCKS")) S->mt_target_blocks = std::max(1, atoi(getenv("SQC_MT_BLOCKS")));
+      for (int i = 0; i < 2; ++i) { CK(cudaEventCreateWithFlags(&S->ev_key_ready[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&S->ev_key_free[i], cudaEventDisableTiming)); }
+      S->mt_seq = S->alloc<uint32_t>(MT_SEQ_WORDS + (size_t)(SQC_MT_JUMP_ROWS + 2) * MT_N);
+      S->mt_table = S->alloc<uint32_t>((size_t)SQC_MT_JUMP_ROWS * MT_N, false);
+      CK(cudaMemcpyAsync(S->mt_table, sqc_mt_jump_table, sizeof sqc_mt_jump_table, cudaMemcpyHostToDevice, S->st));
+      CK(cudaFuncSetAttribute(k_mt_jump, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_SMEM));
+    }
   } else {
     mle_alloc(*S, a, S->ml);
   }
@@ -444,18 +460,60 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
   return up.release();
 }
 
-void gen_keys(sqc_session* S, int call) {
-  // one update_beta_scale_k call consumes exactly N_total draws
-  if (S->rng_mode == SQC_RNG_R_COMPAT) {
-    Launch L(S, SQC_KF_RNG);
-    k_mt_keys<<<1, 256, 0, S->st>>>(S->mt_state, S->keybuf, S->N_total, 0, S->dev.ctl);
-    L.done();
-    S->mb.keys = S->keybuf;
-  } else {
-    S->mb.keys = nullptr;
+// n keys of R's stream: reads the state st_in (625 words), leaves the state after the n draws in st_out.
+// Waves of at most SQC_MT_JUMP_ROWS + 1 blocks; each wave = one sequential 33-chunk kernel + one
+// block-parallel kernel; tmp[2] hold the states between waves.
+void mt_generate(cudaStream_t stream, const uint32_t* st_in, uint32_t* st_out, uint32_t* tmp0, uint32_t* tmp1, uint32_t* seq,
+                 const uint32_t* table, int* out, long long n, const Control* ctl, sqc_session* S, int target_blocks = 146) {
+  long long done = 0; int w = 0;
+  const uint32_t* cur = st_in;
+  if (n <= 0) { CK(cudaMemcpyAsync(st_out, st_in, 625 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream)); return; }
+  // block length = mult * 110 chunks; about target_blocks blocks per call
+  int mult = (int)std::max<long long>(1, std::min<long long>(SQC_MT_JUMP_ROWS / 2, (n / MT_BLOCK_WORDS + target_blocks / 2) / target_blocks));
+  const long long blk_words = MT_BLOCK_WORDS * mult;
+  const long long wave_words = (long long)(SQC_MT_JUMP_ROWS / mult + 1) * blk_words;
+  while (done < n) {
+    const long long m = std::min(n - done, wave_words - MT_N);     // a wave serves this many draws whatever mti is
+    const bool last = done + m >= n;
+    uint32_t* nxt = last ? st_out : ((w & 1) ? tmp1 : tmp0);
+    const int nb = (int)((MT_N + m + blk_words - 1) / blk_words);  // upper bound on the blocks touched (mti <= 624)
+    if (S) { Launch L(S, SQC_KF_RNG); k_mt_seq<<<1, 256, 0, stream>>>(cur, seq, ctl); L.done(); }
+    else k_mt_seq<<<1, 256, 0, stream>>>(cur, seq, ctl);
+    uint32_t* windows = seq + MT_SEQ_WORDS;                        // (SQC_MT_JUMP_ROWS + 1) x 624 behind the sequence
+    if (nb > 1) {
+      if (S) { Launch L(S, SQC_KF_RNG); k_mt_jump<<<nb - 1, MT_THREADS, MT_SMEM, stream>>>(cur, seq, table, windows, m, mult, ctl); L.done(); }
+      else k_mt_jump<<<nb - 1, MT_THREADS, MT_SMEM, stream>>>(cur, seq, table, windows, m, mult, ctl);
+    }
+    if (S) { Launch L(S, SQC_KF_RNG); k_mt_gen<<<nb, MT_GEN_THREADS, 0, stream>>>(cur, nxt, seq, windows, out + done, m, mult, ctl); L.done(); }
+    else k_mt_gen<<<nb, MT_GEN_THREADS, 0, stream>>>(cur, nxt, seq, windows, out + done, m, mult, ctl);
+    cur = nxt; done += m; ++w;
   }
+}
+
+// Keys of update_beta_scale_k call `call` (every call consumes exactly N_total draws).
+// They do not depend on the data, so they are produced on a side stream, up to two calls ahead of the EM
+// loop; state_after[c] lives in slot c % 3 so that the state after the last EXECUTED call survives.
+void enqueue_keys(sqc_session* S, int call) {
+  if (S->rng_mode != SQC_RNG_R_COMPAT) return;
+  const int kb = call & 1;
+  CK(cudaStreamWaitEvent(S->st_rng, S->ev_key_free[kb], 0));
+  uint32_t* base = S->mt_state;
+  mt_generate(S->st_rng, base + 640 * ((call + 2) % 3), base + 640 * (call % 3), base + 640 * 3, base + 640 * 4, S->mt_seq, S->mt_table,
+              S->keybuf + (size_t)kb * S->N_total, S->N_total, S->dev.ctl, S, S->mt_target_blocks);
+  CK(cudaEventRecord(S->ev_key_ready[kb], S->st_rng));
+}
+void use_keys(sqc_session* S, int call) {
+  if (S->rng_mode == SQC_RNG_R_COMPAT) {
+    CK(cudaStreamWaitEvent(S->st, S->ev_key_ready[call & 1], 0));
+    S->mb.keys = S->keybuf + (size_t)(call & 1) * S->N_total;
+  } else S->mb.keys = nullptr;
   S->mb.call_mix = counter_call_mix(S->seed, 0u);
   S->mb.stream_base = (long long)call * S->N_total;
+}
+void release_keys(sqc_session* S, int call) {
+  if (S->rng_mode != SQC_RNG_R_COMPAT) return;
+  CK(cudaEventRecord(S->ev_key_free[call & 1], S->st));
+  if (call + 2 <= S->em_iters) enqueue_keys(S, call + 2);
 }
 
 void run_robust(sqc_session* S) {
@@ -469,7 +527,13 @@ void run_robust(sqc_session* S) {
   CK(cudaMemsetAsync(s.sigma, 0, (size_t)S->K * S->D * S->D * sizeof(double), S->st));
   CK(cudaMemsetAsync(s.like1, 0, (size_t)(std::max(S->em_iters, 0) + 1) * sizeof(double), S->st));
   CK(cudaMemsetAsync(s.like2, 0, (size_t)(std::max(S->em_iters, 0) + 1) * sizeof(double), S->st));
-  if (S->mt_state) { Launch L(S, SQC_KF_RNG); k_mt_seed<<<1, 32, 0, S->st>>>(S->mt_state, S->seed); L.done(); }   // set_seed_cpp, :475
+  if (S->mt_state) {                                                                    // set_seed_cpp, :475
+    CK(cudaEventRecord(S->ev_key_free[0], S->st)); CK(cudaEventRecord(S->ev_key_free[1], S->st));   // after k_ctl_reset
+    CK(cudaStreamWaitEvent(S->st_rng, S->ev_key_free[0], 0));
+    { Launch L(S, SQC_KF_RNG); k_mt_seed<<<1, 32, 0, S->st_rng>>>(S->mt_state + 640 * 2, S->seed); L.done(); }
+    enqueue_keys(S, 0);
+    if (S->em_iters >= 1) enqueue_keys(S, 1);
+  }
   const int nsb = (J + 31) / 32;
   auto post_stats = [&]() {
     Launch L(S, SQC_KF_UPDATE); k_post_stats<<<nsb + 1, 1024, 0, S->st>>>(s, nsb); L.done();
@@ -477,8 +541,9 @@ void run_robust(sqc_session* S) {
   };
   auto m_step = [&](int call, int like) {
     do_partition(S, like);
-    gen_keys(S, call);
+    use_keys(S, call);
     do_mcd(S);
+    release_keys(S, call);
     { Launch L(S, SQC_KF_UPDATE); k_derive<<<1, 32, 0, S->st>>>(s); L.done(); }
   };
   // initial labelling: p_jk (:481), alpha_j (:482), beta_k / Sigma_k (:483)
@@ -508,6 +573,7 @@ void session_run(sqc_session* S) {
   else mle_run(S);
   CK(cudaMemcpyAsync(&S->h_ctl, S->dev.ctl, sizeof(Control), cudaMemcpyDeviceToHost, S->st));
   CK(cudaStreamSynchronize(S->st));
+  if (S->st_rng) CK(cudaStreamSynchronize(S->st_rng));
   S->ran = true;
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, S->ev_run0, S->ev_init)); S->stats.init_ms = ms;
@@ -575,7 +641,7 @@ void session_fetch(sqc_session* S, sqc_fit_out* o) {
   }
   if (S->mt_state) {
     uint32_t st[625];
-    CK(cudaMemcpyAsync(st, S->mt_state, sizeof st, cudaMemcpyDeviceToHost, S->st));
+    CK(cudaMemcpyAsync(st, S->mt_state + 640 * (S->h_ctl.iter % 3), sizeof st, cudaMemcpyDeviceToHost, S->st));   // state after call n_iter
     CK(cudaStreamSynchronize(S->st));
     o->rng_state[0] = (int32_t)st[624];
     for (int i = 0; i < 624; ++i) o->rng_state[i + 1] = (int32_t)st[i];
@@ -713,12 +779,24 @@ int sqc_device_rkeys(uint32_t seed, int64_t skip, int32_t* keys_out, int64_t n, 
   return guarded([&] {
     if (!keys_out || n < 0 || skip < 0) fail(SQC_ERR_BAD_ARG, "bad arguments");
     int d; select_device(device, &d);
-    uint32_t* st = nullptr; int* out = nullptr;
-    CK(cudaMalloc((void**)&st, 640 * sizeof(uint32_t))); CK(cudaMalloc((void**)&out, (size_t)std::max<int64_t>(n, 1) * sizeof(int)));
-    k_mt_seed<<<1, 32>>>(st, seed);
-    k_mt_keys<<<1, 256>>>(st, out, n, skip, nullptr);
-    cudaError_t e = cudaMemcpy(keys_out, out, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost);
-    cudaFree(st); cudaFree(out); CK(e);
+    uint32_t *st = nullptr, *st2 = nullptr, *st3 = nullptr, *st4 = nullptr, *seq = nullptr, *table = nullptr; int* out = nullptr;
+    auto cleanup = [&] { cudaFree(st); cudaFree(st2); cudaFree(st3); cudaFree(st4); cudaFree(seq); cudaFree(table); cudaFree(out); };
+    try {
+      CK(cudaMalloc((void**)&st, 640 * sizeof(uint32_t))); CK(cudaMalloc((void**)&st2, 640 * sizeof(uint32_t)));
+      CK(cudaMalloc((void**)&st3, 640 * sizeof(uint32_t))); CK(cudaMalloc((void**)&st4, 640 * sizeof(uint32_t)));
+      CK(cudaMalloc((void**)&seq, (MT_SEQ_WORDS + (size_t)(SQC_MT_JUMP_ROWS + 2) * MT_N) * sizeof(uint32_t))); CK(cudaMalloc((void**)&table, sizeof sqc_mt_jump_table));
+      CK(cudaMalloc((void**)&out, (size_t)std::max<int64_t>(std::max(n, skip), 1) * sizeof(int)));
+      CK(cudaMemcpy(table, sqc_mt_jump_table, sizeof sqc_mt_jump_table, cudaMemcpyHostToDevice));
+      CK(cudaFuncSetAttribute(k_mt_jump, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_SMEM));
+      k_mt_seed<<<1, 32>>>(st, seed);
+      // skipped draws are generated and discarded as a separate call, so the state hand-over is exercised
+      // target_blocks = 1000: the shortest blocks, so that small requests still exercise the jump table
+      if (skip > 0) { mt_generate(0, st, st2, st3, st4, seq, table, out, skip, nullptr, nullptr, 1000); std::swap(st, st2); }
+      mt_generate(0, st, st2, st3, st4, seq, table, out, n, nullptr, nullptr, n > 2000000 ? 20 : 1000);
+      CK(cudaGetLastError());
+      CK(cudaMemcpy(keys_out, out, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+    } catch (...) { cleanup(); throw; }
+    cleanup();
   }, err, errlen);
 }
 

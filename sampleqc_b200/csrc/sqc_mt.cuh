@@ -1,0 +1,114 @@
+// sqc_mt.cuh — R's Mersenne-Twister key stream (SQC_RNG_R_COMPAT) generated block-parallel.
+//
+// One update_beta_scale_k call consumes N_total draws of R's stream.  MT19937 is a
+// sequential recurrence, but its state transition is linear over GF(2): the window 624 words further
+// down the stream by e words is  x[e + j] = XOR_{i in g_{e-1}} x[i + j + 1]  with g_e = x^e mod phi
+// (scripts/mt_jump_tables.py derives and verifies the polynomials; sqc_mt_jump.inc holds g_{pB-1}).
+//   k_mt_seq     one CTA: the 33 chunks (20 592 words) that follow the current state
+//   k_mt_jump    CTA p: correlate that sequence with row p*mult-1 of the table -> the window at block p
+//   k_mt_gen     CTA p: run the recurrence from that window for up to mult*110 chunks, temper, convert to
+//                randperm keys (key = (int) Rf_runif(0, RAND_MAX)) and store them at their draw position.
+// State layout (device, 625 words) = R's .Random.seed payload: mt[624] then mti.
+#pragma once
+#include "sqc_kernels.cuh"
+#include "sqc_mt_jump.inc"
+
+namespace sqc {
+
+constexpr int MT_N = 624;
+constexpr int MT_SEQ_CHUNKS = 33;                         // 33 * 624 = 20 592 >= 19 937 + 624 + 1
+constexpr int MT_SEQ_WORDS = MT_SEQ_CHUNKS * MT_N;
+constexpr int MT_BLOCK_CHUNKS = SQC_MT_CHUNKS_PER_BLOCK;  // 110
+constexpr long long MT_BLOCK_WORDS = (long long)MT_BLOCK_CHUNKS * MT_N;
+constexpr int MT_THREADS = 640;
+constexpr size_t MT_SMEM = (size_t)(MT_SEQ_WORDS + MT_N) * sizeof(uint32_t);
+
+// one regeneration: nxt[0..623] from cur[0..623]  (dependency distance 227 -> three wavefronts)
+__device__ __forceinline__ void mt_regen(const uint32_t* cur, uint32_t* nxt, int tid) {
+  if (tid < 227) nxt[tid] = cur[tid + 397] ^ mt_twist(cur[tid], cur[tid + 1]);
+  __syncthreads();
+  if (tid < 227) nxt[227 + tid] = nxt[tid] ^ mt_twist(cur[227 + tid], cur[228 + tid]);
+  __syncthreads();
+  if (tid < 169) nxt[454 + tid] = nxt[227 + tid] ^ mt_twist(cur[454 + tid], cur[455 + tid]);
+  if (tid == 169) nxt[623] = nxt[396] ^ mt_twist(cur[623], nxt[0]);
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256) k_mt_seq(const uint32_t* st, uint32_t* seq, const Control* ctl) {
+  __shared__ uint32_t bufA[MT_N], bufB[MT_N];
+  if (ctl && !ctl->cont) return;
+  const int tid = threadIdx.x;
+  uint32_t* cur = bufA; uint32_t* nxt = bufB;
+  for (int i = tid; i < MT_N; i += 256) { cur[i] = st[i]; seq[i] = st[i]; }
+  __syncthreads();
+  for (int c = 1; c < MT_SEQ_CHUNKS; ++c) {
+    mt_regen(cur, nxt, tid);
+    for (int i = tid; i < MT_N; i += 256) seq[c * MT_N + i] = nxt[i];
+    uint32_t* t = cur; cur = nxt; nxt = t;
+  }
+}
+
+// window of block p = 1 .. nb-1 (row p * mult - 1 of the jump table correlated with the 33-chunk sequence)
+__global__ void __launch_bounds__(MT_THREADS) k_mt_jump(const uint32_t* st_in, const uint32_t* seq, const uint32_t* table, uint32_t* windows,
+                                                        long long n, int mult, const Control* ctl) {
+  extern __shared__ uint32_t sh_mt[];
+  uint32_t* sseq = sh_mt;                         // MT_SEQ_WORDS
+  uint32_t* stab = sseq + MT_SEQ_WORDS;           // 624 table words
+  if (ctl && !ctl->cont) return;
+  const int tid = threadIdx.x, p = blockIdx.x + 1;
+  const long long u_end = (long long)st_in[MT_N] + n;
+  if ((long long)p * MT_BLOCK_WORDS * mult >= u_end) return;          // block past the last draw
+  for (int i = tid; i < MT_SEQ_WORDS; i += MT_THREADS) sseq[i] = seq[i];
+  for (int i = tid; i < MT_N; i += MT_THREADS) stab[i] = table[(size_t)(p * mult - 1) * MT_N + i];
+  __syncthreads();
+  if (tid < MT_N) {
+    uint32_t acc = 0;
+    const uint32_t* sj = sseq + tid + 1;
+    for (int w = 0; w < MT_N; ++w) {
+      const uint32_t bits = stab[w];
+      const uint32_t* sw = sj + 32 * w;
+#pragma unroll
+      for (int b = 0; b < 32; ++b) if ((bits >> b) & 1u) acc ^= sw[b];
+    }
+    windows[(size_t)p * MT_N + tid] = acc;
+  }
+}
+
+// One 256-thread CTA per block runs the recurrence in shared memory (three 227-wide wavefronts per chunk), tempers
+// every word of the current chunk, converts it to a randperm key and stores it at its draw position.  Positions u
+// (counted from the start of the current state's chunk) in [mti, mti + n) are draws.  `mult`: a block is
+// mult * 110 chunks long.  (A single warp per block, tried first, is latency-bound at ~2 us per chunk.)
+constexpr int MT_GEN_THREADS = 256;
+__global__ void __launch_bounds__(MT_GEN_THREADS) k_mt_gen(const uint32_t* st_in, uint32_t* st_out, const uint32_t* seq, const uint32_t* windows,
+                                                           int* out, long long n, int mult, const Control* ctl) {
+  __shared__ uint32_t bufA[MT_N], bufB[MT_N];
+  if (ctl && !ctl->cont) return;
+  const int tid = threadIdx.x, p = blockIdx.x;
+  const long long mti = (long long)st_in[MT_N];
+  const long long u_end = mti + n, u_last = u_end - 1, q_last = u_last / MT_N;
+  const long long blk_chunks = (long long)MT_BLOCK_CHUNKS * mult;
+  if ((long long)p * blk_chunks * MT_N >= u_end) return;
+  const uint32_t* src = (p == 0) ? seq : windows + (size_t)p * MT_N;
+  uint32_t* cur = bufA; uint32_t* nxt = bufB;
+  for (int i = tid; i < MT_N; i += MT_GEN_THREADS) cur[i] = src[i];
+  __syncthreads();
+  for (long long c = 0; c < blk_chunks; ++c) {
+    const long long q = (long long)p * blk_chunks + c;
+    const long long u0 = q * MT_N;
+    if (u0 >= u_end) break;
+    const long long o0 = u0 - mti;                // draw index of word 0 of this chunk
+    for (int i = tid; i < MT_N; i += MT_GEN_THREADS) {
+      const long long o = o0 + i;
+      const uint32_t a = cur[i];
+      if (o >= 0 && o < n) out[o] = mt_word_to_key(a);
+      if (q == q_last) st_out[i] = a;             // R's state after the call: this chunk, mti' = offset past the last draw
+    }
+    if (q == q_last && tid == 0) st_out[MT_N] = (uint32_t)(u_last - u0 + 1);
+    if ((c + 1 < blk_chunks) && (u0 + MT_N < u_end)) {
+      mt_regen(cur, nxt, tid);
+      uint32_t* t = cur; cur = nxt; nxt = t;
+    }
+  }
+}
+
+}  // namespace sqc

@@ -107,6 +107,12 @@ def test_device_special_functions(oracle):
         np.testing.assert_allclose(api.device_qchisq(ps, df), chi2.ppf(ps, df), rtol=5e-13)
     np.testing.assert_array_equal(api.device_rkeys(7, 0, 5000), oracle.rkeys(7, 0, 5000))
     np.testing.assert_array_equal(api.device_rkeys(0, 1500, 3000), oracle.rkeys(0, 1500, 3000))
+    # several 68 640-word blocks: exercises the GF(2) jump-ahead table and the state hand-over between calls
+    np.testing.assert_array_equal(api.device_rkeys(1, 100_000, 400_000), oracle.rkeys(1, 100_000, 400_000))
+    # long blocks (the production setting: ~16 blocks of several hundred chunks per call)
+    np.testing.assert_array_equal(api.device_rkeys(2, 77_777, 3_000_000), oracle.rkeys(2, 77_777, 3_000_000))
+    np.testing.assert_array_equal(api.device_rkeys(5, 623, 1), oracle.rkeys(5, 623, 1))
+    np.testing.assert_array_equal(api.device_rkeys(5, 624, 625), oracle.rkeys(5, 624, 625))
 
 
 def test_outlier_mask_matches_oracle(oracle):
