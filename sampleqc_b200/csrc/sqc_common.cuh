@@ -25,6 +25,7 @@
 #define SQC_D_SINGULAR 5
 #define SQC_D_NAN 6
 #define SQC_D_SELECT 7
+#define SQC_D_PEER 8          // multi-GPU: another rank failed
 
 namespace sqc {
 

@@ -57,6 +57,7 @@ const char* device_status_message(int st) {
     case SQC_ERR_SINGULAR: return "inv(): matrix is singular";
     case SQC_ERR_NAN: return "sort_index(): detected NaN (robust_cpp.cpp:50)";
     case SQC_ERR_SELECT: return "exact selection could not be resolved (too many exactly tied distances)";
+    case SQC_D_PEER: return "another rank of the multi-GPU fit reported an error";
     default: return "device error";
   }
 }
@@ -184,6 +185,7 @@ struct sqc_session {
   Xchg xc{};
   uint8_t* z0 = nullptr; double* alpha0 = nullptr; double* gamma0 = nullptr;
   int mt_target_blocks = 146;
+  unsigned long long* xg_gather = nullptr; double* xg_vec = nullptr;
   uint32_t* mt_state = nullptr; uint32_t* mt_seq = nullptr; uint32_t* mt_table = nullptr; int* keybuf = nullptr;
   double* o_buf = nullptr; int* o_z = nullptr; int* o_korder = nullptr; OutPtrs optr{};
   size_t o_doubles = 0;
@@ -223,6 +225,10 @@ namespace {
 void mle_alloc(sqc_session&, const sqc_fit_args*, sqc::MleBufs&);
 void mle_run(sqc_session*);
 void mle_fetch(sqc_session*, sqc_fit_out*);
+void xchg_allreduce_host(sqc_session* S, double* buf, int n);
+void xchg_cluster_layout(sqc_session* S, Dev& s);
+void xchg_allreduce_like(sqc_session* S, Dev& s);
+void xchg_allreduce_mle(sqc_session* S, Dev& s, MleBufs& m, int ll_only, double* like, int slot);
 
 // per-launch accounting: count every launch, time it with events when profiling is on
 struct Launch {
@@ -272,10 +278,65 @@ template <int D> void launch_init_passes(sqc_session* S) {
   const Dev& s = S->dev;
   { Launch L(S, SQC_KF_INIT); k_colsum<D><<<s.T, EST_THREADS, 0, S->st>>>(s); L.done(); }
   { Launch L(S, SQC_KF_INIT); k_colmean<<<1, 1024, 0, S->st>>>(s); L.done(); }
-  if (S->world > 1) xchg_allreduce_host(S->xc, S->st, s.mu0, s.D);
+  if (S->world > 1) xchg_allreduce_host(S, s.mu0, s.D);
   { Launch L(S, SQC_KF_INIT); k_colmean_finish<<<1, 32, 0, S->st>>>(s); L.done(); }
   { Launch L(S, SQC_KF_INIT); k_centre<D><<<s.T, EST_THREADS, 0, S->st>>>(s); L.done(); }
   { Launch L(S, SQC_KF_INIT); k_init_alpha<<<(s.J * 32 + 255) / 256, 256, 0, S->st>>>(s); L.done(); }
+}
+
+// ---- host-stream level exchanges (multi-GPU) -----------------------------------------------------
+// after k_post_stats: global cluster sizes and the key-stream offset of the local segment of every cluster
+// (the stream of one call runs over clusters in order, inside a cluster in cell order,
+// and lower ranks hold the lower cell indices)
+__global__ void k_layout_finish(Dev s, XchgDev x, const unsigned long long* gathered) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    long long run = 0;
+    for (int k = 0; k < s.K; ++k) {
+      long long tot = 0, before = 0;
+      for (int r = 0; r < x.world; ++r) { const long long v = (long long)gathered[r * s.K + k]; tot += v; if (r < x.rank) before += v; }
+      s.clu_n_glob[k] = tot; s.clu_prefix[k] = run + before; run += tot;
+    }
+  }
+}
+// before k_em_control: the tile partial sums become global sums (slot 0 of t_ll1 / t_ll2), z_delta, n_zero and
+// the status are agreed on.  vec = {like_1, like_2, z_delta, n_zero, status flags...}
+__global__ void __launch_bounds__(1024) k_like_local(Dev s, double* vec) {
+  __shared__ double sh[32];
+  if (!s.ctl->cont) return;
+  double a1 = 0.0, a2 = 0.0;
+  for (int t = threadIdx.x; t < s.T; t += 1024) { a1 += s.t_ll1[t]; a2 += s.t_ll2[t]; }
+  const double r1 = block_sum<1024>(a1, sh);
+  const double r2 = block_sum<1024>(a2, sh);
+  if (threadIdx.x == 0) {
+    vec[0] = r1; vec[1] = r2; vec[2] = (double)s.ctl->z_delta; vec[3] = (double)s.ctl->n_zero;
+    vec[4] = (double)s.ctl->status;                     // summed only to detect "somebody failed"; the code itself stays on its rank
+  }
+}
+__global__ void k_like_global(Dev s, const double* vec, const double* loc) {
+  if (!s.ctl->cont) return;
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    // the single-GPU k_em_control sums t_ll1 / t_ll2 over tiles: leave the global sums in tile 0 and zero the rest
+    s.ctl->z_delta = (int)vec[2];
+    if (vec[4] != 0.0 && s.ctl->status == 0) s.ctl->status = SQC_D_PEER;            // a peer failed (its own message says why)
+  }
+  for (int t = threadIdx.x + blockIdx.x * blockDim.x; t < s.T; t += blockDim.x * gridDim.x) { s.t_ll1[t] = (t == 0) ? vec[0] : 0.0; s.t_ll2[t] = (t == 0) ? vec[1] : 0.0; }
+}
+
+void xchg_allreduce_host(sqc_session* S, double* buf, int n) {
+  Launch L(S, SQC_KF_UPDATE); k_xchg_sum_f64<<<1, 256, 0, S->st>>>(S->xc.dev, XCHG_CH_HOST + 0, buf, n, nullptr); L.done();
+}
+void xchg_cluster_layout(sqc_session* S, Dev& s) {
+  { Launch L(S, SQC_KF_UPDATE); k_xchg_gather_u64<<<1, 256, 0, S->st>>>(S->xc.dev, XCHG_CH_HOST + 1, (const unsigned long long*)s.clu_n, S->xg_gather, s.K, &s.ctl->cont); L.done(); }
+  { Launch L(S, SQC_KF_UPDATE); k_layout_finish<<<1, 32, 0, S->st>>>(s, S->xc.dev, S->xg_gather); L.done(); }
+}
+void xchg_allreduce_like(sqc_session* S, Dev& s) {
+  { Launch L(S, SQC_KF_UPDATE); k_like_local<<<1, 1024, 0, S->st>>>(s, S->xg_vec); L.done(); }
+  { Launch L(S, SQC_KF_UPDATE); k_xchg_sum_f64<<<1, 256, 0, S->st>>>(S->xc.dev, XCHG_CH_HOST + 2, S->xg_vec, 5, &s.ctl->cont); L.done(); }
+  { Launch L(S, SQC_KF_UPDATE); k_like_global<<<8, 256, 0, S->st>>>(s, S->xg_vec, nullptr); L.done(); }
+}
+void xchg_allreduce_mle(sqc_session* S, Dev& s, MleBufs& m, int ll_only, double* like, int slot) {
+  if (!ll_only) { Launch L(S, SQC_KF_UPDATE); k_xchg_sum_f64<<<1, 256, 0, S->st>>>(S->xc.dev, XCHG_CH_HOST + 2, m.mom, s.K * SQC_NMOM(s.D), nullptr); L.done(); }
+  if (slot >= 0) { Launch L(S, SQC_KF_UPDATE); k_xchg_sum_f64<<<1, 256, 0, S->st>>>(S->xc.dev, XCHG_CH_HOST + 3, like + slot, 1, nullptr); L.done(); }
 }
 
 #define SQC_CASE_ESTEP(DD) case DD: launch_estep<DD>(S, mode); break;
@@ -411,7 +472,11 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
       CK(cudaStreamSynchronize(S->st));
     }
   }
-  if (S->world > 1) xchg_open(S->xc, S->device, S->rank, S->world, a->peer_handles);
+  if (S->world > 1) {
+    try { xchg_open(S->xc, S->device, S->rank, S->world, a->peer_handles); }
+    catch (const std::exception& e) { fail(SQC_ERR_COMM, "%s", e.what()); }
+    S->xg_gather = S->alloc<unsigned long long>((size_t)XCHG_MAX_WORLD * SQC_MAXK); S->xg_vec = S->alloc<double>(16);
+  }
 
   if (variant == SQC_VARIANT_ROBUST) {
     S->z0 = S->alloc<uint8_t>(N, false);
@@ -433,8 +498,12 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
     mb.work = S->alloc<McdWork>(1);
     mb.hist = S->alloc<unsigned int>((size_t)K * MCD_NB);
     mb.part = S->alloc<double>((size_t)S->mcd_grid * K * SQC_NMOM(D));
-    mb.cand_bits = S->alloc<unsigned long long>((size_t)K * MCD_CAND_CAP);
-    mb.cand_pos = S->alloc<unsigned int>((size_t)K * MCD_CAND_CAP);
+    const size_t nreg = (size_t)K * S->mcd_grid * MCD_WARPS;                 // candidate regions: one per (cluster, CTA, warp)
+    mb.cand_bits = S->alloc<unsigned long long>(nreg * MCD_CAPW, false);
+    mb.cand_pos = S->alloc<unsigned int>(nreg * MCD_CAPW, false);
+    mb.cand_r = S->alloc<double>(nreg * MCD_CAPW * D, false);
+    mb.cand_cnt = S->alloc<unsigned int>(nreg);
+    mb.xc = S->xc.dev;
     mb.bar = S->alloc<GridBar>(1);
     mb.trace = getenv("SQC_MCD_TRACE") ? S->alloc<long long>(8 * 512) : nullptr;
     if (S->rng_mode == SQC_RNG_R_COMPAT) {
@@ -594,7 +663,7 @@ void session_run(sqc_session* S) {
   } else {
     S->stats.family_bytes[SQC_KF_MLE_PASS] = (double)(2 * it + 1) * pass;
   }
-  if (S->h_ctl.status != 0) fail(S->h_ctl.status, "%s", device_status_message(S->h_ctl.status));
+  if (S->h_ctl.status != 0) fail(S->h_ctl.status == SQC_D_PEER ? SQC_ERR_COMM : S->h_ctl.status, "%s", device_status_message(S->h_ctl.status));
 }
 
 void reorder_track(const sqc_session* S, sqc_fit_out* o, const int* korder) {
@@ -751,7 +820,13 @@ int sqc_outlier_maha(const sqc_maha_args* a, double* maha, uint8_t* outlier, dou
   }, err, errlen);
 }
 
-int sqc_xchg_export(int device, void* handle_out, char* err, size_t errlen) { return guarded([&] { int d; select_device(device, &d); xchg_export(d, handle_out); }, err, errlen); }
+int sqc_xchg_export(int device, void* handle_out, char* err, size_t errlen) {
+  return guarded([&] {
+    if (!handle_out) fail(SQC_ERR_BAD_ARG, "null handle buffer");
+    int d; select_device(device, &d);
+    try { xchg_export(d, handle_out); } catch (const std::exception& e) { fail(SQC_ERR_COMM, "%s", e.what()); }
+  }, err, errlen);
+}
 int sqc_xchg_release(int device) { return xchg_release(device); }
 
 int sqc_abi_version(void) { return SQC_ABI_VERSION; }

@@ -11,30 +11,39 @@
 //            space; cells under the window are only counted.
 //   COLLECT  cells strictly under the bin that holds the h-th smallest key are accumulated into
 //            shifted moments (count, sum, upper-triangular scatter); the cells of that one bin are
-//            appended to a small candidate list, which the cluster's leader CTA sorts by (key, position)
-//            to take exactly the remaining members — ties resolved towards the lower position, the
-//            repo's definition of the reference's unspecified tie order.
+//            appended, without atomics, to per-warp candidate regions (deterministic order).  The
+//            cluster's leader CTA bins the candidates once more (4096 fine bins inside the bin), takes
+//            every candidate under the fine bin that holds the h-th key, and sorts only the handful
+//            inside it by (key, rank, position) — ties resolved towards the lower cell index, the repo's
+//            definition of the reference's unspecified tie order.
+// Multi-GPU (cells sharded by sample): the leaders of all ranks exchange the histogram, the fine
+// histogram, the tie candidates and the moments through peer memory (sqc_xchg.cuh) and combine them
+// in rank order, so every rank walks through bit-identical cluster states.
 // A cluster walks through  KEY_HIST -> KEY_COLLECT -> [DIST_HIST -> DIST_COLLECT]* -> final
 // DIST_HIST -> DIST_COLLECT(q only) -> DONE; all clusters share every streaming round.
 // Between rounds: grid.sync, the K leader CTAs do the tiny per-cluster post-processing
 // (histogram scan / candidate sort / moments -> loc, scale, det, Cholesky, loop test :84), grid.sync.
 #pragma once
 #include "sqc_kernels.cuh"
+#include "sqc_xchg.cuh"
 
 namespace sqc {
 
 constexpr int MCD_THREADS = 512;                     // one fat CTA per SM: one histogram per SM, 128 registers per thread
-constexpr int MCD_CPT = 8;                           // cells per thread per chunk (four 128-bit loads per column)
-constexpr int MCD_CHUNK = MCD_THREADS * MCD_CPT;
-constexpr int MCD_NB = 4096;                         // histogram bins per window
-constexpr int MCD_CAND_CAP = 8192;                   // candidates per cluster (bitonic-sorted in smem)
-constexpr size_t MCD_SMEM = (size_t)MCD_CAND_CAP * 12 + 1024;   // sort keys (u64) + positions (u32)
+constexpr int MCD_WARPS = MCD_THREADS / 32;
+constexpr int MCD_NB = 4096;                         // histogram bins per window (and fine bins per candidate bin)
+constexpr int MCD_CAND_CAP = 8192;                   // a bin holding more cells than this is refined by another HIST round
+constexpr int MCD_CAPW = 32;                         // candidate slots per (CTA, warp, cluster) region
+constexpr int MCD_TINY = 512;                        // tie candidates (inside one fine bin) over all ranks
+constexpr size_t MCD_SMEM = (size_t)(MCD_NB + 8) * 4 + (size_t)MCD_TINY * 20 + 256;
+template <int D> struct McdCfg { static constexpr int CPT = (D <= 4) ? 8 : 4; static constexpr int CHUNK = MCD_THREADS * CPT; };
 
 enum { PH_KEY_HIST = 0, PH_KEY_COLLECT = 1, PH_DIST_HIST = 2, PH_DIST_COLLECT = 3, PH_DONE = 4 };
 
 struct McdClu {
-  long long n, h, off, prefix;         // cells, subset size, segment offset in rs, key-stream offset
-  long long below;                     // cells strictly under the candidate bin (set by the HIST post)
+  long long n, h, off, prefix;         // GLOBAL cells and subset size; local segment offset in rs; key-stream offset of the local segment
+  long long n_loc;                     // cells of this cluster on this GPU
+  long long below;                     // cells strictly under the candidate bin, over all ranks (set by the HIST post)
   unsigned long long wlo, whi;         // histogram window (sortable bits)
   unsigned long long blo, bhi;         // candidate bin (sortable bits)
   unsigned long long t_prev;           // last resolved threshold (distance bits), 0 = none
@@ -48,9 +57,9 @@ struct McdClu {
 
 struct McdWork {
   McdClu clu[SQC_MAXK];
-  unsigned long long cnt_below[SQC_MAXK];   // HIST: cells under the window
+  unsigned long long cnt_below[SQC_MAXK];   // HIST: local cells under the window
   unsigned long long cnt_nan[SQC_MAXK];
-  unsigned int cand_cnt[SQC_MAXK];
+  int status;                               // in-kernel error (identical on every rank: derived from exchanged data only)
 };
 
 struct GridBar { unsigned int count; unsigned int gen; };
@@ -59,16 +68,18 @@ struct McdBufs {
   McdWork* work;
   unsigned int* hist;                  // K x MCD_NB
   double* part;                        // grid x K x NMOM(D) per-CTA moment partials
-  unsigned long long* cand_bits;       // K x MCD_CAND_CAP
-  unsigned int* cand_pos;              // K x MCD_CAND_CAP
+  unsigned long long* cand_bits;       // K x regions x MCD_CAPW
+  unsigned int* cand_pos;              // K x regions x MCD_CAPW
+  double* cand_r;                      // K x regions x MCD_CAPW x D residuals of the candidates
+  unsigned int* cand_cnt;              // K x regions
   const int* keys;                     // R-compatible key stream of this call (N_total ints), or null
   unsigned long long call_mix;         // counter-mode key mix for this call
   long long stream_base;               // call * N_total: index of this call's first draw
   GridBar* bar;                        // grid barrier words (count must be 0 at launch)
   long long* trace;                    // optional per-round timeline (debug): 8 words per round, word 0 of the buffer = rounds
+  XchgDev xc;                          // peer windows (world <= 1: unused)
 };
-// Sense-reversing grid barrier on two words of global memory (the launch is cooperative, so all CTAs are
-// co-resident).  About half the latency of cooperative_groups' grid.sync() for one CTA per SM.
+
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   unsigned int v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
 }
@@ -102,24 +113,6 @@ __device__ inline void set_dist_window(McdClu& c, double lo, double hi) {
 __device__ inline void set_full_dist_window(McdClu& c) {       // every finite non-negative double
   c.wlo = 0ull; c.whi = 0x7ff0000000000000ull;
   c.shift = window_shift(c.wlo, c.whi);
-}
-
-// in-block bitonic sort of (key, pos) pairs, ascending, lexicographic
-__device__ inline void bitonic_sort_pairs(unsigned long long* key, unsigned int* pos, int P) {
-  for (int size = 2; size <= P; size <<= 1) {
-    for (int stride = size >> 1; stride > 0; stride >>= 1) {
-      for (int i = threadIdx.x; i < (P >> 1); i += blockDim.x) {
-        const int lo = 2 * i - (i & (stride - 1));
-        const int hi = lo + stride;
-        const bool asc = (lo & size) == 0;
-        const unsigned long long ka = key[lo], kb = key[hi];
-        const unsigned int pa = pos[lo], pb = pos[hi];
-        const bool gt = (ka > kb) || (ka == kb && pa > pb);
-        if (gt == asc) { key[lo] = kb; key[hi] = ka; pos[lo] = pb; pos[hi] = pa; }
-      }
-      __syncthreads();
-    }
-  }
 }
 
 // deterministic block reduction of NM doubles per thread -> out[0..NM) (valid for all threads after return)
@@ -220,22 +213,26 @@ __device__ inline bool prepare_dist(McdClu& c) {
 // ---------------------------------------------------------------------------------------------
 template <int D>
 __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
-  constexpr int NM = SQC_NMOM(D);
+  constexpr int NM = SQC_NMOM(D), CPT = McdCfg<D>::CPT, CHUNK = McdCfg<D>::CHUNK;
   extern __shared__ __align__(16) unsigned char sh_raw[];
-  unsigned long long* sh_key = (unsigned long long*)sh_raw;                  // MCD_CAND_CAP (leader sort)
-  unsigned int* sh_pos = (unsigned int*)(sh_raw + (size_t)MCD_CAND_CAP * 8); // MCD_CAND_CAP
-  unsigned int* sh_hist = (unsigned int*)sh_raw;                             // MCD_NB (streaming rounds), aliases sh_key
+  unsigned int* sh_hist = (unsigned int*)sh_raw;                                       // MCD_NB + 8: streaming histogram / leader fine histogram + extras
+  unsigned long long* sh_tkey = (unsigned long long*)(sh_raw + (size_t)(MCD_NB + 8) * 4);    // MCD_TINY tie keys
+  unsigned int* sh_tpos = (unsigned int*)(sh_tkey + MCD_TINY);                         // MCD_TINY: rank << 28 ... see below
+  unsigned int* sh_tref = sh_tpos + MCD_TINY;                                          // MCD_TINY: region * CAPW + slot (own candidates)
+  unsigned int* sh_trank = sh_tref + MCD_TINY;                                         // MCD_TINY: owning rank
   __shared__ double sh_red[32 * NM];
   __shared__ double sh_out[NM];
   __shared__ long long sh_cstart[SQC_MAXK + 1];
   __shared__ long long sh_scan[33];
-  __shared__ int sh_flag[4];
+  __shared__ int sh_flag[6];
   __shared__ int sh_ph[SQC_MAXK];
   __shared__ long long sh_n[SQC_MAXK];
-  __shared__ unsigned long long sh_u64[2];
+  __shared__ unsigned long long sh_u64[4];
 
-  if (!s.ctl->cont) return;                    // uniform across the grid: nobody reaches a barrier
-  const int tid = threadIdx.x, lane = tid & 31, G = gridDim.x, b = blockIdx.x, K = s.K;
+  if (!s.ctl->cont) return;                    // uniform across the grid (and across ranks): nobody reaches a barrier
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, G = gridDim.x, b = blockIdx.x, K = s.K;
+  const int world = mb.xc.world > 1 ? mb.xc.world : 1, myrank = world > 1 ? mb.xc.rank : 0;
+  const int regions = G * MCD_WARPS, region = b * MCD_WARPS + wid;
   unsigned int bar_gen = ld_acquire_u32(&mb.bar->gen);
   McdWork* W = mb.work;
 
@@ -245,14 +242,14 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
     if (tid == 0) {
       McdClu& c = W->clu[k];
       const long long n = s.clu_n_glob[k];
-      c.n = n; c.off = s.clu_off[k]; c.prefix = s.clu_prefix[k];
+      c.n = n; c.n_loc = s.clu_n[k]; c.off = s.clu_off[k]; c.prefix = s.clu_prefix[k];
       c.h = (long long)(int)((double)(unsigned long long)(n + D + 1) * s.mcd_alpha);   // :306 truncation
       c.iters = 0; c.is_final = 0; c.t_prev = 0ull; c.n_hist_rounds = 0; c.below = 0;
       c.det_old = 0.0; c.det_new = 0.0;
       int err = 0;
       if (n <= 0) err = SQC_D_EMPTY_CLUSTER;                       // x_k.rows(0, -1), :307
       else if (c.h > n || c.h < 1) err = SQC_D_SUBSET_SIZE;        // randperm(N, h) with h > N, :72
-      if (err) { atomicCAS(&s.ctl->status, 0, err); c.phase = PH_DONE; }
+      if (err) { atomicCAS(&W->status, 0, err); c.phase = PH_DONE; }
       else {
         c.q_chisq = dev_qchisq((double)c.h / (double)n, D);        // :101-102
         for (int d = 0; d < D; ++d) c.cshift[d] = s.beta[k * D + d];   // previous beta_k (zeros before the first call)
@@ -266,7 +263,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         c.shift = window_shift(c.wlo, c.whi);
         c.phase = PH_KEY_HIST;
       }
-      W->cnt_below[k] = 0ull; W->cnt_nan[k] = 0ull; W->cand_cnt[k] = 0u;
+      W->cnt_below[k] = 0ull; W->cnt_nan[k] = 0ull;
     }
     for (int i = tid; i < MCD_NB; i += MCD_THREADS) mb.hist[k * MCD_NB + i] = 0u;
   }
@@ -276,8 +273,8 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
   long long rounds = 0;
   for (;;) {
     // ---- active chunk map -------------------------------------------------------------------
-    if (tid < K) { sh_ph[tid] = W->clu[tid].phase; sh_n[tid] = W->clu[tid].n; }      // parallel loads, then a tiny serial prefix
-    if (tid == 32) sh_flag[3] = s.ctl->status;
+    if (tid < K) { sh_ph[tid] = W->clu[tid].phase; sh_n[tid] = W->clu[tid].n_loc; }   // parallel loads, then a tiny serial prefix
+    if (tid == 32) sh_flag[3] = W->status;
     __syncthreads();
     if (tid == 0) {
       long long run = 0, cells = 0, bytes = 0; int any = 0;
@@ -287,7 +284,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         const int ph = sh_ph[k];
         if (ph != PH_DONE && !bad) {
           const long long n = sh_n[k];
-          run += (n + MCD_CHUNK - 1) / MCD_CHUNK; any = 1; cells += n;
+          run += (n + CHUNK - 1) / CHUNK; any = 1; cells += n;
           const bool keyr = (ph == PH_KEY_HIST || ph == PH_KEY_COLLECT);
           bytes += n * ((ph == PH_KEY_HIST ? 0 : 8 * D) + ((keyr && mb.keys) ? 4 : 0));
         }
@@ -300,8 +297,9 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
     ++rounds;
     const bool tr = mb.trace && b == 0 && tid == 0 && rounds < 500;
     long long* trow = mb.trace + 8 * rounds;
-    if (tr) { trow[0] = gtimer(); int ph = 0; for (int k = 0; k < K; ++k) ph |= (W->clu[k].phase & 7) << (3 * k); trow[4] = ph; trow[5] = sh_cstart[K]; }
+    if (tr) { trow[0] = gtimer(); int ph = 0; for (int k = 0; k < K; ++k) ph |= (sh_ph[k] & 7) << (3 * k); trow[4] = ph; trow[5] = sh_cstart[K]; trow[6] = 0; trow[7] = 0; }
     for (int i = tid; i < K * NM; i += MCD_THREADS) mb.part[((long long)b * K) * NM + i] = 0.0;
+    if (lane < K) mb.cand_cnt[(long long)lane * regions + region] = 0u;
     const long long total = sh_cstart[K];
     const long long c0 = total * b / G, c1 = total * (b + 1) / G;
 
@@ -315,7 +313,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
       const int phase = cl.phase;
       const bool hist_round = (phase == PH_KEY_HIST || phase == PH_DIST_HIST);
       const bool key_round = (phase == PH_KEY_HIST || phase == PH_KEY_COLLECT);
-      const long long n = cl.n;
+      const long long n = cl.n_loc;
       const unsigned long long lo_b = hist_round ? cl.wlo : cl.blo, hi_b = hist_round ? cl.whi : cl.bhi;
       const int shift = cl.shift;
       double loc[D], cs[D], lt[SQC_TRI(D)];
@@ -325,27 +323,28 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
       for (int e = 0; e < SQC_TRI(D); ++e) lt[e] = cl.linv[e];
       const bool need_mom = (phase == PH_KEY_COLLECT) || (phase == PH_DIST_COLLECT && !cl.is_final);
       const double* rsb = s.rs + cl.off;
-      const long long kbase = cl.prefix;                            // key-stream offset of the cluster's first cell
+      const long long kbase = cl.prefix;                            // key-stream offset of the local segment's first cell
       if (hist_round) { for (int i = tid; i < MCD_NB; i += MCD_THREADS) sh_hist[i] = 0u; }
       __syncthreads();
       double acc[NM];
 #pragma unroll
       for (int m = 0; m < NM; ++m) acc[m] = 0.0;
-      unsigned int below = 0, nnan = 0;
+      unsigned int below = 0, nnan = 0, wcount = 0;
+      const long long cbase = ((long long)k * regions + region) * MCD_CAPW;
 
       for (long long ch = c; ch < cend; ++ch) {
-        const long long e0 = (ch - sh_cstart[k]) * MCD_CHUNK;
-        double r[MCD_CPT][D]; unsigned long long bits[MCD_CPT]; bool valid[MCD_CPT];
-        long long epos[MCD_CPT];
+        const long long e0 = (ch - sh_cstart[k]) * CHUNK;
+        double r[CPT][D]; unsigned long long bits[CPT]; bool valid[CPT];
+        long long epos[CPT];
 #pragma unroll
-        for (int it = 0; it < MCD_CPT / 2; ++it) {
+        for (int it = 0; it < CPT / 2; ++it) {
           const long long e = e0 + (long long)it * (2 * MCD_THREADS) + 2 * tid;
           epos[2 * it] = e; epos[2 * it + 1] = e + 1;
           valid[2 * it] = e < n; valid[2 * it + 1] = (e + 1) < n;
         }
         if (!(key_round && hist_round)) {                           // KEY_HIST needs no residuals
 #pragma unroll
-          for (int it = 0; it < MCD_CPT / 2; ++it) {
+          for (int it = 0; it < CPT / 2; ++it) {
 #pragma unroll
             for (int d = 0; d < D; ++d) {
               double2 v = make_double2(0.0, 0.0);
@@ -357,19 +356,19 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         if (key_round) {
           if (mb.keys) {
 #pragma unroll
-            for (int it = 0; it < MCD_CPT; ++it) {
+            for (int it = 0; it < CPT; ++it) {
               int key = 0;
               if (valid[it]) key = ld_stream_s32(mb.keys + kbase + epos[it]);
               bits[it] = (unsigned long long)(unsigned int)key;
             }
           } else {
 #pragma unroll
-            for (int it = 0; it < MCD_CPT; ++it)
+            for (int it = 0; it < CPT; ++it)
               bits[it] = (unsigned long long)(unsigned int)counter_key(mb.call_mix, (unsigned long long)(mb.stream_base + kbase + epos[it]));
           }
         } else {
 #pragma unroll
-          for (int it = 0; it < MCD_CPT; ++it) {
+          for (int it = 0; it < CPT; ++it) {
             double v[D];
 #pragma unroll
             for (int d = 0; d < D; ++d) v[d] = r[it][d] - loc[d];
@@ -380,7 +379,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         }
         if (hist_round) {
 #pragma unroll
-          for (int it = 0; it < MCD_CPT; ++it) {
+          for (int it = 0; it < CPT; ++it) {
             if (valid[it]) {
               if (bits[it] < lo_b) ++below;
               else if (bits[it] < hi_b) atomicAdd(&sh_hist[(unsigned int)((bits[it] - lo_b) >> shift)], 1u);
@@ -388,22 +387,20 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
           }
         } else {
 #pragma unroll
-          for (int it = 0; it < MCD_CPT; ++it) {
+          for (int it = 0; it < CPT; ++it) {
             const bool in = valid[it] && bits[it] < lo_b;
             const bool cand = valid[it] && bits[it] >= lo_b && bits[it] < hi_b;
             if (need_mom) Mom<D>::add(acc, r[it], cs, in);
             const unsigned m = __ballot_sync(0xffffffffu, cand);
-            if (m) {
-              unsigned base = 0;
-              if (lane == (__ffs(m) - 1)) base = atomicAdd(&W->cand_cnt[k], (unsigned)__popc(m));
-              base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-              if (cand) {
-                const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
-                if (slot < (unsigned)MCD_CAND_CAP) {
-                  mb.cand_bits[(long long)k * MCD_CAND_CAP + slot] = bits[it];
-                  mb.cand_pos[(long long)k * MCD_CAND_CAP + slot] = (unsigned int)epos[it];
-                }
+            if (m) {                                                // per-warp region, warp-deterministic order, no atomics
+              const unsigned slot = wcount + __popc(m & ((1u << lane) - 1u));
+              if (cand && slot < (unsigned)MCD_CAPW) {
+                mb.cand_bits[cbase + slot] = bits[it];
+                mb.cand_pos[cbase + slot] = (unsigned int)epos[it];
+#pragma unroll
+                for (int d = 0; d < D; ++d) mb.cand_r[(cbase + slot) * D + d] = r[it][d];
               }
+              wcount += __popc(m);
             }
           }
         }
@@ -415,10 +412,13 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         unsigned long long bl = (unsigned long long)warp_sum_i((int)below);
         if (lane == 0 && bl) atomicAdd(&W->cnt_below[k], bl);
         __syncthreads();
-      } else if (need_mom) {
-        block_reduce_vec<NM>(acc, sh_red, sh_out);
-        if (tid < NM) mb.part[((long long)b * K + k) * NM + tid] = sh_out[tid];
-        __syncthreads();
+      } else {
+        if (lane == 0) mb.cand_cnt[(long long)k * regions + region] = wcount;
+        if (need_mom) {
+          block_reduce_vec<NM>(acc, sh_red, sh_out);
+          if (tid < NM) mb.part[((long long)b * K + k) * NM + tid] = sh_out[tid];
+          __syncthreads();
+        }
       }
       const int nn = warp_sum_i((int)nnan);
       if (lane == 0 && nn) atomicAdd(&W->cnt_nan[k], (unsigned long long)nn);
@@ -430,25 +430,33 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
     if (tr) trow[2] = gtimer();
 
     // ---- leaders: per-cluster post-processing -------------------------------------------------
-    if (tid == 0) sh_flag[2] = (b < K && W->clu[b].phase != PH_DONE && s.ctl->status == 0) ? 1 : 0;
+    if (tid == 0) sh_flag[2] = (b < K && W->clu[b].phase != PH_DONE && W->status == 0) ? 1 : 0;
     __syncthreads();
     if (sh_flag[2]) {
       const int k = b;
       McdClu& cl = W->clu[k];
       const int phase = cl.phase;
-      if (W->cnt_nan[k]) {                                          // sort_index(): detected NaN, :50
-        if (tid == 0) { atomicCAS(&s.ctl->status, 0, SQC_D_NAN); cl.phase = PH_DONE; }
-      } else if (phase == PH_KEY_HIST || phase == PH_DIST_HIST) {
-        // locate the bin that holds the h-th smallest key
-        const long long below = (long long)W->cnt_below[k];
+      const bool key_phase = (phase == PH_KEY_HIST || phase == PH_KEY_COLLECT);
+      if (phase == PH_KEY_HIST || phase == PH_DIST_HIST) {
+        // ---- HIST post: locate the bin that holds the h-th smallest key (over all ranks) ----
+        for (int i = tid; i < MCD_NB; i += MCD_THREADS) { sh_hist[i] = mb.hist[k * MCD_NB + i]; mb.hist[k * MCD_NB + i] = 0u; }
+        if (tid == 0) {
+          const unsigned long long bl = W->cnt_below[k], nn = W->cnt_nan[k];
+          sh_hist[MCD_NB] = (unsigned int)bl; sh_hist[MCD_NB + 1] = (unsigned int)(bl >> 32); sh_hist[MCD_NB + 2] = nn ? 1u : 0u;
+          W->cnt_below[k] = 0ull;
+        }
+        __syncthreads();
+        if (world > 1) xchg_sum_u32(mb.xc, k, sh_hist, MCD_NB + 3);      // (the two halves of `below` cannot carry: < 2^32 cells per rank)
+        const long long below = (long long)sh_hist[MCD_NB] + ((long long)sh_hist[MCD_NB + 1] << 32);
+        const bool has_nan = sh_hist[MCD_NB + 2] != 0;
         constexpr int PER = MCD_NB / MCD_THREADS;
         unsigned int hv[PER]; long long mine = 0;
 #pragma unroll
-        for (int i = 0; i < PER; ++i) { hv[i] = mb.hist[k * MCD_NB + tid * PER + i]; mine += hv[i]; }
+        for (int i = 0; i < PER; ++i) { hv[i] = sh_hist[tid * PER + i]; mine += hv[i]; }
         long long total_in;
         long long run = block_excl_scan<MCD_THREADS>(mine, sh_scan, &total_in);
         const long long want = cl.h - below;                        // 1-based rank inside the window
-        if (tid == 0) { sh_flag[1] = -1; }
+        if (tid == 0) sh_flag[1] = -1;
         __syncthreads();
         if (want >= 1 && want <= total_in) {
 #pragma unroll
@@ -461,65 +469,171 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         if (tid == 0) {
           cl.n_hist_rounds++;
           const int bin = sh_flag[1];
-          if (bin < 0) {
+          if (has_nan) { atomicCAS(&W->status, 0, SQC_D_NAN); cl.phase = PH_DONE; }          // sort_index(): detected NaN, :50
+          else if (bin < 0) {
             // the order statistic lies outside the window: widen to the whole side it is on
-            if (phase == PH_KEY_HIST) {
-              if (want < 1) { cl.whi = cl.wlo; cl.wlo = 0ull; } else { cl.wlo = cl.whi; cl.whi = 1ull << 31; }
-            } else {
-              if (want < 1) { cl.whi = cl.wlo; cl.wlo = 0ull; } else { cl.wlo = cl.whi; cl.whi = 0x7ff0000000000001ull; }
-            }
+            const unsigned long long top = key_phase ? (1ull << 31) : 0x7ff0000000000001ull;
+            if (want < 1) { cl.whi = cl.wlo; cl.wlo = 0ull; } else { cl.wlo = cl.whi; cl.whi = top; }
             cl.shift = window_shift(cl.wlo, cl.whi);
-            if (cl.whi <= cl.wlo || cl.n_hist_rounds > 40) { atomicCAS(&s.ctl->status, 0, SQC_D_SELECT); cl.phase = PH_DONE; }
+            if (cl.whi <= cl.wlo || cl.n_hist_rounds > 40) { atomicCAS(&W->status, 0, SQC_D_SELECT); cl.phase = PH_DONE; }
           } else {
             const unsigned long long blo = cl.wlo + ((unsigned long long)bin << cl.shift);
             unsigned long long bhi = blo + (1ull << cl.shift);
             if (bhi > cl.whi) bhi = cl.whi;
-            if (sh_u64[1] > (unsigned long long)MCD_CAND_CAP) {
-              if (cl.shift == 0 || cl.n_hist_rounds > 40) { atomicCAS(&s.ctl->status, 0, SQC_D_SELECT); cl.phase = PH_DONE; }
-              else { cl.wlo = blo; cl.whi = bhi; cl.shift = window_shift(blo, bhi); }       // refine inside the bin
+            if (sh_u64[1] > (unsigned long long)MCD_CAND_CAP && cl.shift > 0 && cl.n_hist_rounds <= 40) {
+              cl.wlo = blo; cl.whi = bhi; cl.shift = window_shift(blo, bhi);                 // refine inside the bin
+            } else if (sh_u64[1] > (unsigned long long)MCD_CAND_CAP) {
+              atomicCAS(&W->status, 0, SQC_D_SELECT); cl.phase = PH_DONE;
             } else {
               cl.blo = blo; cl.bhi = bhi; cl.below = below + (long long)sh_u64[0];
-              cl.phase = (phase == PH_KEY_HIST) ? PH_KEY_COLLECT : PH_DIST_COLLECT;
+              cl.phase = key_phase ? PH_KEY_COLLECT : PH_DIST_COLLECT;
             }
           }
-          W->cnt_below[k] = 0ull; W->cand_cnt[k] = 0u;
         }
-        for (int i = tid; i < MCD_NB; i += MCD_THREADS) mb.hist[k * MCD_NB + i] = 0u;
       } else {
-        // COLLECT post: exact members of the candidate bin, then the moments
-        const int ncand = (int)min(W->cand_cnt[k], (unsigned)MCD_CAND_CAP);
-        int P = 32; while (P < ncand) P <<= 1;
-        for (int i = tid; i < P; i += MCD_THREADS) {
-          if (i < ncand) { sh_key[i] = mb.cand_bits[(long long)k * MCD_CAND_CAP + i]; sh_pos[i] = mb.cand_pos[(long long)k * MCD_CAND_CAP + i]; }
-          else { sh_key[i] = ~0ull; sh_pos[i] = ~0u; }
+        // ---- COLLECT post: exact members of the candidate bin, then the moments ---------------
+        const bool need_mom = (phase == PH_KEY_COLLECT) || !cl.is_final;
+        const unsigned long long blo = cl.blo;
+        const int fshift = cl.shift > 12 ? cl.shift - 12 : 0;        // 4096 fine bins inside the candidate bin
+        const unsigned int* ccnt = mb.cand_cnt + (long long)k * regions;
+        for (int i = tid; i < MCD_NB + 4; i += MCD_THREADS) sh_hist[i] = 0u;
+        if (tid == 0) { sh_flag[4] = 0; sh_flag[5] = 0; }
+        __syncthreads();
+        // 1. fine histogram of the candidates (regions in fixed order: thread t owns regions t, t + 512, ...)
+        for (int rg = tid; rg < regions; rg += MCD_THREADS) {
+          unsigned int cnum = ccnt[rg];
+          if (cnum > (unsigned)MCD_CAPW) { sh_hist[MCD_NB + 1] = 1u; cnum = MCD_CAPW; }     // region overflow -> refine
+          const long long cb = ((long long)k * regions + rg) * MCD_CAPW;
+          for (unsigned int sl = 0; sl < cnum; ++sl) atomicAdd(&sh_hist[(unsigned int)((mb.cand_bits[cb + sl] - blo) >> fshift)], 1u);
         }
         __syncthreads();
-        if (tr) trow[6] = gtimer();
-        bitonic_sort_pairs(sh_key, sh_pos, P);
-        if (tr) { trow[7] = gtimer(); trow[5] |= ((long long)ncand << 32); }
-        const long long take = cl.h - cl.below;                     // candidates that belong to the h-subset
-        const bool ok = (take >= 1 && take <= ncand && W->cand_cnt[k] <= (unsigned)MCD_CAND_CAP);
-        const unsigned long long thr = ok ? sh_key[take - 1] : 0ull;
-        const bool need_mom = (phase == PH_KEY_COLLECT) || !cl.is_final;
+        if (world > 1) xchg_sum_u32(mb.xc, k, sh_hist, MCD_NB + 2);
+        const bool overflow = sh_hist[MCD_NB + 1] != 0;
+        constexpr int PER = MCD_NB / MCD_THREADS;
+        unsigned int hv[PER]; long long mine = 0;
+#pragma unroll
+        for (int i = 0; i < PER; ++i) { hv[i] = sh_hist[tid * PER + i]; mine += hv[i]; }
+        long long ncand_all;
+        long long run = block_excl_scan<MCD_THREADS>(mine, sh_scan, &ncand_all);
+        const long long take = cl.h - cl.below;                      // candidates (over all ranks) that belong to the h-subset
+        if (tid == 0) sh_flag[1] = -1;
+        __syncthreads();
+        if (take >= 1 && take <= ncand_all) {
+#pragma unroll
+          for (int i = 0; i < PER; ++i) {
+            if (run < take && take <= run + (long long)hv[i]) { sh_flag[1] = tid * PER + i; sh_u64[0] = (unsigned long long)run; sh_u64[1] = hv[i]; }
+            run += hv[i];
+          }
+        }
+        __syncthreads();
+        const int fbin = sh_flag[1];
+        const long long fbelow = (long long)sh_u64[0];
+        const bool ok = !overflow && fbin >= 0 && sh_u64[1] <= (unsigned long long)MCD_TINY;
+        if (tr) { trow[6] = gtimer(); trow[5] |= (ncand_all << 32); }
+        // 2. candidates under the fine bin are members; those inside it go to the tie list
         double tot[NM];
 #pragma unroll
         for (int m = 0; m < NM; ++m) tot[m] = 0.0;
-        if (ok && need_mom) {
+        if (ok) {
           double cs[D];
 #pragma unroll
           for (int d = 0; d < D; ++d) cs[d] = cl.cshift[d];
-          const double* rsb = s.rs + cl.off;
-          for (int i = tid; i < (int)take; i += MCD_THREADS) {
-            double r[D];
+          for (int rg = tid; rg < regions; rg += MCD_THREADS) {
+            const unsigned int cnum = ccnt[rg];
+            const long long cb = ((long long)k * regions + rg) * MCD_CAPW;
+            for (unsigned int sl = 0; sl < cnum; ++sl) {
+              const unsigned long long bits = mb.cand_bits[cb + sl];
+              const int fb = (int)((bits - blo) >> fshift);
+              if (fb < fbin) {
+                if (need_mom) {
+                  double r[D];
 #pragma unroll
-            for (int d = 0; d < D; ++d) r[d] = rsb[(long long)d * s.rs_stride + sh_pos[i]];
-            Mom<D>::add(tot, r, cs, true);
+                  for (int d = 0; d < D; ++d) r[d] = mb.cand_r[(cb + sl) * D + d];
+                  Mom<D>::add(tot, r, cs, true);
+                }
+              } else if (fb == fbin) {
+                const int t = atomicAdd(&sh_flag[4], 1);
+                if (t < MCD_TINY) { sh_tkey[t] = bits; sh_tpos[t] = mb.cand_pos[cb + sl]; sh_tref[t] = (unsigned int)(rg * MCD_CAPW + sl); sh_trank[t] = (unsigned)myrank; }
+              }
+            }
           }
-          // per-CTA partials, fixed order: lane-strided over CTAs, then the warp tree
-          const int w = tid >> 5;
+        }
+        __syncthreads();
+        int ntie = min(sh_flag[4], MCD_TINY);
+        // 3. tie list over all ranks: all-gather, then sort by (key, rank, position)
+        if (ok && world > 1) {
+          // pack own list behind the fine histogram: [count, (key lo, key hi, pos) ...]
+          unsigned int* pk = sh_hist;
+          __syncthreads();
+          if (tid == 0) pk[0] = (unsigned)ntie;
+          for (int i = tid; i < ntie; i += MCD_THREADS) { pk[1 + 3 * i] = (unsigned)sh_tkey[i]; pk[2 + 3 * i] = (unsigned)(sh_tkey[i] >> 32); pk[3 + 3 * i] = sh_tpos[i]; }
+          __syncthreads();
+          const unsigned long long seq = xchg_publish(mb.xc, k, pk, 1 + 3 * ntie);
+          // own entries stay in place (with their references); append the peers'
+          if (tid == 0) {
+            int t = ntie;
+            for (int r = 0; r < world; ++r) {
+              if (r == myrank) continue;
+              const unsigned int* ps = xchg_peer_slot(mb.xc, k, seq, r);
+              const int cnt = (int)ld_relaxed_sys_u32(ps);
+              for (int i = 0; i < cnt && t < MCD_TINY; ++i, ++t) {
+                sh_tkey[t] = (unsigned long long)ld_relaxed_sys_u32(ps + 1 + 3 * i) | ((unsigned long long)ld_relaxed_sys_u32(ps + 2 + 3 * i) << 32);
+                sh_tpos[t] = ld_relaxed_sys_u32(ps + 3 + 3 * i); sh_tref[t] = 0xffffffffu; sh_trank[t] = (unsigned)r;
+              }
+            }
+            sh_flag[4] = t;
+          }
+          __syncthreads();
+          ntie = min(sh_flag[4], MCD_TINY);
+        }
+        // tiny selection by rank counting: entry i is a member iff fewer than take2 entries precede it in (key, rank, pos) order
+        const long long take2 = take - fbelow;
+        unsigned long long thr = 0ull;
+        if (ok) {
+          for (int i = tid; i < ntie; i += MCD_THREADS) {
+            const unsigned long long ki = sh_tkey[i]; const unsigned ri = sh_trank[i], pi = sh_tpos[i];
+            int before = 0;
+            for (int j2 = 0; j2 < ntie; ++j2) {
+              const unsigned long long kj = sh_tkey[j2]; const unsigned rj = sh_trank[j2], pj = sh_tpos[j2];
+              before += (kj < ki) || (kj == ki && (rj < ri || (rj == ri && pj < pi)));
+            }
+            if (before == (int)take2 - 1) sh_u64[2] = ki;           // the h-th smallest key itself
+            // remember membership in the top bit of the reference
+            if (before < (int)take2) sh_tref[i] |= 0x80000000u; else sh_tref[i] &= 0x7fffffffu;
+          }
+          __syncthreads();
+          thr = sh_u64[2];
+          if (need_mom && tid == 0) {
+            // own tie members, in ascending list order of a canonical sort: accumulate in (key, pos) order
+            double cs[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) cs[d] = cl.cshift[d];
+            // selection-sort walk over the (few) own members so that the summation order is deterministic
+            unsigned long long lastk = 0ull; unsigned lastp = 0u; bool first = true;
+            for (;;) {
+              int best = -1;
+              for (int i = 0; i < ntie; ++i) {
+                if (sh_trank[i] != (unsigned)myrank || !(sh_tref[i] & 0x80000000u) || (sh_tref[i] & 0x7fffffffu) == 0x7fffffffu) continue;
+                const bool after = first || sh_tkey[i] > lastk || (sh_tkey[i] == lastk && sh_tpos[i] > lastp);
+                if (!after) continue;
+                if (best < 0 || sh_tkey[i] < sh_tkey[best] || (sh_tkey[i] == sh_tkey[best] && sh_tpos[i] < sh_tpos[best])) best = i;
+              }
+              if (best < 0) break;
+              const long long cb = (long long)k * regions * MCD_CAPW + (long long)(sh_tref[best] & 0x7fffffffu);
+              double r[D];
+#pragma unroll
+              for (int d = 0; d < D; ++d) r[d] = mb.cand_r[cb * D + d];
+              Mom<D>::add(tot, r, cs, true);
+              lastk = sh_tkey[best]; lastp = sh_tpos[best]; first = false;
+            }
+          }
+        }
+        if (tr) trow[7] = gtimer();
+        // 4. per-CTA partials, fixed order: lane-strided over CTAs, then the warp tree
+        if (ok && need_mom) {
 #pragma unroll
           for (int m = 0; m < NM; ++m) {
-            if ((m & 31) == w) {                                    // warp (m mod 32) owns moment m
+            if ((m & (MCD_WARPS - 1)) == wid) {                     // warp (m mod 16) owns moment m
               double a = 0.0;
               for (int bb = lane; bb < G; bb += 32) a += mb.part[((long long)bb * K + k) * NM + m];
               a = warp_sum(a);
@@ -527,12 +641,17 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
             }
           }
         }
-        __syncthreads();                                            // sh_key / sh_pos no longer needed
+        __syncthreads();
         block_reduce_vec<NM>(tot, sh_red, sh_out);
+        if (ok && need_mom && world > 1) xchg_sum_f64(mb.xc, k, sh_out, NM);
         if (tid == 0) {
-          W->cand_cnt[k] = 0u;
-          if (!ok) { atomicCAS(&s.ctl->status, 0, SQC_D_SELECT); cl.phase = PH_DONE; }
-          else {
+          if (!ok) {
+            // too many candidates in one place (region overflow or a crowded fine bin): refine with another HIST round
+            if (fbin >= 0 && cl.shift > 0 && cl.n_hist_rounds <= 40) {
+              cl.wlo = cl.blo; cl.whi = cl.bhi; cl.shift = window_shift(cl.wlo, cl.whi);
+              cl.phase = key_phase ? PH_KEY_HIST : PH_DIST_HIST;
+            } else { atomicCAS(&W->status, 0, SQC_D_SELECT); cl.phase = PH_DONE; }
+          } else {
             const double h = (double)cl.h;
             bool go_final = false, done = false;
             if (phase == PH_KEY_COLLECT) {
@@ -558,13 +677,13 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
               done = true;
             }
             if (!done) {
-              if (sh_out[0] != h) { atomicCAS(&s.ctl->status, 0, SQC_D_SELECT); done = true; }
+              if (sh_out[0] != h) { atomicCAS(&W->status, 0, SQC_D_SELECT); done = true; }
               const bool cont = ((cl.det_old - cl.det_new) > 1e-10) & (cl.det_new > 0) & (cl.iters < s.mcd_iters);   // :84
               go_final = !cont;
               if (go_final && cl.iters == s.mcd_iters) atomicAdd(&s.ctl->mcd_hit, 1);   // :94-95
             }
             if (done) cl.phase = PH_DONE;
-            else if (!prepare_dist<D>(cl)) { atomicCAS(&s.ctl->status, 0, SQC_D_NOT_SPD); cl.phase = PH_DONE; }   // chol(), :19
+            else if (!prepare_dist<D>(cl)) { atomicCAS(&W->status, 0, SQC_D_NOT_SPD); cl.phase = PH_DONE; }   // chol(), :19
             else {
               cl.is_final = go_final ? 1 : 0;
               cl.phase = PH_DIST_HIST; cl.n_hist_rounds = 0;
@@ -585,7 +704,10 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
     __threadfence();
     grid_barrier(mb.bar, (unsigned)G, bar_gen);
   }
-  if (b == 0 && tid == 0) { s.ctl->mcd_passes += rounds; s.ctl->mcd_call += 1; }
+  if (b == 0 && tid == 0) {
+    s.ctl->mcd_passes += rounds; s.ctl->mcd_call += 1;
+    if (W->status) { atomicCAS(&s.ctl->status, 0, W->status); W->status = 0; }
+  }
 }
 
 }  // namespace sqc

@@ -1,17 +1,168 @@
-// sqc_xchg.cuh — cross-GPU exchange over peer memory (NVLink / NVSwitch).  STUB: single GPU only for now.
+// sqc_xchg.cuh — cross-GPU exchange through peer memory (NVLink 5 / NVSwitch), one process per GPU.
+//
+// Cells are sharded by sample: alpha_j, p_jk and the labels never leave their GPU; what
+// the ranks must agree on are a few small vectors per step (histograms of the exact selection, candidate
+// lists, K x (1 + D + D^2) moments, log-likelihood sums).  Those are exchanged INSIDE the kernels that
+// produce them: every rank owns a window in its HBM (cudaMalloc, exported with cudaIpcGetMemHandle and mapped
+// by all peers), publishes its vector there and a monotonically increasing sequence number behind it
+// (st.release.sys), then reads every peer's copy over NVLink (ld.acquire.sys on the flag, ld.relaxed.sys on
+// the data) and combines the copies in RANK ORDER — so all ranks hold bit-identical results and take
+// identical control-flow decisions without any host round trip or NCCL launch.  Messages are <= 32 KB:
+// what matters is latency, not the 900 GB/s links.  Slots are double-buffered by sequence parity: a rank can
+// publish exchange q + 1 only after it has read everybody's q, so a slot is never overwritten while a peer
+// may still read it.
 #pragma once
+#include <cstdint>
+#include <cstring>
+#include <stdexcept>
+#include <string>
 #include <cuda_runtime.h>
-struct sqc_session;
+#include "sqc_common.cuh"
+
 namespace sqc {
-struct XchgDev { int world, rank; };
-struct Xchg { XchgDev* dev = nullptr; int world = 1, rank = 0; };
-inline void xchg_open(Xchg&, int, int, int, const void*) { throw std::runtime_error("multi-GPU exchange not built"); }
-inline void xchg_close(Xchg&) {}
-inline void xchg_allreduce_host(Xchg&, cudaStream_t, double*, int) {}
-inline void xchg_cluster_layout(sqc_session*, Dev&) {}
-inline void xchg_allreduce_like(sqc_session*, Dev&) {}
-struct MleBufs;
-inline void xchg_allreduce_mle(sqc_session*, Dev&, MleBufs&, int, double*, int) {}
-inline void xchg_export(int, void*) { throw std::runtime_error("multi-GPU exchange not built"); }
-inline int xchg_release(int) { return 0; }
+
+constexpr int XCHG_MAX_WORLD = 8;
+constexpr int XCHG_CHANNELS = SQC_MAXK + 4;          // one per cluster leader + host-stream level channels
+constexpr int XCHG_CH_HOST = SQC_MAXK;               // first host-stream channel
+constexpr int XCHG_SLOT_BYTES = 32 * 1024;
+constexpr size_t XCHG_WINDOW_BYTES = 4096 + (size_t)XCHG_CHANNELS * 2 * XCHG_SLOT_BYTES;
+
+struct XchgDev {
+  int world, rank;
+  unsigned char* peer[XCHG_MAX_WORLD];               // window base of every rank (own window: local pointer)
+  unsigned long long* next_seq;                      // XCHG_CHANNELS counters in LOCAL memory (same value on all ranks)
+};
+
+__device__ __forceinline__ unsigned long long* xw_flag(unsigned char* base, int ch) { return (unsigned long long*)base + ch; }
+__device__ __forceinline__ unsigned char* xw_slot(unsigned char* base, int ch, unsigned long long seq) {
+  return base + 4096 + ((size_t)ch * 2 + (size_t)(seq & 1ull)) * XCHG_SLOT_BYTES;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_relaxed_sys_u32(const unsigned int* p) {
+  unsigned int v; asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v; asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+}
+
+// Block-wide: publish n_words 32-bit words from `src` (shared or global) on channel ch, wait for every rank.
+// Returns the sequence number; afterwards xchg_peer_slot(x, ch, seq, r) is readable for every rank r.
+__device__ inline unsigned long long xchg_publish(const XchgDev& x, int ch, const unsigned int* src, int n_words) {
+  __shared__ unsigned long long sh_seq;
+  if (threadIdx.x == 0) sh_seq = ++x.next_seq[ch];
+  __syncthreads();
+  const unsigned long long seq = sh_seq;
+  unsigned int* dst = (unsigned int*)xw_slot(x.peer[x.rank], ch, seq);
+  for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = src[i];
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) st_release_sys_u64(xw_flag(x.peer[x.rank], ch), seq);
+  if ((int)threadIdx.x < x.world) {
+    const unsigned long long* f = xw_flag(x.peer[threadIdx.x], ch);
+    while (ld_acquire_sys_u64(f) < seq) { }
+  }
+  __syncthreads();
+  return seq;
+}
+__device__ __forceinline__ const unsigned int* xchg_peer_slot(const XchgDev& x, int ch, unsigned long long seq, int r) {
+  return (const unsigned int*)xw_slot(x.peer[r], ch, seq);
+}
+// sum of 32-bit counters over ranks, in place (block-wide)
+__device__ inline void xchg_sum_u32(const XchgDev& x, int ch, unsigned int* buf, int n) {
+  const unsigned long long seq = xchg_publish(x, ch, buf, n);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    unsigned int a = 0;
+    for (int r = 0; r < x.world; ++r) a += ld_relaxed_sys_u32(xchg_peer_slot(x, ch, seq, r) + i);
+    buf[i] = a;
+  }
+  __syncthreads();
+}
+// sum of doubles over ranks in rank order (bit-identical on every rank), in place (block-wide)
+__device__ inline void xchg_sum_f64(const XchgDev& x, int ch, double* buf, int n) {
+  const unsigned long long seq = xchg_publish(x, ch, (const unsigned int*)buf, 2 * n);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    double a = 0.0;
+    for (int r = 0; r < x.world; ++r)
+      a += __longlong_as_double((long long)ld_relaxed_sys_u64((const unsigned long long*)xchg_peer_slot(x, ch, seq, r) + i));
+    buf[i] = a;
+  }
+  __syncthreads();
+}
+
+// host-stream level reductions (one CTA); used between the streaming kernels of the EM loop
+__global__ void k_xchg_sum_f64(XchgDev x, int ch, double* buf, int n, const int* cont) {
+  if (cont && !*cont) return;
+  xchg_sum_f64(x, ch, buf, n);
+}
+// all-gather of n 64-bit words per rank: out[r * n + i]
+__global__ void k_xchg_gather_u64(XchgDev x, int ch, const unsigned long long* in, unsigned long long* out, int n, const int* cont) {
+  if (cont && !*cont) return;
+  const unsigned long long seq = xchg_publish(x, ch, (const unsigned int*)in, 2 * n);
+  for (int i = threadIdx.x; i < n * x.world; i += blockDim.x) {
+    const int r = i / n, e = i % n;
+    out[i] = ld_relaxed_sys_u64((const unsigned long long*)xchg_peer_slot(x, ch, seq, r) + e);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct Xchg {
+  XchgDev dev{};                 // passed by value to kernels
+  int world = 1, rank = 0;
+  void* mapped[XCHG_MAX_WORLD] = {};
+  bool open = false;
+};
+
+struct XchgLocal { unsigned char* window = nullptr; unsigned long long* next_seq = nullptr; };
+inline XchgLocal& xchg_local(int device) { static XchgLocal w[64]; return w[device & 63]; }
+
+// allocate (once per device and process) this rank's window and export its IPC handle
+inline void xchg_export(int device, void* handle_out) {
+  XchgLocal& L = xchg_local(device);
+  if (!L.window) {
+    if (cudaMalloc((void**)&L.window, XCHG_WINDOW_BYTES) != cudaSuccess) throw std::runtime_error("exchange window allocation failed");
+    cudaMemset(L.window, 0, XCHG_WINDOW_BYTES);
+    cudaMalloc((void**)&L.next_seq, XCHG_CHANNELS * sizeof(unsigned long long));
+    cudaMemset(L.next_seq, 0, XCHG_CHANNELS * sizeof(unsigned long long));
+    cudaDeviceSynchronize();
+  }
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, L.window) != cudaSuccess) throw std::runtime_error("cudaIpcGetMemHandle failed");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(handle_out, &h, sizeof h);
+}
+inline int xchg_release(int device) {
+  XchgLocal& L = xchg_local(device);
+  if (L.window) { cudaSetDevice(device); cudaFree(L.window); cudaFree(L.next_seq); L.window = nullptr; L.next_seq = nullptr; }
+  return 0;
+}
+inline void xchg_open(Xchg& X, int device, int rank, int world, const void* handles) {
+  if (world > XCHG_MAX_WORLD) throw std::runtime_error("world size above XCHG_MAX_WORLD");
+  if (!handles) throw std::runtime_error("peer_handles missing for a multi-GPU fit");
+  XchgLocal& L = xchg_local(device);
+  if (!L.window) throw std::runtime_error("sqc_xchg_export must be called before a multi-GPU session is created");
+  X.world = world; X.rank = rank;
+  X.dev.world = world; X.dev.rank = rank; X.dev.next_seq = L.next_seq;
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { X.dev.peer[r] = L.window; continue; }
+    cudaIpcMemHandle_t h; memcpy(&h, (const char*)handles + (size_t)r * 64, sizeof h);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(e));
+    X.mapped[r] = p; X.dev.peer[r] = (unsigned char*)p;
+  }
+  X.open = true;
+}
+inline void xchg_close(Xchg& X) {
+  if (!X.open) return;
+  for (int r = 0; r < X.world; ++r) if (X.mapped[r]) { cudaIpcCloseMemHandle(X.mapped[r]); X.mapped[r] = nullptr; }
+  X.open = false;
+}
+
 }  // namespace sqc
