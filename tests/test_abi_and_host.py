@@ -1,0 +1,123 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/sampleqc_cuda.h declares, the ctypes
+structures match the header, compute entry points fail loudly without a GPU (no CPU fallback), and the
+multi-GPU host logic (sharding, handle exchange, result assembly) works under gloo with world_size 2."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _lib():
+    from sampleqc_b200 import build
+    build.build()
+    from sampleqc_b200 import _lib
+    return _lib
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib()
+    hdr = open(os.path.join(ROOT, "include", "sampleqc_cuda.h")).read()
+    declared = set(re.findall(r"SQC_API\s+(?:const\s+)?\w+\*?\s+\*?(sqc_\w+)\s*\(", hdr))
+    assert declared == set(L.EXPORTS), declared ^ set(L.EXPORTS)
+    lib = L.lib()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.sqc_abi_version() == 1
+    assert lib.sqc_status_name(2) == b"SQC_ERR_EMPTY_CLUSTER"
+
+
+def test_ctypes_structs_match_header_sizes(tmp_path):
+    from sampleqc_b200 import _abi as A
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "sampleqc_cuda.h"\nint main(){printf("%zu %zu %zu %zu\\n", sizeof(sqc_fit_args), sizeof(sqc_fit_out), sizeof(sqc_maha_args), sizeof(sqc_run_stats));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    sizes = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    assert sizes == [C.sizeof(A.SqcFitArgs), C.sizeof(A.SqcFitOut), C.sizeof(A.SqcMahaArgs), C.sizeof(A.SqcRunStats)]
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    from sampleqc_b200 import api
+    from sampleqc_b200._abi import SampleQCError
+    _lib()
+    x = np.asfortranarray(np.random.default_rng(0).normal(size=(50, 3)))
+    g = np.repeat(np.arange(5, dtype=np.int32), 10)
+    with pytest.raises(SampleQCError) as e:
+        api.fit_sampleqc_robust_cpp(x, np.zeros(50, np.int32), g, 3, 5, 1, 50, 3, 0.5, 10, 0)
+    assert e.value.status == -1                      # SQC_ERR_CUDA
+    with pytest.raises(SampleQCError):
+        api.fit_sampleqc_mle_cpp(x, np.ones((50, 1)), g, 3, 5, 1, 50, 2, 0)
+    with pytest.raises(SampleQCError):
+        api.calc_outliers(x, g, np.zeros(3), np.zeros((5, 3)), np.zeros((1, 3)), np.eye(3).reshape(3, 3, 1), 0.01)
+
+
+def test_product_package_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "sampleqc_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".inl", ".h")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "sqc_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_shard_by_sample_balanced_and_contiguous():
+    from sampleqc_b200.multigpu import shard_by_sample
+    rng = np.random.default_rng(1)
+    n_j = rng.integers(5, 500, size=37)
+    groups = np.repeat(np.arange(37), n_j)
+    for world in (1, 2, 3, 4, 8):
+        sh = shard_by_sample(groups, 37, world)
+        assert sh[0][0] == 0 and sh[-1][1] == 37 and sh[0][2] == 0 and sh[-1][3] == groups.size
+        for a, b in zip(sh[:-1], sh[1:]):
+            assert a[1] == b[0] and a[3] == b[2]
+        for (j0, j1, i0, i1) in sh:
+            assert i1 - i0 == n_j[j0:j1].sum()
+        assert max(i1 - i0 for (_, _, i0, i1) in sh) <= groups.size / world + n_j.max()
+    with pytest.raises(ValueError):
+        shard_by_sample(groups[::-1], 37, 2)
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch.distributed as dist
+from sampleqc_b200 import multigpu
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+# handle all-gather: rank r contributes 64 bytes of value r + 1
+h = multigpu.gather_handles(dist, bytes([rank + 1]) * 64, 2)
+assert h == bytes([1]) * 64 + bytes([2]) * 64, h
+# result assembly: global parameters identical, per-sample rows / labels concatenated in rank order
+J, K, D, N = 5, 2, 3, 40
+groups = np.repeat(np.arange(J), 8)
+j0, j1, i0, i1 = multigpu.shard_by_sample(groups, J, 2)[rank]
+loc = {"alpha_j": np.full((j1 - j0, D), rank + 1.0), "p_jk": np.full((j1 - j0, K), 0.5), "z": np.full((i1 - i0, 1), rank + 1.0),
+       "beta_k": np.arange(K * D, dtype=float).reshape(K, D), "n_zero_like": rank + 3, "n_iter": 7}
+full = multigpu.assemble(dist, rank, 2, loc, (j0, j1, i0, i1), J, N)
+if rank == 0:
+    assert full["alpha_j"].shape == (J, D) and full["z"].shape == (N, 1) and full["p_jk"].shape == (J, K)
+    assert full["alpha_j"][0, 0] == 1.0 and full["alpha_j"][-1, 0] == 2.0 and full["z"][0, 0] == 1.0 and full["z"][-1, 0] == 2.0
+    assert full["n_zero_like"] == 7 and full["n_iter"] == 7 and full["J"] == J and full["N"] == N
+else:
+    assert full is None
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_multigpu_host_logic_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER)
+    port = str(29600 + os.getpid() % 300)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    for r, (p, o) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"ok {r}" in o, o
