@@ -417,18 +417,39 @@ __global__ void __launch_bounds__(1024) k_post_stats(Dev s, int n_sample_blocks)
     }
     return;
   }
+  // per-component exclusive scan of the tile counts: every thread owns a contiguous run of tiles, reads all K
+  // counters of a tile together (independent loads), then one block scan per component
   const int per = (s.T + 1023) / 1024;
   const int b0 = min(tid * per, s.T), b1 = min(b0 + per, s.T);
+  const int K = s.K;
+  int sums[SQC_MAXK];
+#pragma unroll
+  for (int k = 0; k < SQC_MAXK; ++k) sums[k] = 0;
+#pragma unroll 2
+  for (int t = b0; t < b1; ++t) {
+    const int* row = s.t_nk + (long long)t * K;
+#pragma unroll
+    for (int k = 0; k < SQC_MAXK; ++k) if (k < K) sums[k] += row[k];
+  }
+  long long run[SQC_MAXK];
   long long off_run = 0;
-  for (int k = 0; k < s.K; ++k) {
-    long long mine = 0;
-    for (int t = b0; t < b1; ++t) mine += s.t_nk[t * s.K + k];
-    long long total;
-    long long run = block_excl_scan<1024>(mine, sh_scan, &total);
-    for (int t = b0; t < b1; ++t) { s.t_base[t * s.K + k] = (int)run; run += s.t_nk[t * s.K + k]; }
-    if (tid == 0) { s.clu_n[k] = total; s.clu_off[k] = off_run; }
-    off_run += (total + 31) & ~31ll;        // 256-byte aligned cluster segments
-    __syncthreads();
+#pragma unroll
+  for (int k = 0; k < SQC_MAXK; ++k) {
+    run[k] = 0;
+    if (k < K) {
+      long long total;
+      run[k] = block_excl_scan<1024>((long long)sums[k], sh_scan, &total);
+      if (tid == 0) { s.clu_n[k] = total; s.clu_off[k] = off_run; }
+      off_run += (total + 31) & ~31ll;      // 256-byte aligned cluster segments
+      __syncthreads();
+    }
+  }
+#pragma unroll 2
+  for (int t = b0; t < b1; ++t) {
+    const int* row = s.t_nk + (long long)t * K;
+    int* out = s.t_base + (long long)t * K;
+#pragma unroll
+    for (int k = 0; k < SQC_MAXK; ++k) if (k < K) { out[k] = (int)run[k]; run[k] += row[k]; }
   }
   // single GPU: the key stream of one update_beta_scale_k call runs over the clusters in order
   // (SURVEY Appendix A3); the multi-GPU exchange overwrites these with the global values
@@ -437,24 +458,80 @@ __global__ void __launch_bounds__(1024) k_post_stats(Dev s, int n_sample_blocks)
 
 // alpha_j from the (j,k) statistics: update_alpha_j :116-157 with the per-cell sums factored out
 //   denom_j = sum_k n_jk A_k,  numer_j = sum_k A_k (s_jk - n_jk beta_k),  alpha_j = inv(denom_j) numer_j
+// one thread per sample, D compile-time so that the small matrices live in registers
+template <int D>
+__device__ __forceinline__ bool inv_small(const double (&m)[D * D], double (&inv)[D * D]) {   // Gauss-Jordan, partial pivoting (arma::inv)
+  double a[D * D];
+#pragma unroll
+  for (int i = 0; i < D * D; ++i) { a[i] = m[i]; inv[i] = 0.0; }
+#pragma unroll
+  for (int i = 0; i < D; ++i) inv[i + D * i] = 1.0;
+  bool ok = true;
+#pragma unroll
+  for (int c = 0; c < D; ++c) {
+    int piv = c; double best = fabs(a[c + D * c]);
+#pragma unroll
+    for (int r = c + 1; r < D; ++r) { const double v = fabs(a[r + D * c]); if (v > best) { best = v; piv = r; } }
+    if (!(best > 0.0) || !(best < CUDART_INF)) ok = false;
+#pragma unroll
+    for (int r = c + 1; r < D; ++r) {
+      if (piv == r) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          double t = a[c + D * k]; a[c + D * k] = a[r + D * k]; a[r + D * k] = t;
+          t = inv[c + D * k]; inv[c + D * k] = inv[r + D * k]; inv[r + D * k] = t;
+        }
+      }
+    }
+    const double d = a[c + D * c];
+#pragma unroll
+    for (int k = 0; k < D; ++k) { a[c + D * k] /= d; inv[c + D * k] /= d; }
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+      if (r != c) {
+        const double f = a[r + D * c];
+#pragma unroll
+        for (int k = 0; k < D; ++k) { a[r + D * k] -= f * a[c + D * k]; inv[r + D * k] -= f * inv[c + D * k]; }
+      }
+    }
+  }
+  return ok;
+}
+template <int D>
 __global__ void k_update_alpha(Dev s) {
   if (!s.ctl->cont) return;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= s.J) return;
-  const int D = s.D, K = s.K;
-  double denom[SQC_MAXD * SQC_MAXD], numer[SQC_MAXD], inv[SQC_MAXD * SQC_MAXD];
+  const int K = s.K;
+  double denom[D * D], numer[D], inv[D * D];
+#pragma unroll
   for (int e = 0; e < D * D; ++e) denom[e] = 0.0;
+#pragma unroll
   for (int d = 0; d < D; ++d) numer[d] = 0.0;
   for (int k = 0; k < K; ++k) {
     const double n = (double)s.n_jk[j * K + k];
     const double* A = s.ainv + k * D * D;
-    double v[SQC_MAXD];
+    double v[D];
+#pragma unroll
     for (int d = 0; d < D; ++d) v[d] = s.s_jk[((long long)j * K + k) * D + d] - n * s.beta[k * D + d];
-    for (int r = 0; r < D; ++r) { double a = 0.0; for (int c = 0; c < D; ++c) a += A[r + D * c] * v[c]; numer[r] += a; }
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+      double a = 0.0;
+#pragma unroll
+      for (int c = 0; c < D; ++c) a += A[r + D * c] * v[c];
+      numer[r] += a;
+    }
+#pragma unroll
     for (int e = 0; e < D * D; ++e) denom[e] += n * A[e];
   }
-  if (!small_inv(denom, D, inv)) { atomicCAS(&s.ctl->status, 0, SQC_D_SINGULAR); return; }   // arma::inv throws, :153
-  for (int r = 0; r < D; ++r) { double a = 0.0; for (int c = 0; c < D; ++c) a += inv[r + D * c] * numer[c]; s.alpha[j * D + r] = a; }
+  if (!inv_small<D>(denom, inv)) { atomicCAS(&s.ctl->status, 0, SQC_D_SINGULAR); return; }   // arma::inv throws, :153
+#pragma unroll
+  for (int r = 0; r < D; ++r) {
+    double a = 0.0;
+#pragma unroll
+    for (int c = 0; c < D; ++c) a += inv[r + D * c] * numer[c];
+    s.alpha[j * D + r] = a;
+  }
 }
 // p_jk = (1 + n_jk) / (K + n_j), update_p_jk :322-341
 __global__ void k_update_p(Dev s) {

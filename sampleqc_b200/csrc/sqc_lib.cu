@@ -75,22 +75,38 @@ __global__ void k_ctl_reset(Dev s) {
 __global__ void k_ctl_start_loop(Dev s) {
   if (threadIdx.x == 0 && blockIdx.x == 0) { Control* c = s.ctl; c->cont = (s.em_iters > 0) && (c->status == 0); c->z_delta = 0; }
 }
-// derived per-component constants after an M-step: inverse Cholesky factor, inverse, normalisers
-// (what RcppDist::dmvnorm recomputes on every call — SURVEY Appendix A4 — hoisted)
-__global__ void k_derive(Dev s) {
-  if (!s.ctl->cont) return;
-  const int k = threadIdx.x, D = s.D;
-  if (k >= s.K) return;
-  const double* S = s.sigma + k * D * D;
-  double L[SQC_MAXD * SQC_MAXD], Li[SQC_MAXD * SQC_MAXD], Ai[SQC_MAXD * SQC_MAXD];
-  const bool ok1 = small_inv(S, D, Ai);
+// after an M-step: block 0 derives the per-component constants (inverse Cholesky factor, inverse, normalisers —
+// what RcppDist::dmvnorm recomputes on every call, SURVEY Appendix A4, hoisted); the other blocks update
+// p_jk = (1 + n_jk) / (K + n_j) (update_p_jk :322-341) when with_p is set
+template <int D>
+__device__ void derive_component(Dev& s, int k) {
+  double S[D * D], Ai[D * D];
+#pragma unroll
+  for (int e = 0; e < D * D; ++e) S[e] = s.sigma[k * D * D + e];
+  const bool ok1 = inv_small<D>(S, Ai);
+  double L[SQC_MAXD * SQC_MAXD], Li[SQC_MAXD * SQC_MAXD];
   const bool ok2 = small_chol_inv(S, D, L, Li);
   if (!ok1) { atomicCAS(&s.ctl->status, 0, SQC_D_SINGULAR); return; }
   if (!ok2) { atomicCAS(&s.ctl->status, 0, SQC_D_NOT_SPD); return; }
   const double det = small_det(S, D);
+#pragma unroll
   for (int e = 0; e < D * D; ++e) { s.linv[k * D * D + e] = Li[e]; s.ainv[k * D * D + e] = Ai[e]; }
   s.logP[k] = -1.0 * (D / 2.0) * 1.837877066409345483560659472811 - 0.5 * log(det);
   s.Pk[k] = 1.0 / sqrt(pow(6.283185307179586476925286766559, (double)D) * det);
+}
+template <int D>
+__global__ void k_after_mstep(Dev s, int with_p) {
+  if (!s.ctl->cont) return;
+  if (blockIdx.x == 0) { if ((int)threadIdx.x < s.K) derive_component<D>(s, threadIdx.x); return; }
+  if (!with_p) return;
+  const int j = (blockIdx.x - 1) * blockDim.x + threadIdx.x;
+  if (j >= s.J) return;
+  long long nj = s.K;
+  for (int k = 0; k < s.K; ++k) nj += s.n_jk[j * s.K + k];
+  for (int k = 0; k < s.K; ++k) {
+    const double p = (1.0 + (double)s.n_jk[j * s.K + k]) / (double)nj;
+    s.p_jk[j * s.K + k] = p; s.logp_jk[j * s.K + k] = log(p);
+  }
 }
 // final relabel by ascending beta_k[,0] (robust_cpp.cpp:527-531, reorder_z :434-445) and packing of
 // every output into the column-major shapes of the Rcpp list
@@ -349,6 +365,18 @@ void do_mcd(sqc_session* S) { switch (S->D) { SQC_FOR_D(SQC_CASE_MCD) default: f
 int do_mcd_grid(int D, int n_sm) { switch (D) { SQC_FOR_D(SQC_CASE_GRID) default: fail(SQC_ERR_BAD_ARG, "D = %d not compiled in", D); } }
 #define SQC_CASE_INIT(DD) case DD: launch_init_passes<DD>(S); break;
 void do_init_passes(sqc_session* S) { switch (S->D) { SQC_FOR_D(SQC_CASE_INIT) default: fail(SQC_ERR_BAD_ARG, "D = %d not compiled in", S->D); } }
+#define SQC_CASE_ALPHA(DD) case DD: k_update_alpha<DD><<<(S->J + 127) / 128, 128, 0, S->st>>>(S->dev); break;
+void do_update_alpha(sqc_session* S) {
+  Launch L(S, SQC_KF_UPDATE);
+  switch (S->D) { SQC_FOR_D(SQC_CASE_ALPHA) default: fail(SQC_ERR_BAD_ARG, "D = %d not compiled in", S->D); }
+  L.done();
+}
+#define SQC_CASE_AFTER(DD) case DD: k_after_mstep<DD><<<1 + (with_p ? (S->J + 127) / 128 : 0), 128, 0, S->st>>>(S->dev, with_p); break;
+void do_after_mstep(sqc_session* S, int with_p) {
+  Launch L(S, SQC_KF_UPDATE);
+  switch (S->D) { SQC_FOR_D(SQC_CASE_AFTER) default: fail(SQC_ERR_BAD_ARG, "D = %d not compiled in", S->D); }
+  L.done();
+}
 #define SQC_CASE_MLE(DD) case DD: mle_launch_pass<DD>(S->dev, S->ml, which, S->st); break;
 void do_mle_pass(sqc_session* S, int which) {
   Launch L(S, SQC_KF_MLE_PASS);
@@ -494,6 +522,7 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
     s.rs_stride = ((N + 32ll * (K + 1)) + 31) & ~31ll;
     s.rs = S->alloc<double>((size_t)s.rs_stride * D);
     S->mcd_grid = do_mcd_grid(D, S->n_sm);
+    if (S->mcd_grid * MCD_WARPS > MCD_RPT * MCD_THREADS) S->mcd_grid = MCD_RPT * MCD_THREADS / MCD_WARPS;
     McdBufs& mb = S->mb;
     mb.work = S->alloc<McdWork>(1);
     mb.hist = S->alloc<unsigned int>((size_t)K * MCD_NB);
@@ -505,7 +534,7 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
     mb.cand_cnt = S->alloc<unsigned int>(nreg);
     mb.xc = S->xc.dev;
     mb.bar = S->alloc<GridBar>(1);
-    mb.trace = getenv("SQC_MCD_TRACE") ? S->alloc<long long>(8 * 512) : nullptr;
+    mb.trace = getenv("SQC_MCD_TRACE") ? S->alloc<long long>(16 * 512) : nullptr;
     if (S->rng_mode == SQC_RNG_R_COMPAT) {
       S->mt_state = S->alloc<uint32_t>(640 * 5); S->keybuf = S->alloc<int>(2 * (size_t)S->N_total, false);
       if (getenv("SQC_RNG_INLINE") && atoi(getenv("SQC_RNG_INLINE"))) S->st_rng = S->st;      // debug: no side stream
@@ -613,7 +642,7 @@ void run_robust(sqc_session* S) {
     use_keys(S, call);
     do_mcd(S);
     release_keys(S, call);
-    { Launch L(S, SQC_KF_UPDATE); k_derive<<<1, 32, 0, S->st>>>(s); L.done(); }
+    do_after_mstep(S, like);                     // derived constants; inside the loop also p_jk (:504)
   };
   // initial labelling: p_jk (:481), alpha_j (:482), beta_k / Sigma_k (:483)
   do_estep(S, 1);
@@ -623,9 +652,8 @@ void run_robust(sqc_session* S) {
   { Launch L(S, SQC_KF_UPDATE); k_ctl_start_loop<<<1, 32, 0, S->st>>>(s); L.done(); }
   CK(cudaEventRecord(S->ev_init, S->st));
   for (int it = 0; it < S->em_iters; ++it) {                                            // :490
-    { Launch L(S, SQC_KF_UPDATE); k_update_alpha<<<(J + 127) / 128, 128, 0, S->st>>>(s); L.done(); }   // :496
-    m_step(it + 1, 1);                                                                  // like_1 :499, M-step :502
-    { Launch L(S, SQC_KF_UPDATE); k_update_p<<<(J + 127) / 128, 128, 0, S->st>>>(s); L.done(); }       // :504
+    do_update_alpha(S);                                                                 // :496
+    m_step(it + 1, 1);                                                                  // like_1 :499, M-step :502, p_jk :504
     do_estep(S, 0);                                                                     // :506, :509, :519
     post_stats();
     if (S->world > 1) xchg_allreduce_like(S, s);
@@ -770,7 +798,7 @@ int sqc_session_stats(const sqc_session* s, sqc_run_stats* st) { if (!s || !st) 
 SQC_API int sqc_session_mcd_trace(sqc_session* s, long long* out, int n_words) {
   if (!s || !out || !s->mb.trace) return SQC_ERR_BAD_ARG;
   cudaSetDevice(s->device);
-  return cudaMemcpy(out, s->mb.trace, sizeof(long long) * std::min(n_words, 8 * 512), cudaMemcpyDeviceToHost) == cudaSuccess ? SQC_OK : SQC_ERR_CUDA;
+  return cudaMemcpy(out, s->mb.trace, sizeof(long long) * std::min(n_words, 16 * 512), cudaMemcpyDeviceToHost) == cudaSuccess ? SQC_OK : SQC_ERR_CUDA;
 }
 int sqc_session_profile(sqc_session* s, int on) { if (!s) return SQC_ERR_BAD_ARG; s->profile = on != 0; return SQC_OK; }
 void sqc_session_destroy(sqc_session* s) { delete s; }

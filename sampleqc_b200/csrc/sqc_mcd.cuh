@@ -76,7 +76,7 @@ struct McdBufs {
   unsigned long long call_mix;         // counter-mode key mix for this call
   long long stream_base;               // call * N_total: index of this call's first draw
   GridBar* bar;                        // grid barrier words (count must be 0 at launch)
-  long long* trace;                    // optional per-round timeline (debug): 8 words per round, word 0 of the buffer = rounds
+  long long* trace;                    // optional per-round timeline (debug): 16 words per round, word 0 of the buffer = rounds
   XchgDev xc;                          // peer windows (world <= 1: unused)
 };
 
@@ -296,8 +296,8 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
     if (!sh_flag[0]) break;
     ++rounds;
     const bool tr = mb.trace && b == 0 && tid == 0 && rounds < 500;
-    long long* trow = mb.trace + 8 * rounds;
-    if (tr) { trow[0] = gtimer(); int ph = 0; for (int k = 0; k < K; ++k) ph |= (sh_ph[k] & 7) << (3 * k); trow[4] = ph; trow[5] = sh_cstart[K]; trow[6] = 0; trow[7] = 0; }
+    long long* trow = mb.trace + 16 * rounds;
+    if (tr) { trow[0] = gtimer(); int ph = 0; for (int k = 0; k < K; ++k) ph |= (sh_ph[k] & 7) << (3 * k); trow[4] = ph; trow[5] = sh_cstart[K]; for (int e = 6; e < 16; ++e) trow[e] = 0; }
     for (int i = tid; i < K * NM; i += MCD_THREADS) mb.part[((long long)b * K) * NM + i] = 0.0;
     if (lane < K) mb.cand_cnt[(long long)lane * regions + region] = 0u;
     const long long total = sh_cstart[K];
@@ -507,6 +507,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
           for (unsigned int sl = 0; sl < cnum; ++sl) atomicAdd(&sh_hist[(unsigned int)((mb.cand_bits[cb + sl] - blo) >> fshift)], 1u);
         }
         __syncthreads();
+        if (tr) trow[8] = gtimer();
         if (world > 1) xchg_sum_u32(mb.xc, k, sh_hist, MCD_NB + 2);
         const bool overflow = sh_hist[MCD_NB + 1] != 0;
         constexpr int PER = MCD_NB / MCD_THREADS;
@@ -559,6 +560,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
           }
         }
         __syncthreads();
+        if (tr) trow[9] = gtimer();
         int ntie = min(sh_flag[4], MCD_TINY);
         // 3. tie list over all ranks: all-gather, then sort by (key, rank, position)
         if (ok && world > 1) {
@@ -642,8 +644,10 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
           }
         }
         __syncthreads();
+        if (tr) trow[10] = gtimer();
         block_reduce_vec<NM>(tot, sh_red, sh_out);
         if (ok && need_mom && world > 1) xchg_sum_f64(mb.xc, k, sh_out, NM);
+        if (tr) trow[11] = gtimer();
         if (tid == 0) {
           if (!ok) {
             // too many candidates in one place (region overflow or a crowded fine bin): refine with another HIST round
@@ -667,6 +671,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
               cl.det_new = small_det(cl.scale, D);
               cl.iters++;
               cl.t_prev = thr;
+              if (tr) trow[12] = (long long)thr;
               atomicAdd((unsigned long long*)&s.ctl->mcd_csteps, 1ull);
             } else {
               // consistency rescale (:98-103): q = h-th smallest distance under the final estimates

@@ -15,15 +15,16 @@ s.profile(True)
 s.run(); s.run()
 st = s.stats()
 print({k: v for k, v in st.items() if k != "family_bytes"})
-buf = np.zeros(8 * 512, dtype=np.int64)
+buf = np.zeros(16 * 512, dtype=np.int64)
 L = lib(); L.sqc_session_mcd_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
 L.sqc_session_mcd_trace(s._h, buf.ctypes.data_as(C.c_void_p), buf.size)
-R = int(buf[0]); t = buf.reshape(-1, 8)
+R = int(buf[0]); t = buf.reshape(-1, 16)
 names = "KH KC DH DC DONE".split()
-print("round  stream_us  sync1_us  post_us  sync2+map_us  chunks  ncand presort_us sort_us phases")
+print("round stream sync1  post  sync2 | finehist scan pass2 tie partials reduce+linalg | chunks ncand phases")
 for r in range(1, R + 1):
-    t0, t1, t2, t3, ph, ch, t6, t7 = t[r][:8]
+    t0, t1, t2, t3, ph, ch, t6, t7, t8, t9, t10, t11 = t[r][:12]
     nc = ch >> 32; ch &= 0xffffffff
     nxt = t[r + 1][0] if r < R else t3
     phs = " ".join(names[(ph >> (3 * k)) & 7] for k in range(K))
-    print(f"{r:4d} {(t1-t0)/1e3:9.1f} {(t2-t1)/1e3:9.1f} {(t3-t2)/1e3:8.1f} {(nxt-t3)/1e3:9.1f} {ch:8d} {nc:6d} {(t6-t2)/1e3 if nc or t6>t2 else 0:8.1f} {(t7-t6)/1e3 if t7>t6 else 0:8.1f}  {phs}")
+    u = lambda a, b: (b - a) / 1e3 if (a > 0 and b > 0) else 0.0
+    print(f"{r:4d} {u(t0,t1):6.1f} {u(t1,t2):5.1f} {u(t2,t3):5.1f} {u(t3,nxt):5.1f} | {u(t2,t8):6.1f} {u(t8,t6):5.1f} {u(t6,t9):5.1f} {u(t9,t7):5.1f} {u(t7,t10):6.1f} {u(t10,t3):6.1f} | {ch:6d} {nc:6d} {phs}  T={np.array([t[r][12]]).view(np.float64)[0]:.4f}")
