@@ -522,7 +522,6 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
     s.rs_stride = ((N + 32ll * (K + 1)) + 31) & ~31ll;
     s.rs = S->alloc<double>((size_t)s.rs_stride * D);
     S->mcd_grid = do_mcd_grid(D, S->n_sm);
-    if (S->mcd_grid * MCD_WARPS > MCD_RPT * MCD_THREADS) S->mcd_grid = MCD_RPT * MCD_THREADS / MCD_WARPS;
     McdBufs& mb = S->mb;
     mb.work = S->alloc<McdWork>(1);
     mb.hist = S->alloc<unsigned int>((size_t)K * MCD_NB);
