@@ -203,6 +203,8 @@ SQC_API const char* sqc_status_name(int status);
  * routine the MCD consistency factor uses (replaces R::qchisq, robust_cpp.cpp:102)            */
 SQC_API int sqc_device_qchisq(const double* p, const double* df, double* out, int32_t n, int device,
                       char* err, size_t errlen);
+/* the kernels' own exp(x), x <= 0 (density exponents), exposed for accuracy tests               */
+SQC_API int sqc_device_expneg(const double* x, double* out, int32_t n, int device, char* err, size_t errlen);
 /* the R-compatible Mersenne-Twister key stream generated on the device (tests)               */
 SQC_API int sqc_device_rkeys(uint32_t seed, int64_t skip, int32_t* keys_out, int64_t n, int device,
                      char* err, size_t errlen);

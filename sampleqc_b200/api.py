@@ -146,3 +146,11 @@ def device_rkeys(seed, skip, n, device=-1):
     err = C.create_string_buffer(512)
     check(lib().sqc_device_rkeys(seed, skip, A.ptr_i(out), n, device, err, 512), err)
     return out
+
+
+def device_expneg(x, device=-1):
+    x = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1))
+    out = np.zeros_like(x)
+    err = C.create_string_buffer(512)
+    check(lib().sqc_device_expneg(A.ptr_d(x), A.ptr_d(out), x.size, device, err, 512), err)
+    return out

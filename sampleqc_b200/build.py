@@ -29,6 +29,8 @@ def build(force: bool = False, dims: str | None = None, verbose: bool = False) -
     cmd = [nvcc] + NVCC_FLAGS
     if dims:
         cmd.append("-DSQC_FOR_D(X)=" + " ".join(f"X({int(d)})" for d in dims.split(",")))
+    if os.environ.get("SQC_EXTRA_NVCC"):
+        cmd += os.environ["SQC_EXTRA_NVCC"].split()
     if verbose:
         cmd += ["-Xptxas", "-v"]
     cmd += ["-o", OUT, SRC]

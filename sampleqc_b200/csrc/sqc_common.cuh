@@ -53,6 +53,53 @@ __device__ __forceinline__ int ld_stream_s32(const int* p) {
   return v;
 }
 
+// exp(x) for x <= 0 (the density exponents -q/2): n = rint(x / ln 2) by the 1.5 * 2^52 trick, two-step Cody-Waite
+// reduction, degree-13 Taylor polynomial in Horner form with the coefficients in the constant bank, scaling by
+// exponent arithmetic.  <= 2 ulp from the correctly rounded value over the whole range including the gradual
+// underflow below -708 (handled by a two-step scaling); about half the instructions of the library exp().
+__constant__ double c_exp_coef[12] = {
+  1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0,
+  1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
+__device__ __forceinline__ double exp_neg(double x) {
+  const double magic = 6755399441055744.0;
+  const double t = fma(x, 1.4426950408889634074, magic);
+  const int n = __double2loint(t);
+  const double nf = t - magic;
+  double r = fma(nf, -6.93147180369123816490e-01, x);
+  r = fma(nf, -1.90821492927058770002e-10, r);
+  double p = c_exp_coef[0];
+#pragma unroll
+  for (int i = 1; i < 12; ++i) p = fma(p, r, c_exp_coef[i]);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  if (!(x >= -746.0)) return (x != x) ? x : 0.0;                      // underflow to zero (also -inf); NaN stays NaN
+  if (n >= -1020) return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
+  const double s1 = __hiloint2double((n + 1000 + 1023) << 20, 0);     // 2^(n + 1000), normal
+  return (p * s1) * 9.33263618503218878990e-302;                      // * 2^-1000: the hardware rounds the subnormal
+}
+
+// sum over the warp of NV doubles per lane with recursive halving: every step halves the number of values a lane
+// carries, so the shuffle count is about 2 NV instead of 5 NV.  NP = NV padded to a power of two (<= 16).
+// On return, lane l with (l & (32 / NP - 1)) == 0 holds the total of value index  l / (32 / NP)  in v[0].
+template <int NP>
+__device__ __forceinline__ void warp_sum_vec(double (&v)[NP], int lane) {
+  static_assert(NP == 1 || NP == 2 || NP == 4 || NP == 8 || NP == 16, "NP must be a power of two <= 16");
+  int mask = 16;
+#pragma unroll
+  for (int half = NP / 2; half >= 1; half >>= 1) {
+    const bool up = (lane & mask) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const double send = up ? v[i] : v[i + half];
+      const double keep = up ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+    }
+    mask >>= 1;
+  }
+#pragma unroll
+  for (; mask >= 1; mask >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], mask);
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

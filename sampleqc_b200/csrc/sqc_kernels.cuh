@@ -20,6 +20,12 @@ namespace cg = cooperative_groups;
 
 namespace sqc {
 
+#ifndef SQC_EST_MINB
+#define SQC_EST_MINB 3      // resident CTAs per SM the E-step kernel is compiled for (register cap 80; measured best of 2/3/4)
+#endif
+#ifndef SQC_PART_MINB
+#define SQC_PART_MINB 4     // same for the partition kernel (register cap 64)
+#endif
 constexpr int EST_THREADS = 256;     // E-step / partition CTAs: one sample-aligned tile each
 // cells per thread of a tile, by dimension (register budget)
 template <int D> struct TileCfg { static constexpr int CPT = (D <= 4) ? 4 : 2; static constexpr int TILE = EST_THREADS * CPT; };
@@ -137,7 +143,7 @@ template <int D> __device__ __forceinline__ double maha_tri(const double (&v)[D]
 // Statistics per tile: n_k (int) and sum_k x (D doubles) -> reduced per sample by k_post_stats.
 // ---------------------------------------------------------------------------------------------
 template <int D, int MODE>
-__global__ void __launch_bounds__(EST_THREADS) k_estep(Dev s) {
+__global__ void __launch_bounds__(EST_THREADS, SQC_EST_MINB) k_estep(Dev s) {
   constexpr int CPT = TileCfg<D>::CPT, SZ = ParK<D>::SZ, NW = EST_THREADS / 32;
   extern __shared__ double sh_dyn[];
   double* sh_par = sh_dyn;                                   // K * SZ
@@ -182,7 +188,7 @@ __global__ void __launch_bounds__(EST_THREADS) k_estep(Dev s) {
         const double l = logp + (logP - 0.5 * q);            // log(p_jk) + dmvnorm(log=TRUE), :364
         if (l > best[c]) { best[c] = l; zn[c] = k; }         // strict >, first max, :375-378
         if (valid[c] && best[c] == -CUDART_INF) ++nzero;     // :380-382
-        like[c] += p * (P * exp(-0.5 * q));                  // p_jk * dmvnorm(log=FALSE), :424
+        like[c] += p * (P * exp_neg(-0.5 * q));              // p_jk * dmvnorm(log=FALSE), :424
       }
     }
 #pragma unroll
@@ -196,26 +202,21 @@ __global__ void __launch_bounds__(EST_THREADS) k_estep(Dev s) {
     for (int c = 0; c < CPT; ++c) zn[c] = zo[c];
   }
   // statistics of the labels zn: per component count and sum of x, reduced over the tile
+  constexpr int NP = (D + 1 <= 2) ? 2 : (D + 1 <= 4) ? 4 : (D + 1 <= 8) ? 8 : 16;
   for (int k = 0; k < s.K; ++k) {
-    int cnt = 0; double sx[D];
+    double sv[NP];
 #pragma unroll
-    for (int d = 0; d < D; ++d) sx[d] = 0.0;
+    for (int e = 0; e < NP; ++e) sv[e] = 0.0;
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
       const bool in = valid[c] && zn[c] == k;
-      cnt += in;
+      sv[0] += in ? 1.0 : 0.0;
 #pragma unroll
-      for (int d = 0; d < D; ++d) sx[d] += in ? xv[c][d] : 0.0;
+      for (int d = 0; d < D; ++d) sv[1 + d] += in ? xv[c][d] : 0.0;
     }
-    cnt = warp_sum_i(cnt);
-#pragma unroll
-    for (int d = 0; d < D; ++d) sx[d] = warp_sum(sx[d]);
-    if (lane == 0) {
-      double* r = sh_red + (w * s.K + k) * (D + 1);
-      r[0] = (double)cnt;
-#pragma unroll
-      for (int d = 0; d < D; ++d) r[1 + d] = sx[d];
-    }
+    warp_sum_vec<NP>(sv, lane);
+    constexpr int STR = 32 / NP;
+    if ((lane & (STR - 1)) == 0 && lane / STR < D + 1) sh_red[(w * s.K + k) * (D + 1) + lane / STR] = sv[0];
   }
   ll = warp_sum(ll); delta = warp_sum_i(delta); nzero = warp_sum_i(nzero);
   if (lane == 0) { sh_w[w] = ll; sh_i[w] = delta; sh_i[NW + w] = nzero; }
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(EST_THREADS) k_estep(Dev s) {
 //   LIKE = 1: also the log-likelihood with the new alpha_j and the previous beta/Sigma/p_jk (:499).
 // ---------------------------------------------------------------------------------------------
 template <int D, int LIKE>
-__global__ void __launch_bounds__(EST_THREADS) k_partition(Dev s) {
+__global__ void __launch_bounds__(EST_THREADS, SQC_PART_MINB) k_partition(Dev s) {
   constexpr int CPT = TileCfg<D>::CPT, SZ = ParK<D>::SZ, NW = EST_THREADS / 32;
   extern __shared__ double sh_dyn[];
   double* sh_par = sh_dyn;                                   // K * SZ
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(EST_THREADS) k_partition(Dev s) {
         double v[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) v[d] = xv[c][d] - m[d];
-        like[c] += p * (P * exp(-0.5 * maha_tri<D>(v, lt)));
+        like[c] += p * (P * exp_neg(-0.5 * maha_tri<D>(v, lt)));
       }
     }
     double ll = 0.0;

@@ -140,6 +140,10 @@ __global__ void k_widen_labels(const int* in, uint8_t* out, long long n, int K, 
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x, gsz = (long long)gridDim.x * blockDim.x;
   for (long long i = gid; i < n; i += gsz) { int v = in[i]; if (v < 0 || v >= K) { *bad = 1; v = 0; } out[i] = (uint8_t)v; }
 }
+__global__ void k_expneg(const double* x, double* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = exp_neg(x[i]);
+}
 __global__ void k_qchisq(const double* p, const double* df, double* out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = dev_qchisq(p[i], (int)df[i]);
@@ -874,6 +878,17 @@ int sqc_device_qchisq(const double* p, const double* df, double* out, int32_t n,
     cudaMemcpy(buf, p, n * sizeof(double), cudaMemcpyHostToDevice); cudaMemcpy(buf + n, df, n * sizeof(double), cudaMemcpyHostToDevice);
     k_qchisq<<<(n + 127) / 128, 128>>>(buf, buf + n, buf + 2 * (size_t)n, n);
     cudaError_t e = cudaMemcpy(out, buf + 2 * (size_t)n, n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(buf); CK(e);
+  }, err, errlen);
+}
+int sqc_device_expneg(const double* x, double* out, int32_t n, int device, char* err, size_t errlen) {
+  return guarded([&] {
+    if (!x || !out || n < 0) fail(SQC_ERR_BAD_ARG, "bad arguments");
+    int d; select_device(device, &d);
+    double* buf = nullptr; CK(cudaMalloc((void**)&buf, (size_t)2 * std::max(n, 1) * sizeof(double)));
+    cudaMemcpy(buf, x, n * sizeof(double), cudaMemcpyHostToDevice);
+    k_expneg<<<(n + 127) / 128, 128>>>(buf, buf + n, n);
+    cudaError_t e = cudaMemcpy(out, buf + n, n * sizeof(double), cudaMemcpyDeviceToHost);
     cudaFree(buf); CK(e);
   }, err, errlen);
 }

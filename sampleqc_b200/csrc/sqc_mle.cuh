@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(EST_THREADS) k_mle_pass(Dev s, MleBufs m) {
         double v[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) v[d] = xv[c][d] - mu[d];
-        const double dens = coef * exp(-0.5 * maha_tri<D>(v, lt));   // p_k * dmvnorm(x, mu, Sigma), :171
+        const double dens = coef * exp_neg(-0.5 * maha_tri<D>(v, lt));   // p_k * dmvnorm(x, mu, Sigma), :171
         like[c] += dens;
         if (MODE != MLE_LIKE) sh_d[k * TILE + c * EST_THREADS + tid] = dens;
       }

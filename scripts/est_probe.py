@@ -1,0 +1,10 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import workload
+from sampleqc_b200 import api
+x, g, iz, prm = workload("C3", 1.0)
+D, J, K, N = prm["D"], prm["J"], prm["K"], prm["N"]
+s = api.Session(x, g, D, J, K, N, 6, init_z=iz, rng_mode=1)
+s.profile(True); s.run(); s.run()
+st = s.stats()
+print(sys.argv[1:], f"loop {st['loop_ms']:.2f} ms: estep {st['family_ms']['estep']/6*1e3:.0f} us  partition {st['family_ms']['partition']/7*1e3:.0f} us  mcd {st['family_ms']['mcd']/7*1e3:.0f} us  update {st['family_ms']['update']/6*1e3:.0f} us/iter")
