@@ -29,7 +29,10 @@
 
 namespace sqc {
 
-constexpr int MCD_THREADS = 512;                     // one fat CTA per SM: one histogram per SM, 128 registers per thread
+#ifndef SQC_MCD_THREADS
+#define SQC_MCD_THREADS 512      // 16 warps x 128 registers (384 threads, leaving room for the key-stream CTAs, measured slower)
+#endif
+constexpr int MCD_THREADS = SQC_MCD_THREADS;         // one fat CTA per SM: one histogram per SM
 constexpr int MCD_WARPS = MCD_THREADS / 32;
 constexpr int MCD_NB = 4096;                         // histogram bins per window (and fine bins per candidate bin)
 constexpr int MCD_CAND_CAP = 8192;                   // a bin holding more cells than this is refined by another HIST round
@@ -449,10 +452,10 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         if (world > 1) xchg_sum_u32(mb.xc, k, sh_hist, MCD_NB + 3);      // (the two halves of `below` cannot carry: < 2^32 cells per rank)
         const long long below = (long long)sh_hist[MCD_NB] + ((long long)sh_hist[MCD_NB + 1] << 32);
         const bool has_nan = sh_hist[MCD_NB + 2] != 0;
-        constexpr int PER = MCD_NB / MCD_THREADS;
+        constexpr int PER = (MCD_NB + MCD_THREADS - 1) / MCD_THREADS;
         unsigned int hv[PER]; long long mine = 0;
 #pragma unroll
-        for (int i = 0; i < PER; ++i) { hv[i] = sh_hist[tid * PER + i]; mine += hv[i]; }
+        for (int i = 0; i < PER; ++i) { hv[i] = (tid * PER + i < MCD_NB) ? sh_hist[tid * PER + i] : 0u; mine += hv[i]; }
         long long total_in;
         long long run = block_excl_scan<MCD_THREADS>(mine, sh_scan, &total_in);
         const long long want = cl.h - below;                        // 1-based rank inside the window
@@ -510,10 +513,10 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         if (tr) trow[8] = gtimer();
         if (world > 1) xchg_sum_u32(mb.xc, k, sh_hist, MCD_NB + 2);
         const bool overflow = sh_hist[MCD_NB + 1] != 0;
-        constexpr int PER = MCD_NB / MCD_THREADS;
+        constexpr int PER = (MCD_NB + MCD_THREADS - 1) / MCD_THREADS;
         unsigned int hv[PER]; long long mine = 0;
 #pragma unroll
-        for (int i = 0; i < PER; ++i) { hv[i] = sh_hist[tid * PER + i]; mine += hv[i]; }
+        for (int i = 0; i < PER; ++i) { hv[i] = (tid * PER + i < MCD_NB) ? sh_hist[tid * PER + i] : 0u; mine += hv[i]; }
         long long ncand_all;
         long long run = block_excl_scan<MCD_THREADS>(mine, sh_scan, &ncand_all);
         const long long take = cl.h - cl.below;                      // candidates (over all ranks) that belong to the h-subset
@@ -635,7 +638,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         if (ok && need_mom) {
 #pragma unroll
           for (int m = 0; m < NM; ++m) {
-            if ((m & (MCD_WARPS - 1)) == wid) {                     // warp (m mod 16) owns moment m
+            if ((m % MCD_WARPS) == wid) {                            // warp (m mod warps) owns moment m
               double a = 0.0;
               for (int bb = lane; bb < G; bb += 32) a += mb.part[((long long)bb * K + k) * NM + m];
               a = warp_sum(a);

@@ -20,7 +20,7 @@ constexpr int MT_SEQ_CHUNKS = 33;                         // 33 * 624 = 20 592 >
 constexpr int MT_SEQ_WORDS = MT_SEQ_CHUNKS * MT_N;
 constexpr int MT_BLOCK_CHUNKS = SQC_MT_CHUNKS_PER_BLOCK;  // 110
 constexpr long long MT_BLOCK_WORDS = (long long)MT_BLOCK_CHUNKS * MT_N;
-constexpr int MT_THREADS = 640;
+constexpr int MT_THREADS = 512;                          // <= 32 registers: fits beside the persistent M-step kernel
 constexpr size_t MT_SMEM = (size_t)(MT_SEQ_WORDS + MT_N) * sizeof(uint32_t);
 
 // one regeneration: nxt[0..623] from cur[0..623]  (dependency distance 227 -> three wavefronts)
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) k_mt_seq(const uint32_t* st, uint32_t* se
 }
 
 // window of block p = 1 .. nb-1 (row p * mult - 1 of the jump table correlated with the 33-chunk sequence)
-__global__ void __launch_bounds__(MT_THREADS) k_mt_jump(const uint32_t* st_in, const uint32_t* seq, const uint32_t* table, uint32_t* windows,
+__global__ void __launch_bounds__(MT_THREADS, 2) k_mt_jump(const uint32_t* st_in, const uint32_t* seq, const uint32_t* table, uint32_t* windows,
                                                         long long n, int mult, const Control* ctl) {
   extern __shared__ uint32_t sh_mt[];
   uint32_t* sseq = sh_mt;                         // MT_SEQ_WORDS
@@ -61,17 +61,20 @@ __global__ void __launch_bounds__(MT_THREADS) k_mt_jump(const uint32_t* st_in, c
   for (int i = tid; i < MT_SEQ_WORDS; i += MT_THREADS) sseq[i] = seq[i];
   for (int i = tid; i < MT_N; i += MT_THREADS) stab[i] = table[(size_t)(p * mult - 1) * MT_N + i];
   __syncthreads();
-  if (tid < MT_N) {
-    uint32_t acc = 0;
-    const uint32_t* sj = sseq + tid + 1;
-    for (int w = 0; w < MT_N; ++w) {
-      const uint32_t bits = stab[w];
-      const uint32_t* sw = sj + 32 * w;
+  // thread t owns output words t and t + 512 (the latter for t < 112)
+  uint32_t acc0 = 0, acc1 = 0;
+  const uint32_t* sj0 = sseq + tid + 1;
+  const bool two = tid + MT_THREADS < MT_N;
+  const uint32_t* sj1 = sseq + (two ? tid + MT_THREADS : tid) + 1;
+  for (int w = 0; w < MT_N; ++w) {
+    const uint32_t bits = stab[w];
+    const uint32_t* s0 = sj0 + 32 * w;
+    const uint32_t* s1 = sj1 + 32 * w;
 #pragma unroll
-      for (int b = 0; b < 32; ++b) if ((bits >> b) & 1u) acc ^= sw[b];
-    }
-    windows[(size_t)p * MT_N + tid] = acc;
+    for (int b = 0; b < 32; ++b) if ((bits >> b) & 1u) { acc0 ^= s0[b]; if (two) acc1 ^= s1[b]; }
   }
+  windows[(size_t)p * MT_N + tid] = acc0;
+  if (two) windows[(size_t)p * MT_N + tid + MT_THREADS] = acc1;
 }
 
 // One 256-thread CTA per block runs the recurrence in shared memory (three 227-wide wavefronts per chunk), tempers

@@ -4,8 +4,8 @@ from bench import workload
 from sampleqc_b200 import api
 x, g, iz, prm = workload("C3", 1.0)
 D, J, K, N = prm["D"], prm["J"], prm["K"], prm["N"]
-for inline in (1, 0):
-    for nb in (10, 20, 40, 146):
+for inline in (0,):
+    for nb in (8, 12, 20, 40, 146):
         os.environ["SQC_RNG_INLINE"] = str(inline); os.environ["SQC_MT_BLOCKS"] = str(nb)
         s = api.Session(x, g, D, J, K, N, 6, init_z=iz, rng_mode=0)
         s.profile(True); s.run(); s.run()
