@@ -254,14 +254,16 @@ def main():
         h2d = xp.nbytes + gp.nbytes + zp.nbytes
         e2e_iters = 0
 
+        from sampleqc_b200 import _abi as A
+        obufs = A.FitBuffers(D, j1 - j0, K, i1 - i0, EM_ITERS, A.SQC_VARIANT_ROBUST, False, alloc=pinned)   # caller-owned, reused every step
+
         def one():
             nonlocal e2e_iters
-            pinned.keep = pinned.keep[:3]
             if world > 1:
                 from sampleqc_b200 import multigpu
-                fit = multigpu.fit_robust_sharded(dist, local, rank, world, xp, zp, gp, D, j1 - j0, K, i1 - i0, i0, N, EM_ITERS, MCD_ALPHA, MCD_ITERS, SEED, rng_mode, alloc=pinned)
+                fit = multigpu.fit_robust_sharded(dist, local, rank, world, xp, zp, gp, D, j1 - j0, K, i1 - i0, i0, N, EM_ITERS, MCD_ALPHA, MCD_ITERS, SEED, rng_mode, out=obufs)
             else:
-                fit = api.fit_sampleqc_robust_cpp(xp, zp, gp, D, J, K, N, EM_ITERS, MCD_ALPHA, MCD_ITERS, SEED, rng_mode=rng_mode, device=local, alloc=pinned)
+                fit = api.fit_sampleqc_robust_cpp(xp, zp, gp, D, J, K, N, EM_ITERS, MCD_ALPHA, MCD_ITERS, SEED, rng_mode=rng_mode, device=local, out=obufs)
             e2e_iters = fit["n_iter"]
             return fit
         for _ in range(2):

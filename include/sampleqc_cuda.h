@@ -196,6 +196,9 @@ SQC_API int sqc_xchg_export(int device, void* handle_out /* SQC_IPC_HANDLE_BYTES
 SQC_API int sqc_xchg_release(int device);
 
 /* ---- misc ------------------------------------------------------------------------------ */
+/* Finished fits keep their device memory in a per-device cache (allocation costs tens of ms); this
+ * releases it.  device < 0: all devices.                                                       */
+SQC_API int         sqc_trim(int device);
 SQC_API int         sqc_abi_version(void);
 SQC_API int         sqc_device_count(void);          /* <0 on CUDA failure                            */
 SQC_API const char* sqc_status_name(int status);

@@ -17,7 +17,7 @@ EXPORTS = (
     "sqc_fit_robust", "sqc_fit_mle", "sqc_outlier_maha",
     "sqc_session_create", "sqc_session_run", "sqc_session_fetch", "sqc_session_stats", "sqc_session_profile",
     "sqc_session_destroy", "sqc_xchg_export", "sqc_xchg_release",
-    "sqc_abi_version", "sqc_device_count", "sqc_status_name", "sqc_device_qchisq", "sqc_device_rkeys", "sqc_device_expneg",
+    "sqc_trim", "sqc_abi_version", "sqc_device_count", "sqc_status_name", "sqc_device_qchisq", "sqc_device_rkeys", "sqc_device_expneg",
 )
 
 
@@ -53,6 +53,8 @@ def lib():
     L.sqc_xchg_export.restype = C.c_int
     L.sqc_xchg_release.argtypes = [C.c_int]
     L.sqc_xchg_release.restype = C.c_int
+    L.sqc_trim.argtypes = [C.c_int]
+    L.sqc_trim.restype = C.c_int
     L.sqc_abi_version.restype = C.c_int
     L.sqc_device_count.restype = C.c_int
     L.sqc_status_name.argtypes = [C.c_int]

@@ -22,11 +22,12 @@ from ._lib import check, lib
 
 
 def fit_sampleqc_robust_cpp(x, init_z, groups, D, J, K, N, em_iters, mcd_alpha, mcd_iters, seed, track=False,
-                            rng_mode=SQC_RNG_R_COMPAT, device=-1, alloc=None):
-    """reference src/fit_sampleQC_robust_cpp.cpp:451-577; returns the Rcpp list as a dict (:562-575)."""
+                            rng_mode=SQC_RNG_R_COMPAT, device=-1, alloc=None, out=None):
+    """reference src/fit_sampleQC_robust_cpp.cpp:451-577; returns the Rcpp list as a dict (:562-575).
+    `out`: a FitBuffers of matching shape to be reused across calls (e.g. pinned host memory)."""
     args, keep = A.make_fit_args(x, groups, D, J, K, N, em_iters, init_z=init_z, mcd_alpha=mcd_alpha,
                                  mcd_iters=mcd_iters, seed=seed, track=track, rng_mode=rng_mode, device=device)
-    bufs = A.FitBuffers(D, J, K, N, em_iters, SQC_VARIANT_ROBUST, track, alloc=alloc)
+    bufs = out if out is not None else A.FitBuffers(D, J, K, N, em_iters, SQC_VARIANT_ROBUST, track, alloc=alloc)
     err = C.create_string_buffer(512)
     check(lib().sqc_fit_robust(C.byref(args), C.byref(bufs.out), err, 512), err)
     return bufs.as_list()

@@ -11,9 +11,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -189,6 +192,40 @@ __global__ void __launch_bounds__(256) k_outlier_maha(const double* x, const int
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
+// device memory: sessions carve their buffers out of a few large chunks; finished sessions hand the chunks to a
+// per-device cache instead of cudaFree (cudaMalloc / cudaFree of GBs cost tens of ms and synchronise the device),
+// so repeated fits — one per sample group in fit_sampleqc(K_list = ...) — pay for the allocation once.
+// sqc_trim() releases the cache.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct Chunk { char* base; size_t bytes; };
+struct ChunkCache {
+  std::mutex mu; std::vector<Chunk> free_chunks[64];
+  Chunk take(int device, size_t bytes) {
+    std::lock_guard<std::mutex> lk(mu);
+    auto& v = free_chunks[device & 63];
+    int best = -1;
+    for (int i = 0; i < (int)v.size(); ++i) if (v[i].bytes >= bytes && (best < 0 || v[i].bytes < v[best].bytes)) best = i;
+    if (best >= 0) { Chunk c = v[best]; v.erase(v.begin() + best); return c; }
+    // nothing fits: drop the cached chunks (they would only fragment the device) and allocate
+    for (auto& c : v) cudaFree(c.base);
+    v.clear();
+    Chunk c{nullptr, bytes};
+    cudaError_t e = cudaMalloc((void**)&c.base, bytes);
+    if (e != cudaSuccess) fail(e == cudaErrorMemoryAllocation ? SQC_ERR_NOMEM : SQC_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    return c;
+  }
+  void give(int device, Chunk c) { std::lock_guard<std::mutex> lk(mu); free_chunks[device & 63].push_back(c); }
+  void trim(int device) {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& c : free_chunks[device & 63]) cudaFree(c.base);
+    free_chunks[device & 63].clear();
+  }
+};
+ChunkCache g_chunks;
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
 // session
 // ---------------------------------------------------------------------------------------------
 struct sqc_session {
@@ -219,18 +256,23 @@ struct sqc_session {
   bool ran = false;
   Control h_ctl{};
 
+  std::vector<Chunk> chunks; size_t chunk_used = 0, first_chunk_bytes = 64ull << 20;
   template <class T> T* alloc(size_t n, bool zero = true) {
-    void* p = nullptr;
-    size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
-    CK(cudaMalloc(&p, bytes));
-    allocs.push_back(p);
+    const size_t bytes = (std::max<size_t>(n, 1) * sizeof(T) + 255) & ~(size_t)255;
+    if (chunks.empty() || chunk_used + bytes > chunks.back().bytes) {
+      chunks.push_back(g_chunks.take(device, std::max(bytes, chunks.empty() ? first_chunk_bytes : (size_t)(64ull << 20))));
+      chunk_used = 0;
+    }
+    void* p = chunks.back().base + chunk_used;
+    chunk_used += bytes;
     if (zero) CK(cudaMemsetAsync(p, 0, bytes, st));
     return (T*)p;
   }
   ~sqc_session() {
     if (device >= 0) cudaSetDevice(device);
     xchg_close(xc);
-    for (void* p : allocs) cudaFree(p);
+    if (st) cudaStreamSynchronize(st);
+    for (auto& c : chunks) g_chunks.give(device, c);
     for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     if (ev_run0) cudaEventDestroy(ev_run0);
     if (ev_init) cudaEventDestroy(ev_init);
@@ -422,8 +464,7 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
   sqc_session* S = up.get();
   select_device(a->device, &S->device);
   CK(cudaStreamCreateWithFlags(&S->st, cudaStreamNonBlocking));
-  cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, S->device));
-  S->n_sm = prop.multiProcessorCount;
+  CK(cudaDeviceGetAttribute(&S->n_sm, cudaDevAttrMultiProcessorCount, S->device));
   S->D = a->D; S->J = a->J; S->K = a->K; S->N = a->N; S->variant = variant;
   S->world = a->world > 1 ? a->world : 1; S->rank = S->world > 1 ? a->rank : 0;
   S->N_total = S->world > 1 ? a->N_total : a->N;
@@ -433,14 +474,48 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
   const int D = S->D, J = S->J, K = S->K; const long long N = S->N;
   const int em = std::max(S->em_iters, 0);
 
-  // ---- sample layout: cells of a sample must be contiguous; permute once if they are not -------
+  // one chunk for (almost) everything: generous estimate of what the session will carve out
+  {
+    const double n = (double)N, nt = (double)S->N_total;
+    double est = n * (8.0 * D * 2 + 16) + nt * 8.0 + 64.0 * (K + 2) * 8 * D;
+    est += (n / tile_cells(D) + J + 16) * (K * (16.0 + 8 * D) + 64 + 8.0 * D + (variant == SQC_VARIANT_MLE ? 8.0 * K * SQC_NMOM(D) : 0.0));
+    est += (double)K * 256 * MCD_WARPS * MCD_CAPW * (12.0 + 8 * D) + (double)J * (K * (24.0 + 8 * D) + 16.0 * D) + (32 << 20);
+    if (variant == SQC_VARIANT_MLE) est += n * 16.0 * K;
+    if (S->track) est += (double)em * (J * (D + K) + K * D * (D + 1)) * 8.0;
+    S->first_chunk_bytes = (size_t)est;
+  }
+  // ---- upload x first (asynchronous from pinned memory), scan the sample layout on the host meanwhile ----
+  Dev& s = S->dev;
+  s.x = S->alloc<double>((size_t)N * D, false);
+  CK(cudaMemcpyAsync(s.x, a->x, (size_t)N * D * sizeof(double), cudaMemcpyHostToDevice, S->st));
+  // cells of a sample must be contiguous; permute once if they are not
   std::vector<long long> n_j(J, 0);
   bool sorted = true;
-  for (long long i = 0; i < N; ++i) {
-    const int g = a->groups[i];
-    if (g < 0 || g >= J) fail(SQC_ERR_BAD_ARG, "groups out of range at cell %lld", i);
-    n_j[g]++;
-    if (i && g < a->groups[i - 1]) sorted = false;
+  {
+    const int nth = (N >= (1 << 20)) ? 4 : 1;           // a few host threads: the scan hides behind the upload of x
+    std::vector<std::vector<long long>> cnt(nth, std::vector<long long>(J, 0));
+    std::vector<long long> bad(nth, -1); std::vector<char> srt(nth, 1);
+    auto scan = [&](int t) {
+      const long long i0 = N * t / nth, i1 = N * (t + 1) / nth;
+      long long* c = cnt[t].data();
+      int prev = i0 ? a->groups[i0 - 1] : -1;
+      for (long long i = i0; i < i1; ++i) {
+        const int g = a->groups[i];
+        if ((unsigned)g >= (unsigned)J) { bad[t] = i; return; }
+        c[g]++;
+        if (g < prev) srt[t] = 0;
+        prev = g;
+      }
+    };
+    std::vector<std::thread> th;
+    for (int t = 1; t < nth; ++t) th.emplace_back(scan, t);
+    scan(0);
+    for (auto& x : th) x.join();
+    for (int t = 0; t < nth; ++t) {
+      if (bad[t] >= 0) { cudaStreamSynchronize(S->st); fail(SQC_ERR_BAD_ARG, "groups out of range at cell %lld", bad[t]); }
+      if (!srt[t]) sorted = false;
+      for (int j = 0; j < J; ++j) n_j[j] += cnt[t][j];
+    }
   }
   S->sorted = sorted;
   if (!sorted) {                                    // stable counting sort by sample
@@ -463,10 +538,8 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
   }
   const int T = (int)t_start.size();
 
-  Dev& s = S->dev;
   s.D = D; s.J = J; s.K = K; s.T = T; s.N = N; s.N_total = S->N_total; s.cell_offset = S->world > 1 ? a->cell_offset : 0;
   s.em_iters = S->em_iters; s.mcd_iters = S->mcd_iters; s.rng_mode = S->rng_mode; s.track = S->track; s.mcd_alpha = S->mcd_alpha; s.seed = S->seed;
-  s.x = S->alloc<double>((size_t)N * D, false);
   s.z = S->alloc<uint8_t>(N);
   auto up_i = [&](const std::vector<int>& v) { int* p = S->alloc<int>(v.size(), false); CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, S->st)); return p; };
   s.tile_start = up_i(t_start); s.tile_len = up_i(t_len); s.tile_sample = up_i(t_sample); s.sample_tile_begin = up_i(s_tb); s.sample_n = up_i(s_n);
@@ -494,9 +567,8 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
   S->optr.sigma = S->optr.beta + (size_t)K * D; S->optr.p_jk = S->optr.sigma + (size_t)K * D * D; S->optr.z = S->o_z; S->optr.korder = S->o_korder;
 
   // ---- upload ----------------------------------------------------------------------------------
-  if (sorted) {
-    CK(cudaMemcpyAsync(s.x, a->x, (size_t)N * D * sizeof(double), cudaMemcpyHostToDevice, S->st));
-  } else {
+  if (!sorted) {                                    // the optimistic upload above was in the wrong order
+    CK(cudaStreamSynchronize(S->st));
     std::vector<double> col(N);
     for (int d = 0; d < D; ++d) {
       for (long long i = 0; i < N; ++i) col[i] = a->x[(size_t)d * N + S->perm[i]];
@@ -514,13 +586,12 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
     S->z0 = S->alloc<uint8_t>(N, false);
     int* bad = S->alloc<int>(1);
     {                                               // labels travel as int32 (the export's arma::uvec); narrow on the device
-      int* tmp = nullptr; CK(cudaMalloc((void**)&tmp, (size_t)N * sizeof(int)));
+      int* tmp = S->o_z;                               // the output label buffer doubles as the int32 staging area
       if (sorted) CK(cudaMemcpyAsync(tmp, a->init_z, (size_t)N * sizeof(int), cudaMemcpyHostToDevice, S->st));
       else { std::vector<int> zz(N); for (long long i = 0; i < N; ++i) zz[i] = a->init_z[S->perm[i]]; CK(cudaMemcpy(tmp, zz.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice)); }
       k_widen_labels<<<std::min<long long>((N + 255) / 256, 4096), 256, 0, S->st>>>(tmp, S->z0, N, K, bad);
       int hb = 0; CK(cudaMemcpyAsync(&hb, bad, sizeof(int), cudaMemcpyDeviceToHost, S->st));
       CK(cudaStreamSynchronize(S->st));
-      cudaFree(tmp);
       if (hb) fail(SQC_ERR_BAD_ARG, "init_z out of range");
     }
     s.rs_stride = ((N + 32ll * (K + 1)) + 31) & ~31ll;
@@ -765,15 +836,20 @@ template <class F> int guarded(F&& f, char* err, size_t errlen) {
   catch (const std::exception& e) { if (err && errlen) snprintf(err, errlen, "%s", e.what()); return SQC_ERR_CUDA; }
 }
 
+double now_ms() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+
 int one_shot(const sqc_fit_args* a, sqc_fit_out* o, int variant, char* err, size_t errlen) {
   sqc_session* S = nullptr;
+  const bool timing = getenv("SQC_TIMING") != nullptr;
+  double t0 = now_ms(), t1 = t0, t2 = t0, t3 = t0;
   int st = guarded([&] {
     if (!o) fail(SQC_ERR_BAD_ARG, "null output");
-    S = session_create(a, variant);
-    session_run(S);
-    session_fetch(S, o);
+    S = session_create(a, variant); t1 = now_ms();
+    session_run(S); t2 = now_ms();
+    session_fetch(S, o); t3 = now_ms();
   }, err, errlen);
   delete S;
+  if (timing) fprintf(stderr, "[sqc timing] create %.2f ms  run %.2f ms  fetch %.2f ms  destroy %.2f ms\n", t1 - t0, t2 - t1, t3 - t2, now_ms() - t3);
   return st;
 }
 
@@ -860,6 +936,12 @@ int sqc_xchg_export(int device, void* handle_out, char* err, size_t errlen) {
 }
 int sqc_xchg_release(int device) { return xchg_release(device); }
 
+int sqc_trim(int device) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return SQC_ERR_CUDA;
+  for (int d = 0; d < n; ++d) if (device < 0 || device == d) { cudaSetDevice(d); g_chunks.trim(d); }
+  return SQC_OK;
+}
 int sqc_abi_version(void) { return SQC_ABI_VERSION; }
 int sqc_device_count(void) { int n = 0; cudaError_t e = cudaGetDeviceCount(&n); return e == cudaSuccess ? n : -1; }
 const char* sqc_status_name(int st) {

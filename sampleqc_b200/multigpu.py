@@ -71,13 +71,13 @@ def assemble(dist, rank: int, world: int, fit: dict, shard, J: int, N: int):
 
 
 def fit_robust_sharded(dist, local_device, rank, world, x_local, init_z_local, groups_local, D, J_local, K, N_local,
-                       cell_offset, N_total, em_iters, mcd_alpha, mcd_iters, seed, rng_mode=A.SQC_RNG_R_COMPAT, alloc=None, track=False):
+                       cell_offset, N_total, em_iters, mcd_alpha, mcd_iters, seed, rng_mode=A.SQC_RNG_R_COMPAT, alloc=None, track=False, out=None):
     """this rank's part of a sharded fit_sampleqc_robust_cpp; every rank must call it (returns the local list)"""
     from ._lib import check, lib
     kw = exchange_kwargs(dist, local_device, rank, world, cell_offset, N_total)
     args, keep = A.make_fit_args(x_local, groups_local, D, J_local, K, N_local, em_iters, init_z=init_z_local, mcd_alpha=mcd_alpha,
                                  mcd_iters=mcd_iters, seed=seed, track=track, rng_mode=rng_mode, device=local_device, **kw)
-    bufs = A.FitBuffers(D, J_local, K, N_local, em_iters, A.SQC_VARIANT_ROBUST, track, alloc=alloc)
+    bufs = out if out is not None else A.FitBuffers(D, J_local, K, N_local, em_iters, A.SQC_VARIANT_ROBUST, track, alloc=alloc)
     err = C.create_string_buffer(512)
     check(lib().sqc_fit_robust(C.byref(args), C.byref(bufs.out), err, 512), err)
     return bufs.as_list()
