@@ -34,7 +34,8 @@ namespace sqc {
 #endif
 constexpr int MCD_THREADS = SQC_MCD_THREADS;         // one fat CTA per SM: one histogram per SM
 constexpr int MCD_WARPS = MCD_THREADS / 32;
-constexpr int MCD_NB = 4096;                         // histogram bins per window (and fine bins per candidate bin)
+constexpr int MCD_NB = 4096;                         // histogram bins per window
+constexpr int MCD_NF = 1024;                         // fine bins inside the candidate bin (leader post; a 4 KB exchange on multi-GPU)
 constexpr int MCD_CAND_CAP = 8192;                   // a bin holding more cells than this is refined by another HIST round
 constexpr int MCD_CAPW = 32;                         // candidate slots per (CTA, warp, cluster) region
 constexpr int MCD_TINY = 512;                        // tie candidates (inside one fine bin) over all ranks
@@ -497,26 +498,26 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         // ---- COLLECT post: exact members of the candidate bin, then the moments ---------------
         const bool need_mom = (phase == PH_KEY_COLLECT) || !cl.is_final;
         const unsigned long long blo = cl.blo;
-        const int fshift = cl.shift > 12 ? cl.shift - 12 : 0;        // 4096 fine bins inside the candidate bin
+        const int fshift = cl.shift > 10 ? cl.shift - 10 : 0;        // MCD_NF = 1024 fine bins inside the candidate bin
         const unsigned int* ccnt = mb.cand_cnt + (long long)k * regions;
-        for (int i = tid; i < MCD_NB + 4; i += MCD_THREADS) sh_hist[i] = 0u;
+        for (int i = tid; i < MCD_NF + 4; i += MCD_THREADS) sh_hist[i] = 0u;
         if (tid == 0) { sh_flag[4] = 0; sh_flag[5] = 0; }
         __syncthreads();
         // 1. fine histogram of the candidates (regions in fixed order: thread t owns regions t, t + 512, ...)
         for (int rg = tid; rg < regions; rg += MCD_THREADS) {
           unsigned int cnum = ccnt[rg];
-          if (cnum > (unsigned)MCD_CAPW) { sh_hist[MCD_NB + 1] = 1u; cnum = MCD_CAPW; }     // region overflow -> refine
+          if (cnum > (unsigned)MCD_CAPW) { sh_hist[MCD_NF + 1] = 1u; cnum = MCD_CAPW; }     // region overflow -> refine
           const long long cb = ((long long)k * regions + rg) * MCD_CAPW;
           for (unsigned int sl = 0; sl < cnum; ++sl) atomicAdd(&sh_hist[(unsigned int)((mb.cand_bits[cb + sl] - blo) >> fshift)], 1u);
         }
         __syncthreads();
         if (tr) trow[8] = gtimer();
-        if (world > 1) xchg_sum_u32(mb.xc, k, sh_hist, MCD_NB + 2);
-        const bool overflow = sh_hist[MCD_NB + 1] != 0;
-        constexpr int PER = (MCD_NB + MCD_THREADS - 1) / MCD_THREADS;
+        if (world > 1) xchg_sum_u32(mb.xc, k, sh_hist, MCD_NF + 2);
+        const bool overflow = sh_hist[MCD_NF + 1] != 0;
+        constexpr int PER = (MCD_NF + MCD_THREADS - 1) / MCD_THREADS;
         unsigned int hv[PER]; long long mine = 0;
 #pragma unroll
-        for (int i = 0; i < PER; ++i) { hv[i] = (tid * PER + i < MCD_NB) ? sh_hist[tid * PER + i] : 0u; mine += hv[i]; }
+        for (int i = 0; i < PER; ++i) { hv[i] = (tid * PER + i < MCD_NF) ? sh_hist[tid * PER + i] : 0u; mine += hv[i]; }
         long long ncand_all;
         long long run = block_excl_scan<MCD_THREADS>(mine, sh_scan, &ncand_all);
         const long long take = cl.h - cl.below;                      // candidates (over all ranks) that belong to the h-subset

@@ -59,9 +59,8 @@ __device__ inline unsigned long long xchg_publish(const XchgDev& x, int ch, cons
   const unsigned long long seq = sh_seq;
   unsigned int* dst = (unsigned int*)xw_slot(x.peer[x.rank], ch, seq);
   for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = src[i];
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) st_release_sys_u64(xw_flag(x.peer[x.rank], ch), seq);
+  __syncthreads();                                   // the block's stores happen-before thread 0's release (cumulativity)
+  if (threadIdx.x == 0) { __threadfence_system(); st_release_sys_u64(xw_flag(x.peer[x.rank], ch), seq); }
   if ((int)threadIdx.x < x.world) {
     const unsigned long long* f = xw_flag(x.peer[threadIdx.x], ch);
     while (ld_acquire_sys_u64(f) < seq) { }
@@ -72,24 +71,43 @@ __device__ inline unsigned long long xchg_publish(const XchgDev& x, int ch, cons
 __device__ __forceinline__ const unsigned int* xchg_peer_slot(const XchgDev& x, int ch, unsigned long long seq, int r) {
   return (const unsigned int*)xw_slot(x.peer[r], ch, seq);
 }
-// sum of 32-bit counters over ranks, in place (block-wide)
+__device__ __forceinline__ uint4 ld_relaxed_sys_v4(const unsigned int* p) {      // 16-byte aligned; not volatile: loads may overlap
+  uint4 v; asm("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+// sum of 32-bit counters over ranks, in place (block-wide).  n is rounded up to a multiple of 4 words (the slots
+// are 16-byte aligned and larger than any message); every thread issues all its remote 128-bit loads before it
+// uses any of them, so one exchange costs about one NVLink round trip.
 __device__ inline void xchg_sum_u32(const XchgDev& x, int ch, unsigned int* buf, int n) {
   const unsigned long long seq = xchg_publish(x, ch, buf, n);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    unsigned int a = 0;
-    for (int r = 0; r < x.world; ++r) a += ld_relaxed_sys_u32(xchg_peer_slot(x, ch, seq, r) + i);
-    buf[i] = a;
+  const int n4 = (n + 3) >> 2;
+  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+    uint4 v[XCHG_MAX_WORLD];
+#pragma unroll
+    for (int r = 0; r < XCHG_MAX_WORLD; ++r) if (r < x.world) v[r] = ld_relaxed_sys_v4(xchg_peer_slot(x, ch, seq, r) + 4 * i);
+    uint4 a = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+    for (int r = 0; r < XCHG_MAX_WORLD; ++r) if (r < x.world) { a.x += v[r].x; a.y += v[r].y; a.z += v[r].z; a.w += v[r].w; }
+    if (4 * i + 0 < n) buf[4 * i + 0] = a.x;
+    if (4 * i + 1 < n) buf[4 * i + 1] = a.y;
+    if (4 * i + 2 < n) buf[4 * i + 2] = a.z;
+    if (4 * i + 3 < n) buf[4 * i + 3] = a.w;
   }
   __syncthreads();
 }
 // sum of doubles over ranks in rank order (bit-identical on every rank), in place (block-wide)
 __device__ inline void xchg_sum_f64(const XchgDev& x, int ch, double* buf, int n) {
   const unsigned long long seq = xchg_publish(x, ch, (const unsigned int*)buf, 2 * n);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    double a = 0.0;
-    for (int r = 0; r < x.world; ++r)
-      a += __longlong_as_double((long long)ld_relaxed_sys_u64((const unsigned long long*)xchg_peer_slot(x, ch, seq, r) + i));
-    buf[i] = a;
+  const int n2 = (n + 1) >> 1;
+  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+    uint4 v[XCHG_MAX_WORLD];
+#pragma unroll
+    for (int r = 0; r < XCHG_MAX_WORLD; ++r) if (r < x.world) v[r] = ld_relaxed_sys_v4(xchg_peer_slot(x, ch, seq, r) + 4 * i);
+    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+    for (int r = 0; r < XCHG_MAX_WORLD; ++r) if (r < x.world) { a0 += __hiloint2double((int)v[r].y, (int)v[r].x); a1 += __hiloint2double((int)v[r].w, (int)v[r].z); }
+    buf[2 * i] = a0;
+    if (2 * i + 1 < n) buf[2 * i + 1] = a1;
   }
   __syncthreads();
 }
