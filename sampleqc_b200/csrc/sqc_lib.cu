@@ -640,8 +640,11 @@ void mt_generate(cudaStream_t stream, const uint32_t* st_in, uint32_t* st_out, u
   long long done = 0; int w = 0;
   const uint32_t* cur = st_in;
   if (n <= 0) { CK(cudaMemcpyAsync(st_out, st_in, 625 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream)); return; }
-  // block length = mult * 110 chunks; about target_blocks blocks per call
-  int mult = (int)std::max<long long>(1, std::min<long long>(SQC_MT_JUMP_ROWS / 2, (n / MT_BLOCK_WORDS + target_blocks / 2) / target_blocks));
+  // block length = mult * 110 chunks.  One wave serves up to 149 blocks; the shortest blocks (mult = 1) give the
+  // shortest latency and are used whenever a wave is filled; target_blocks < 146 asks for longer blocks (tests).
+  int mult = 1;
+  if (target_blocks < SQC_MT_JUMP_ROWS - 2)
+    mult = (int)std::max<long long>(1, std::min<long long>(SQC_MT_JUMP_ROWS / 2, (n / MT_BLOCK_WORDS + target_blocks / 2) / target_blocks));
   const long long blk_words = MT_BLOCK_WORDS * mult;
   const long long wave_words = (long long)(SQC_MT_JUMP_ROWS / mult + 1) * blk_words;
   while (done < n) {
