@@ -656,8 +656,8 @@ void mt_generate(cudaStream_t stream, const uint32_t* st_in, uint32_t* st_out, u
     else k_mt_seq<<<1, 256, 0, stream>>>(cur, seq, ctl);
     uint32_t* windows = seq + MT_SEQ_WORDS;                        // (SQC_MT_JUMP_ROWS + 1) x 624 behind the sequence
     if (nb > 1) {
-      if (S) { Launch L(S, SQC_KF_RNG); k_mt_jump<<<nb - 1, MT_THREADS, MT_SMEM, stream>>>(cur, seq, table, windows, m, mult, ctl); L.done(); }
-      else k_mt_jump<<<nb - 1, MT_THREADS, MT_SMEM, stream>>>(cur, seq, table, windows, m, mult, ctl);
+      if (S) { Launch L(S, SQC_KF_RNG); k_mt_jump<<<nb - 1, MT_JUMP_THREADS, MT_SMEM, stream>>>(cur, seq, table, windows, m, mult, ctl); L.done(); }
+      else k_mt_jump<<<nb - 1, MT_JUMP_THREADS, MT_SMEM, stream>>>(cur, seq, table, windows, m, mult, ctl);
     }
     if (S) { Launch L(S, SQC_KF_RNG); k_mt_gen<<<nb, MT_GEN_THREADS, 0, stream>>>(cur, nxt, seq, windows, out + done, m, mult, ctl); L.done(); }
     else k_mt_gen<<<nb, MT_GEN_THREADS, 0, stream>>>(cur, nxt, seq, windows, out + done, m, mult, ctl);

@@ -20,8 +20,6 @@ constexpr int MT_SEQ_CHUNKS = 33;                         // 33 * 624 = 20 592 >
 constexpr int MT_SEQ_WORDS = MT_SEQ_CHUNKS * MT_N;
 constexpr int MT_BLOCK_CHUNKS = SQC_MT_CHUNKS_PER_BLOCK;  // 110
 constexpr long long MT_BLOCK_WORDS = (long long)MT_BLOCK_CHUNKS * MT_N;
-constexpr int MT_THREADS = 512;                          // <= 32 registers: fits beside the persistent M-step kernel
-constexpr size_t MT_SMEM = (size_t)(MT_SEQ_WORDS + MT_N) * sizeof(uint32_t);
 
 // one regeneration: nxt[0..623] from cur[0..623]  (dependency distance 227 -> three wavefronts)
 __device__ __forceinline__ void mt_regen(const uint32_t* cur, uint32_t* nxt, int tid) {
@@ -48,33 +46,61 @@ __global__ void __launch_bounds__(256) k_mt_seq(const uint32_t* st, uint32_t* se
   }
 }
 
-// window of block p = 1 .. nb-1 (row p * mult - 1 of the jump table correlated with the 33-chunk sequence)
-__global__ void __launch_bounds__(MT_THREADS, 2) k_mt_jump(const uint32_t* st_in, const uint32_t* seq, const uint32_t* table, uint32_t* windows,
-                                                        long long n, int mult, const Control* ctl) {
-  extern __shared__ uint32_t sh_mt[];
-  uint32_t* sseq = sh_mt;                         // MT_SEQ_WORDS
-  uint32_t* stab = sseq + MT_SEQ_WORDS;           // 624 table words
+// window of block p = 1 .. nb-1: row p * mult - 1 of the jump table correlated with the 33-chunk sequence,
+//     window[j] = XOR_{i : bit i of the row} seq[i + j + 1],   j = 0 .. 623.
+// Register-tiled: a thread owns 8 consecutive outputs and walks the taps 32 at a time; the 39 sequence words a
+// table word can touch are fetched with ten 128-bit shared-memory loads and reused for all (tap, output) pairs,
+// so shared-memory traffic is ~1 byte per pair instead of 4.  The taps are split over 6 groups of 3 warps
+// (the tap bits are warp-uniform: no divergence); the 6 partial windows are XOR-ed through shared memory.
+constexpr int MT_JT = 96;                                 // threads per tap group (78 own outputs, 3 warps)
+constexpr int MT_JG = 6;                                  // tap groups: 624 / 6 = 104 table words each
+constexpr int MT_JUMP_THREADS = MT_JT * MT_JG;            // 576
+constexpr int MT_SEQ_PAD = MT_SEQ_WORDS + 64;             // the last tiles read a few words past the sequence
+constexpr size_t MT_SMEM = (size_t)(MT_SEQ_PAD + MT_N + MT_JG * MT_N) * sizeof(uint32_t);
+__global__ void __launch_bounds__(MT_JUMP_THREADS) k_mt_jump(const uint32_t* st_in, const uint32_t* seq, const uint32_t* table, uint32_t* windows,
+                                                             long long n, int mult, const Control* ctl) {
+  extern __shared__ __align__(16) uint32_t sh_mt[];
+  uint32_t* sseq = sh_mt;                         // sseq[m] = seq[m + 1]
+  uint32_t* stab = sseq + MT_SEQ_PAD;             // 624 table words
+  uint32_t* spart = stab + MT_N;                  // MT_JG x 624 partial windows
   if (ctl && !ctl->cont) return;
   const int tid = threadIdx.x, p = blockIdx.x + 1;
   const long long u_end = (long long)st_in[MT_N] + n;
   if ((long long)p * MT_BLOCK_WORDS * mult >= u_end) return;          // block past the last draw
-  for (int i = tid; i < MT_SEQ_WORDS; i += MT_THREADS) sseq[i] = seq[i];
-  for (int i = tid; i < MT_N; i += MT_THREADS) stab[i] = table[(size_t)(p * mult - 1) * MT_N + i];
+  for (int i = tid; i < MT_SEQ_PAD; i += MT_JUMP_THREADS) sseq[i] = (i + 1 < MT_SEQ_WORDS) ? seq[i + 1] : 0u;
+  for (int i = tid; i < MT_N; i += MT_JUMP_THREADS) stab[i] = table[(size_t)(p * mult - 1) * MT_N + i];
   __syncthreads();
-  // thread t owns output words t and t + 512 (the latter for t < 112)
-  uint32_t acc0 = 0, acc1 = 0;
-  const uint32_t* sj0 = sseq + tid + 1;
-  const bool two = tid + MT_THREADS < MT_N;
-  const uint32_t* sj1 = sseq + (two ? tid + MT_THREADS : tid) + 1;
-  for (int w = 0; w < MT_N; ++w) {
-    const uint32_t bits = stab[w];
-    const uint32_t* s0 = sj0 + 32 * w;
-    const uint32_t* s1 = sj1 + 32 * w;
+  const int g = tid / MT_JT, t = tid % MT_JT;
+  uint32_t acc[8];
 #pragma unroll
-    for (int b = 0; b < 32; ++b) if ((bits >> b) & 1u) { acc0 ^= s0[b]; if (two) acc1 ^= s1[b]; }
+  for (int o = 0; o < 8; ++o) acc[o] = 0u;
+  if (t < MT_N / 8) {
+    const int w0 = g * (MT_N / MT_JG);
+    for (int w = w0; w < w0 + MT_N / MT_JG; ++w) {
+      const uint32_t bits = stab[w];
+      if (bits == 0u) continue;
+      const uint4* src = reinterpret_cast<const uint4*>(sseq + 32 * w + 8 * t);     // 32-byte aligned
+      uint32_t X[40];
+#pragma unroll
+      for (int v = 0; v < 10; ++v) { const uint4 q = src[v]; X[4 * v] = q.x; X[4 * v + 1] = q.y; X[4 * v + 2] = q.z; X[4 * v + 3] = q.w; }
+#pragma unroll
+      for (int b = 0; b < 32; ++b) {
+        if (bits & (1u << b)) {
+#pragma unroll
+          for (int o = 0; o < 8; ++o) acc[o] ^= X[b + o];
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 8; ++o) spart[g * MT_N + 8 * t + o] = acc[o];
   }
-  windows[(size_t)p * MT_N + tid] = acc0;
-  if (two) windows[(size_t)p * MT_N + tid + MT_THREADS] = acc1;
+  __syncthreads();
+  for (int j = tid; j < MT_N; j += MT_JUMP_THREADS) {
+    uint32_t a = 0u;
+#pragma unroll
+    for (int gg = 0; gg < MT_JG; ++gg) a ^= spart[gg * MT_N + j];
+    windows[(size_t)p * MT_N + j] = a;
+  }
 }
 
 // One 256-thread CTA per block runs the recurrence in shared memory (three 227-wide wavefronts per chunk), tempers
