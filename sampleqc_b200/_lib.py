@@ -53,16 +53,18 @@ def lib():
     L.sqc_xchg_export.restype = C.c_int
     L.sqc_xchg_release.argtypes = [C.c_int]
     L.sqc_xchg_release.restype = C.c_int
-    L.sqc_trim.argtypes = [C.c_int]
-    L.sqc_trim.restype = C.c_int
+    if hasattr(L, "sqc_trim"):
+        L.sqc_trim.argtypes = [C.c_int]
+        L.sqc_trim.restype = C.c_int
     L.sqc_abi_version.restype = C.c_int
     L.sqc_device_count.restype = C.c_int
     L.sqc_status_name.argtypes = [C.c_int]
     L.sqc_status_name.restype = C.c_char_p
     L.sqc_device_qchisq.argtypes = [A.c_double_p, A.c_double_p, A.c_double_p, C.c_int32, C.c_int, C.c_char_p, C.c_size_t]
     L.sqc_device_qchisq.restype = C.c_int
-    L.sqc_device_expneg.argtypes = [A.c_double_p, A.c_double_p, C.c_int32, C.c_int, C.c_char_p, C.c_size_t]
-    L.sqc_device_expneg.restype = C.c_int
+    if hasattr(L, "sqc_device_expneg"):
+        L.sqc_device_expneg.argtypes = [A.c_double_p, A.c_double_p, C.c_int32, C.c_int, C.c_char_p, C.c_size_t]
+        L.sqc_device_expneg.restype = C.c_int
     L.sqc_device_rkeys.argtypes = [C.c_uint32, C.c_int64, A.c_int32_p, C.c_int64, C.c_int, C.c_char_p, C.c_size_t]
     L.sqc_device_rkeys.restype = C.c_int
     if L.sqc_abi_version() != A.SQC_ABI_VERSION:

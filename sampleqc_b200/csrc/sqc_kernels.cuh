@@ -57,7 +57,7 @@ struct Dev {
   double* mu0; double* alpha; double* beta; double* sigma; double* linv; double* ainv; double* logP; double* Pk;
   double* p_jk; double* logp_jk;
   // tile partials / reduced statistics
-  double* t_ll1; double* t_ll2; int* t_nk; double* t_sk; int* t_base; double* t_col;
+  double* t_ll1; double* t_ll2; int* t_nk; double* t_sk; int* s_base; int* t_rel; unsigned int* done_ctr; double* t_col;
   int* n_jk; double* s_jk;
   long long* clu_n; long long* clu_off;        // local cells per cluster, segment offsets in rs
   long long* clu_n_glob; long long* clu_prefix; // cells per cluster over all shards; key-stream offset of the local segment
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(EST_THREADS, SQC_EST_MINB) k_estep(Dev s) {
 
 // ---------------------------------------------------------------------------------------------
 // like_1 + stable partition by label.  One CTA per tile.
-//   r_i = x_i - alpha_{j}  written to rs[d][clu_off[z] + t_base[tile][z] + rank in tile]
+//   r_i = x_i - alpha_{j}  written to rs[d][clu_off[z] + (cells of z in earlier samples / tiles) + rank in tile]
 //   (restrict_to_x_k :265-283 keeps original cell order inside each cluster; so does this).
 //   LIKE = 1: also the log-likelihood with the new alpha_j and the previous beta/Sigma/p_jk (:499).
 // ---------------------------------------------------------------------------------------------
@@ -278,7 +278,8 @@ __global__ void __launch_bounds__(EST_THREADS, SQC_PART_MINB) k_partition(Dev s)
   }
   __syncthreads();
   if (tid < s.K) {                                           // tiny serial scan per component
-    int run = s.t_base[t * s.K + tid];
+    // base of this tile inside the cluster segment: cells of the earlier samples (s_base) + of the earlier tiles of this sample (t_rel)
+    int run = s.s_base[j * s.K + tid] + s.t_rel[t * s.K + tid];
     for (int e = 0; e < CPT * NW; ++e) { int v = sh_cnt[e * s.K + tid]; sh_cnt[e * s.K + tid] = run; run += v; }
   }
   __syncthreads();
@@ -399,62 +400,55 @@ __global__ void k_init_alpha(Dev s) {
 
 // ---------------------------------------------------------------------------------------------
 // statistics reduction after an E-step / stats pass:
-//   blocks 0 .. : one warp per sample sums its tiles' partials -> n_jk, s_jk
-//   last block  : per-component exclusive scan of tile counts (partition bases), cluster sizes/offsets
+//   every block: one warp per sample sums its tiles' partials -> n_jk, s_jk
+//   the block that finishes last: per-component exclusive scan of n_jk over the samples (-> s_base: the
+//   position of a sample's first cell of component k inside the cluster-sorted segment), cluster sizes and
+//   segment offsets.  k_partition adds the counts of the earlier tiles of its own sample.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_post_stats(Dev s, int n_sample_blocks) {
   __shared__ long long sh_scan[33];
+  __shared__ int sh_last;
   if (!s.ctl->cont) return;
-  const int tid = threadIdx.x, lane = tid & 31;
-  if ((int)blockIdx.x < n_sample_blocks) {
+  const int tid = threadIdx.x, lane = tid & 31, K = s.K;
+  {
     const int j = blockIdx.x * 32 + (tid >> 5);
-    if (j >= s.J) return;
-    const int t0 = s.sample_tile_begin[j], t1 = s.sample_tile_begin[j + 1];
-    const int ne = s.K * (s.D + 1);
-    for (int e = lane; e < ne; e += 32) {
-      const int k = e / (s.D + 1), c = e % (s.D + 1);
-      if (c == 0) { int a = 0; for (int t = t0; t < t1; ++t) a += s.t_nk[t * s.K + k]; s.n_jk[j * s.K + k] = a; }
-      else { double a = 0.0; for (int t = t0; t < t1; ++t) a += s.t_sk[((long long)t * s.K + k) * s.D + (c - 1)]; s.s_jk[((long long)j * s.K + k) * s.D + (c - 1)] = a; }
+    if (j < s.J) {
+      const int t0 = s.sample_tile_begin[j], t1 = s.sample_tile_begin[j + 1];
+      const int ne = K * (s.D + 1);
+      for (int e = lane; e < ne; e += 32) {
+        const int k = e / (s.D + 1), c = e % (s.D + 1);
+        if (c == 0) { int a = 0; for (int t = t0; t < t1; ++t) { s.t_rel[t * K + k] = a; a += s.t_nk[t * K + k]; } s.n_jk[j * K + k] = a; }
+        else { double a = 0.0; for (int t = t0; t < t1; ++t) a += s.t_sk[((long long)t * K + k) * s.D + (c - 1)]; s.s_jk[((long long)j * K + k) * s.D + (c - 1)] = a; }
+      }
     }
-    return;
   }
-  // per-component exclusive scan of the tile counts: every thread owns a contiguous run of tiles, reads all K
-  // counters of a tile together (independent loads), then one block scan per component
-  const int per = (s.T + 1023) / 1024;
-  const int b0 = min(tid * per, s.T), b1 = min(b0 + per, s.T);
-  const int K = s.K;
-  int sums[SQC_MAXK];
-#pragma unroll
-  for (int k = 0; k < SQC_MAXK; ++k) sums[k] = 0;
-#pragma unroll 2
-  for (int t = b0; t < b1; ++t) {
-    const int* row = s.t_nk + (long long)t * K;
-#pragma unroll
-    for (int k = 0; k < SQC_MAXK; ++k) if (k < K) sums[k] += row[k];
-  }
-  long long run[SQC_MAXK];
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) sh_last = (atomicAdd(s.done_ctr, 1u) == (unsigned)n_sample_blocks - 1u) ? 1 : 0;
+  __syncthreads();
+  if (!sh_last) return;
+  __threadfence();
+  // exclusive scan over the samples, one block scan per component (thread t owns a contiguous run of samples)
+  const int per = (s.J + 1023) / 1024;
+  const int j0 = min(tid * per, s.J), j1 = min(j0 + per, s.J);
   long long off_run = 0;
-#pragma unroll
-  for (int k = 0; k < SQC_MAXK; ++k) {
-    run[k] = 0;
-    if (k < K) {
-      long long total;
-      run[k] = block_excl_scan<1024>((long long)sums[k], sh_scan, &total);
-      if (tid == 0) { s.clu_n[k] = total; s.clu_off[k] = off_run; }
-      off_run += (total + 31) & ~31ll;      // 256-byte aligned cluster segments
-      __syncthreads();
-    }
-  }
-#pragma unroll 2
-  for (int t = b0; t < b1; ++t) {
-    const int* row = s.t_nk + (long long)t * K;
-    int* out = s.t_base + (long long)t * K;
-#pragma unroll
-    for (int k = 0; k < SQC_MAXK; ++k) if (k < K) { out[k] = (int)run[k]; run[k] += row[k]; }
+  for (int k = 0; k < K; ++k) {
+    long long mine = 0;
+    for (int j = j0; j < j1; ++j) mine += __ldcg(s.n_jk + j * K + k);
+    long long total;
+    long long run = block_excl_scan<1024>(mine, sh_scan, &total);
+    for (int j = j0; j < j1; ++j) { s.s_base[j * K + k] = (int)run; run += __ldcg(s.n_jk + j * K + k); }
+    if (tid == 0) { s.clu_n[k] = total; s.clu_off[k] = off_run; }
+    off_run += (total + 31) & ~31ll;        // 256-byte aligned cluster segments
+    __syncthreads();
   }
   // single GPU: the key stream of one update_beta_scale_k call runs over the clusters in order
   // (SURVEY Appendix A3); the multi-GPU exchange overwrites these with the global values
-  if (tid == 0) { long long run = 0; for (int k = 0; k < s.K; ++k) { s.clu_n_glob[k] = s.clu_n[k]; s.clu_prefix[k] = run; run += s.clu_n[k]; } }
+  if (tid == 0) {
+    long long run = 0;
+    for (int k = 0; k < K; ++k) { s.clu_n_glob[k] = s.clu_n[k]; s.clu_prefix[k] = run; run += s.clu_n[k]; }
+    *s.done_ctr = 0u;
+  }
 }
 
 // alpha_j from the (j,k) statistics: update_alpha_j :116-157 with the per-cell sums factored out

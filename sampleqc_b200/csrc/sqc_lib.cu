@@ -259,8 +259,9 @@ struct sqc_session {
   std::vector<Chunk> chunks; size_t chunk_used = 0, first_chunk_bytes = 64ull << 20;
   template <class T> T* alloc(size_t n, bool zero = true) {
     const size_t bytes = (std::max<size_t>(n, 1) * sizeof(T) + 255) & ~(size_t)255;
-    if (chunks.empty() || chunk_used + bytes > chunks.back().bytes) {
-      chunks.push_back(g_chunks.take(device, std::max(bytes, chunks.empty() ? first_chunk_bytes : (size_t)(64ull << 20))));
+    static const bool no_arena = getenv("SQC_NO_ARENA") != nullptr;     // debug: one allocation per buffer
+    if (no_arena || chunks.empty() || chunk_used + bytes > chunks.back().bytes) {
+      chunks.push_back(g_chunks.take(device, no_arena ? bytes : std::max(bytes, chunks.empty() ? first_chunk_bytes : (size_t)(64ull << 20))));
       chunk_used = 0;
     }
     void* p = chunks.back().base + chunk_used;
@@ -326,13 +327,15 @@ template <int D> void launch_partition(sqc_session* S, int like) {
 template <int D> void launch_mcd(sqc_session* S) {
   Launch L(S, SQC_KF_MCD);
   void* args[] = {(void*)&S->dev, (void*)&S->mb};
-  CK(cudaLaunchCooperativeKernel((void*)k_mcd<D>, dim3(S->mcd_grid), dim3(MCD_THREADS), args, MCD_SMEM, S->st));
+  void* fn = S->world > 1 ? (void*)k_mcd<D, true> : (void*)k_mcd<D, false>;
+  CK(cudaLaunchCooperativeKernel(fn, dim3(S->mcd_grid), dim3(MCD_THREADS), args, MCD_SMEM, S->st));
   L.done();
 }
 template <int D> int mcd_max_grid(int n_sm) {
-  CK(cudaFuncSetAttribute(k_mcd<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MCD_SMEM));
+  CK(cudaFuncSetAttribute(k_mcd<D, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MCD_SMEM));
+  CK(cudaFuncSetAttribute(k_mcd<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MCD_SMEM));
   int per = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_mcd<D>, MCD_THREADS, MCD_SMEM));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_mcd<D, true>, MCD_THREADS, MCD_SMEM));
   if (per < 1) fail(SQC_ERR_CUDA, "k_mcd<%d> does not fit on an SM", D);
   return n_sm;                                   // one CTA per SM
 }
@@ -549,7 +552,7 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
   s.logP = S->alloc<double>(K); s.Pk = S->alloc<double>(K);
   s.p_jk = S->alloc<double>((size_t)J * K); s.logp_jk = S->alloc<double>((size_t)J * K);
   s.t_ll1 = S->alloc<double>(T); s.t_ll2 = S->alloc<double>(T);
-  s.t_nk = S->alloc<int>((size_t)T * K); s.t_sk = S->alloc<double>((size_t)T * K * D); s.t_base = S->alloc<int>((size_t)T * K);
+  s.t_nk = S->alloc<int>((size_t)T * K); s.t_sk = S->alloc<double>((size_t)T * K * D); s.s_base = S->alloc<int>((size_t)J * K); s.t_rel = S->alloc<int>((size_t)T * K); s.done_ctr = S->alloc<unsigned int>(4);
   s.t_col = S->alloc<double>((size_t)T * D);
   s.n_jk = S->alloc<int>((size_t)J * K); s.s_jk = S->alloc<double>((size_t)J * K * D);
   s.clu_n = S->alloc<long long>(K); s.clu_off = S->alloc<long long>(K); s.clu_n_glob = S->alloc<long long>(K); s.clu_prefix = S->alloc<long long>(K);
@@ -711,7 +714,7 @@ void run_robust(sqc_session* S) {
   }
   const int nsb = (J + 31) / 32;
   auto post_stats = [&]() {
-    Launch L(S, SQC_KF_UPDATE); k_post_stats<<<nsb + 1, 1024, 0, S->st>>>(s, nsb); L.done();
+    Launch L(S, SQC_KF_UPDATE); k_post_stats<<<nsb, 1024, 0, S->st>>>(s, nsb); L.done();
     if (S->world > 1) xchg_cluster_layout(S, s);
   };
   auto m_step = [&](int call, int like) {

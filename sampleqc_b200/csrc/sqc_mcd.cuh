@@ -215,7 +215,8 @@ __device__ inline bool prepare_dist(McdClu& c) {
 // ---------------------------------------------------------------------------------------------
 // the persistent kernel
 // ---------------------------------------------------------------------------------------------
-template <int D>
+// MULTI = false compiles the cross-GPU exchanges out: their register needs otherwise add spills to the streaming loop
+template <int D, bool MULTI>
 __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
   constexpr int NM = SQC_NMOM(D), CPT = McdCfg<D>::CPT, CHUNK = McdCfg<D>::CHUNK;
   extern __shared__ __align__(16) unsigned char sh_raw[];
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
 
   if (!s.ctl->cont) return;                    // uniform across the grid (and across ranks): nobody reaches a barrier
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, G = gridDim.x, b = blockIdx.x, K = s.K;
-  const int world = mb.xc.world > 1 ? mb.xc.world : 1, myrank = world > 1 ? mb.xc.rank : 0;
+  const int world = (MULTI && mb.xc.world > 1) ? mb.xc.world : 1, myrank = world > 1 ? mb.xc.rank : 0;
   const int regions = G * MCD_WARPS, region = b * MCD_WARPS + wid;
   unsigned int bar_gen = ld_acquire_u32(&mb.bar->gen);
   McdWork* W = mb.work;
@@ -450,7 +451,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
           W->cnt_below[k] = 0ull;
         }
         __syncthreads();
-        if (world > 1) xchg_sum_u32(mb.xc, k, sh_hist, MCD_NB + 3);      // (the two halves of `below` cannot carry: < 2^32 cells per rank)
+        if constexpr (MULTI) xchg_sum_u32(mb.xc, k, sh_hist, MCD_NB + 3);      // (the two halves of `below` cannot carry: < 2^32 cells per rank)
         const long long below = (long long)sh_hist[MCD_NB] + ((long long)sh_hist[MCD_NB + 1] << 32);
         const bool has_nan = sh_hist[MCD_NB + 2] != 0;
         constexpr int PER = (MCD_NB + MCD_THREADS - 1) / MCD_THREADS;
@@ -512,7 +513,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         }
         __syncthreads();
         if (tr) trow[8] = gtimer();
-        if (world > 1) xchg_sum_u32(mb.xc, k, sh_hist, MCD_NF + 2);
+        if constexpr (MULTI) xchg_sum_u32(mb.xc, k, sh_hist, MCD_NF + 2);
         const bool overflow = sh_hist[MCD_NF + 1] != 0;
         constexpr int PER = (MCD_NF + MCD_THREADS - 1) / MCD_THREADS;
         unsigned int hv[PER]; long long mine = 0;
@@ -567,7 +568,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         if (tr) trow[9] = gtimer();
         int ntie = min(sh_flag[4], MCD_TINY);
         // 3. tie list over all ranks: all-gather, then sort by (key, rank, position)
-        if (ok && world > 1) {
+        if (MULTI && ok) {
           // pack own list behind the fine histogram: [count, (key lo, key hi, pos) ...]
           unsigned int* pk = sh_hist;
           __syncthreads();
@@ -650,7 +651,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         __syncthreads();
         if (tr) trow[10] = gtimer();
         block_reduce_vec<NM>(tot, sh_red, sh_out);
-        if (ok && need_mom && world > 1) xchg_sum_f64(mb.xc, k, sh_out, NM);
+        if constexpr (MULTI) { if (ok && need_mom) xchg_sum_f64(mb.xc, k, sh_out, NM); }
         if (tr) trow[11] = gtimer();
         if (tid == 0) {
           if (!ok) {
