@@ -326,6 +326,8 @@ template <int D> void launch_partition(sqc_session* S, int like) {
 }
 template <int D> void launch_mcd(sqc_session* S) {
   Launch L(S, SQC_KF_MCD);
+  CK(cudaMemsetAsync(S->mb.epoch, 0, 2 * SQC_MAXK * sizeof(unsigned int), S->st));     // cluster epochs / worker arrivals
+  CK(cudaMemsetAsync(&S->mb.work->status, 0, sizeof(int), S->st));
   void* args[] = {(void*)&S->dev, (void*)&S->mb};
   void* fn = S->world > 1 ? (void*)k_mcd<D, true> : (void*)k_mcd<D, false>;
   CK(cudaLaunchCooperativeKernel(fn, dim3(S->mcd_grid), dim3(MCD_THREADS), args, MCD_SMEM, S->st));
@@ -610,7 +612,7 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
     mb.cand_r = S->alloc<double>(nreg * MCD_CAPW * D, false);
     mb.cand_cnt = S->alloc<unsigned int>(nreg);
     mb.xc = S->xc.dev;
-    mb.bar = S->alloc<GridBar>(1);
+    mb.epoch = S->alloc<unsigned int>(2 * SQC_MAXK); mb.arrive = mb.epoch + SQC_MAXK;
     mb.trace = getenv("SQC_MCD_TRACE") ? S->alloc<long long>(16 * 512) : nullptr;
     if (S->rng_mode == SQC_RNG_R_COMPAT) {
       S->mt_state = S->alloc<uint32_t>(640 * 5); S->keybuf = S->alloc<int>(2 * (size_t)S->N_total, false);

@@ -21,8 +21,13 @@
 // in rank order, so every rank walks through bit-identical cluster states.
 // A cluster walks through  KEY_HIST -> KEY_COLLECT -> [DIST_HIST -> DIST_COLLECT]* -> final
 // DIST_HIST -> DIST_COLLECT(q only) -> DONE; all clusters share every streaming round.
-// Between rounds: grid.sync, the K leader CTAs do the tiny per-cluster post-processing
-// (histogram scan / candidate sort / moments -> loc, scale, det, Cholesky, loop test :84), grid.sync.
+// Dataflow, no grid-wide barriers: CTAs 0 .. K-1 are the cluster LEADERS, the others are WORKERS.  Leader k publishes
+// the state of its cluster under an epoch number; every worker streams its static share of the cluster's chunks
+// whenever it sees a new epoch, flushes (histogram / moment partials / candidates) and arrives on a counter;
+// when all workers have arrived the leader post-processes (histogram scan / candidate ranking / moments -> loc,
+// scale, det, Cholesky, loop test :84) and publishes the next epoch.  Clusters advance independently, so one
+// cluster's post-processing overlaps the streaming of the others and a slowly converging cluster does not
+// hold grid barriers for everybody.
 #pragma once
 #include "sqc_kernels.cuh"
 #include "sqc_xchg.cuh"
@@ -79,7 +84,8 @@ struct McdBufs {
   const int* keys;                     // R-compatible key stream of this call (N_total ints), or null
   unsigned long long call_mix;         // counter-mode key mix for this call
   long long stream_base;               // call * N_total: index of this call's first draw
-  GridBar* bar;                        // grid barrier words (count must be 0 at launch)
+  unsigned int* epoch;                 // K: state version of every cluster (0 at launch; the leader publishes 1, 2, ...)
+  unsigned int* arrive;                // K: worker arrivals (0 at launch)
   long long* trace;                    // optional per-round timeline (debug): 16 words per round, word 0 of the buffer = rounds
   XchgDev xc;                          // peer windows (world <= 1: unused)
 };
@@ -98,6 +104,9 @@ __device__ __forceinline__ void grid_barrier(GridBar* bar, unsigned int nblocks,
   }
   ++gen;
   __syncthreads();
+}
+__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
@@ -233,12 +242,14 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
   __shared__ int sh_ph[SQC_MAXK];
   __shared__ long long sh_n[SQC_MAXK];
   __shared__ unsigned long long sh_u64[4];
+  __shared__ McdClu sh_clu;                    // worker: snapshot of the state of the cluster being streamed
+  __shared__ int sh_ep[SQC_MAXK], sh_eloc[SQC_MAXK], sh_done[SQC_MAXK], sh_off[SQC_MAXK];
 
   if (!s.ctl->cont) return;                    // uniform across the grid (and across ranks): nobody reaches a barrier
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, G = gridDim.x, b = blockIdx.x, K = s.K;
   const int world = (MULTI && mb.xc.world > 1) ? mb.xc.world : 1, myrank = world > 1 ? mb.xc.rank : 0;
   const int regions = G * MCD_WARPS, region = b * MCD_WARPS + wid;
-  unsigned int bar_gen = ld_acquire_u32(&mb.bar->gen);
+  const int NWK = G - K;                       // worker CTAs; CTAs 0 .. K-1 are the cluster leaders
   McdWork* W = mb.work;
 
   // ---- setup: one leader CTA per cluster ----------------------------------------------------
@@ -272,173 +283,36 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
     }
     for (int i = tid; i < MCD_NB; i += MCD_THREADS) mb.hist[k * MCD_NB + i] = 0u;
   }
-  __threadfence();
-  grid_barrier(mb.bar, (unsigned)G, bar_gen);
 
-  long long rounds = 0;
-  for (;;) {
-    // ---- active chunk map -------------------------------------------------------------------
-    if (tid < K) { sh_ph[tid] = W->clu[tid].phase; sh_n[tid] = W->clu[tid].n_loc; }   // parallel loads, then a tiny serial prefix
-    if (tid == 32) sh_flag[3] = W->status;
-    __syncthreads();
-    if (tid == 0) {
-      long long run = 0, cells = 0, bytes = 0; int any = 0;
-      const bool bad = sh_flag[3] != 0;
-      for (int k = 0; k < K; ++k) {
-        sh_cstart[k] = run;
-        const int ph = sh_ph[k];
-        if (ph != PH_DONE && !bad) {
-          const long long n = sh_n[k];
-          run += (n + CHUNK - 1) / CHUNK; any = 1; cells += n;
-          const bool keyr = (ph == PH_KEY_HIST || ph == PH_KEY_COLLECT);
-          bytes += n * ((ph == PH_KEY_HIST ? 0 : 8 * D) + ((keyr && mb.keys) ? 4 : 0));
-        }
-      }
-      sh_cstart[K] = run; sh_flag[0] = any;
-      if (b == 0) { s.ctl->mcd_cells += cells; s.ctl->mcd_bytes += bytes; }
-    }
-    __syncthreads();
-    if (!sh_flag[0]) break;
-    ++rounds;
-    const bool tr = mb.trace && b == 0 && tid == 0 && rounds < 500;
-    long long* trow = mb.trace + 16 * rounds;
-    if (tr) { trow[0] = gtimer(); int ph = 0; for (int k = 0; k < K; ++k) ph |= (sh_ph[k] & 7) << (3 * k); trow[4] = ph; trow[5] = sh_cstart[K]; for (int e = 6; e < 16; ++e) trow[e] = 0; }
-    for (int i = tid; i < K * NM; i += MCD_THREADS) mb.part[((long long)b * K) * NM + i] = 0.0;
-    if (lane < K) mb.cand_cnt[(long long)lane * regions + region] = 0u;
-    const long long total = sh_cstart[K];
-    const long long c0 = total * b / G, c1 = total * (b + 1) / G;
-
-    // ---- streaming round ----------------------------------------------------------------------
-    long long c = c0;
-    while (c < c1) {
-      int k = 0;
-      while (k + 1 < K && sh_cstart[k + 1] <= c) ++k;
-      const long long cend = (sh_cstart[k + 1] < c1) ? sh_cstart[k + 1] : c1;
-      const McdClu& cl = W->clu[k];
-      const int phase = cl.phase;
-      const bool hist_round = (phase == PH_KEY_HIST || phase == PH_DIST_HIST);
-      const bool key_round = (phase == PH_KEY_HIST || phase == PH_KEY_COLLECT);
-      const long long n = cl.n_loc;
-      const unsigned long long lo_b = hist_round ? cl.wlo : cl.blo, hi_b = hist_round ? cl.whi : cl.bhi;
-      const int shift = cl.shift;
-      double loc[D], cs[D], lt[SQC_TRI(D)];
-#pragma unroll
-      for (int d = 0; d < D; ++d) { loc[d] = cl.loc[d]; cs[d] = cl.cshift[d]; }
-#pragma unroll
-      for (int e = 0; e < SQC_TRI(D); ++e) lt[e] = cl.linv[e];
-      const bool need_mom = (phase == PH_KEY_COLLECT) || (phase == PH_DIST_COLLECT && !cl.is_final);
-      const double* rsb = s.rs + cl.off;
-      const long long kbase = cl.prefix;                            // key-stream offset of the local segment's first cell
-      if (hist_round) { for (int i = tid; i < MCD_NB; i += MCD_THREADS) sh_hist[i] = 0u; }
-      __syncthreads();
-      double acc[NM];
-#pragma unroll
-      for (int m = 0; m < NM; ++m) acc[m] = 0.0;
-      unsigned int below = 0, nnan = 0, wcount = 0;
-      const long long cbase = ((long long)k * regions + region) * MCD_CAPW;
-
-      for (long long ch = c; ch < cend; ++ch) {
-        const long long e0 = (ch - sh_cstart[k]) * CHUNK;
-        double r[CPT][D]; unsigned long long bits[CPT]; bool valid[CPT];
-        long long epos[CPT];
-#pragma unroll
-        for (int it = 0; it < CPT / 2; ++it) {
-          const long long e = e0 + (long long)it * (2 * MCD_THREADS) + 2 * tid;
-          epos[2 * it] = e; epos[2 * it + 1] = e + 1;
-          valid[2 * it] = e < n; valid[2 * it + 1] = (e + 1) < n;
-        }
-        if (!(key_round && hist_round)) {                           // KEY_HIST needs no residuals
-#pragma unroll
-          for (int it = 0; it < CPT / 2; ++it) {
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-              double2 v = make_double2(0.0, 0.0);
-              if (valid[2 * it]) v = ld_stream2(rsb + (long long)d * s.rs_stride + epos[2 * it]);
-              r[2 * it][d] = v.x; r[2 * it + 1][d] = v.y;
-            }
-          }
-        }
-        if (key_round) {
-          if (mb.keys) {
-#pragma unroll
-            for (int it = 0; it < CPT; ++it) {
-              int key = 0;
-              if (valid[it]) key = ld_stream_s32(mb.keys + kbase + epos[it]);
-              bits[it] = (unsigned long long)(unsigned int)key;
-            }
-          } else {
-#pragma unroll
-            for (int it = 0; it < CPT; ++it)
-              bits[it] = (unsigned long long)(unsigned int)counter_key(mb.call_mix, (unsigned long long)(mb.stream_base + kbase + epos[it]));
-          }
-        } else {
-#pragma unroll
-          for (int it = 0; it < CPT; ++it) {
-            double v[D];
-#pragma unroll
-            for (int d = 0; d < D; ++d) v[d] = r[it][d] - loc[d];
-            const double dd = maha_tri<D>(v, lt);
-            bits[it] = dist_bits(dd);
-            if (valid[it] && !(dd == dd)) ++nnan;
-          }
-        }
-        if (hist_round) {
-#pragma unroll
-          for (int it = 0; it < CPT; ++it) {
-            if (valid[it]) {
-              if (bits[it] < lo_b) ++below;
-              else if (bits[it] < hi_b) atomicAdd(&sh_hist[(unsigned int)((bits[it] - lo_b) >> shift)], 1u);
-            }
-          }
-        } else {
-#pragma unroll
-          for (int it = 0; it < CPT; ++it) {
-            const bool in = valid[it] && bits[it] < lo_b;
-            const bool cand = valid[it] && bits[it] >= lo_b && bits[it] < hi_b;
-            if (need_mom) Mom<D>::add(acc, r[it], cs, in);
-            const unsigned m = __ballot_sync(0xffffffffu, cand);
-            if (m) {                                                // per-warp region, warp-deterministic order, no atomics
-              const unsigned slot = wcount + __popc(m & ((1u << lane) - 1u));
-              if (cand && slot < (unsigned)MCD_CAPW) {
-                mb.cand_bits[cbase + slot] = bits[it];
-                mb.cand_pos[cbase + slot] = (unsigned int)epos[it];
-#pragma unroll
-                for (int d = 0; d < D; ++d) mb.cand_r[(cbase + slot) * D + d] = r[it][d];
-              }
-              wcount += __popc(m);
-            }
-          }
-        }
-      }
-      // ---- flush this CTA's share of cluster k ------------------------------------------------
-      if (hist_round) {
-        __syncthreads();
-        for (int i = tid; i < MCD_NB; i += MCD_THREADS) { const unsigned v = sh_hist[i]; if (v) atomicAdd(&mb.hist[k * MCD_NB + i], v); }
-        unsigned long long bl = (unsigned long long)warp_sum_i((int)below);
-        if (lane == 0 && bl) atomicAdd(&W->cnt_below[k], bl);
-        __syncthreads();
-      } else {
-        if (lane == 0) mb.cand_cnt[(long long)k * regions + region] = wcount;
-        if (need_mom) {
-          block_reduce_vec<NM>(acc, sh_red, sh_out);
-          if (tid < NM) mb.part[((long long)b * K + k) * NM + tid] = sh_out[tid];
-          __syncthreads();
-        }
-      }
-      const int nn = warp_sum_i((int)nnan);
-      if (lane == 0 && nn) atomicAdd(&W->cnt_nan[k], (unsigned long long)nn);
-      c = cend;
-    }
-    if (tr) trow[1] = gtimer();
+  if (b < K) {
+    // =========================== leader of cluster k: waits for the workers, post-processes, publishes ===========================
+    const int k = b;
     __threadfence();
-    grid_barrier(mb.bar, (unsigned)G, bar_gen);
-    if (tr) trow[2] = gtimer();
-
-    // ---- leaders: per-cluster post-processing -------------------------------------------------
-    if (tid == 0) sh_flag[2] = (b < K && W->clu[b].phase != PH_DONE && W->status == 0) ? 1 : 0;
     __syncthreads();
-    if (sh_flag[2]) {
-      const int k = b;
+    int ep = 1;
+    if (tid == 0) st_release_u32(&mb.epoch[k], 1u);
+    long long my_epochs = 0, my_cells = 0, my_bytes = 0;
+    for (;;) {
+      if (tid == 0) sh_flag[2] = (W->clu[k].phase != PH_DONE) ? 1 : 0;
+      __syncthreads();
+      if (!sh_flag[2]) break;
+      ++my_epochs;
+      const bool tr = mb.trace && b == 0 && tid == 0 && my_epochs < 500;
+      long long* trow = mb.trace + 16 * my_epochs;
+      if (tr) { trow[0] = gtimer(); trow[4] = W->clu[k].phase; trow[5] = 0; for (int e = 6; e < 16; ++e) trow[e] = 0; }
+      if (tid == 0) {
+        const int ph = W->clu[k].phase; const long long n = W->clu[k].n_loc;
+        const bool keyr = (ph == PH_KEY_HIST || ph == PH_KEY_COLLECT);
+        my_cells += n; my_bytes += n * ((ph == PH_KEY_HIST ? 0 : 8 * D) + ((keyr && mb.keys) ? 4 : 0));
+        // every worker arrives once per epoch, whether or not it holds cells of this cluster
+        const unsigned int want_arrivals = (unsigned)NWK * (unsigned)ep;
+        unsigned long long spins = 0;
+        while (ld_acquire_u32(&mb.arrive[k]) < want_arrivals) { if (++spins > (1ull << 24)) { atomicCAS(&W->status, 0, SQC_D_SELECT); break; } }   // watchdog (seconds)
+        __threadfence();
+      }
+      __syncthreads();
+      if (tr) { trow[1] = gtimer(); trow[2] = trow[1]; }
+      {
       McdClu& cl = W->clu[k];
       const int phase = cl.phase;
       const bool key_phase = (phase == PH_KEY_HIST || phase == PH_KEY_COLLECT);
@@ -709,14 +583,176 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
           }
         }
       }
+      }
+      if (tr) { trow[3] = gtimer(); mb.trace[0] = my_epochs; }
+      __threadfence();
+      __syncthreads();
+      ++ep;
+      if (tid == 0) st_release_u32(&mb.epoch[k], (unsigned)ep);
     }
-    if (tr) { trow[3] = gtimer(); mb.trace[0] = rounds; }
-    __threadfence();
-    grid_barrier(mb.bar, (unsigned)G, bar_gen);
-  }
-  if (b == 0 && tid == 0) {
-    s.ctl->mcd_passes += rounds; s.ctl->mcd_call += 1;
-    if (W->status) { atomicCAS(&s.ctl->status, 0, W->status); W->status = 0; }
+    if (tid == 0) {
+      atomicAdd((unsigned long long*)&s.ctl->mcd_passes, (unsigned long long)my_epochs);
+      atomicAdd((unsigned long long*)&s.ctl->mcd_cells, (unsigned long long)my_cells);
+      atomicAdd((unsigned long long*)&s.ctl->mcd_bytes, (unsigned long long)my_bytes);
+      if (k == 0) s.ctl->mcd_call += 1;
+      if (W->status) atomicCAS(&s.ctl->status, 0, W->status);
+    }
+  } else {
+    // =========================== worker: streams its share of every cluster whenever that cluster's state is renewed ===========================
+    const int w = b - K;
+    if (tid < K) { sh_eloc[tid] = 0; sh_done[tid] = 0; }
+    if (tid == 0) {                                               // static chunk assignment: round robin over the concatenated chunk lists
+      long long run = 0;
+      for (int k = 0; k < K; ++k) { sh_off[k] = (int)(run % NWK); run += (s.clu_n[k] + CHUNK - 1) / CHUNK; }
+    }
+    __syncthreads();
+    unsigned long long idle = 0;
+    for (;;) {
+      if (tid < K) sh_ep[tid] = (int)ld_acquire_u32(&mb.epoch[tid]);
+      __syncthreads();
+      int n_done = 0; bool any_new = false;
+      for (int k = 0; k < K; ++k) {
+        if (sh_done[k]) { ++n_done; continue; }
+        const int ep = sh_ep[k];
+        if (ep == sh_eloc[k]) continue;
+        any_new = true;
+        // snapshot of the cluster state (L2 loads: another SM wrote it)
+        {
+          const unsigned long long* src = (const unsigned long long*)&W->clu[k];
+          unsigned long long* dst = (unsigned long long*)&sh_clu;
+          for (int i = tid; i < (int)(sizeof(McdClu) / 8); i += MCD_THREADS) dst[i] = __ldcg(src + i);
+        }
+        __syncthreads();
+        if (sh_clu.phase == PH_DONE) {
+          __syncthreads();
+          if (tid == 0) { sh_done[k] = 1; sh_eloc[k] = ep; }
+          __syncthreads();
+          ++n_done;
+          continue;
+        }
+        const long long nch = (sh_clu.n_loc + CHUNK - 1) / CHUNK;
+        const long long c_first = ((long long)w - sh_off[k] + NWK) % NWK;
+      const McdClu& cl = sh_clu;
+      const int phase = cl.phase;
+      const bool hist_round = (phase == PH_KEY_HIST || phase == PH_DIST_HIST);
+      const bool key_round = (phase == PH_KEY_HIST || phase == PH_KEY_COLLECT);
+      const long long n = cl.n_loc;
+      const unsigned long long lo_b = hist_round ? cl.wlo : cl.blo, hi_b = hist_round ? cl.whi : cl.bhi;
+      const int shift = cl.shift;
+      double loc[D], cs[D], lt[SQC_TRI(D)];
+#pragma unroll
+      for (int d = 0; d < D; ++d) { loc[d] = cl.loc[d]; cs[d] = cl.cshift[d]; }
+#pragma unroll
+      for (int e = 0; e < SQC_TRI(D); ++e) lt[e] = cl.linv[e];
+      const bool need_mom = (phase == PH_KEY_COLLECT) || (phase == PH_DIST_COLLECT && !cl.is_final);
+      const double* rsb = s.rs + cl.off;
+      const long long kbase = cl.prefix;                            // key-stream offset of the local segment's first cell
+      if (hist_round) { for (int i = tid; i < MCD_NB; i += MCD_THREADS) sh_hist[i] = 0u; }
+      __syncthreads();
+      double acc[NM];
+#pragma unroll
+      for (int m = 0; m < NM; ++m) acc[m] = 0.0;
+      unsigned int below = 0, nnan = 0, wcount = 0;
+      const long long cbase = ((long long)k * regions + region) * MCD_CAPW;
+
+      for (long long ch = c_first; ch < nch; ch += NWK) {
+        const long long e0 = ch * CHUNK;
+        double r[CPT][D]; unsigned long long bits[CPT]; bool valid[CPT];
+        long long epos[CPT];
+#pragma unroll
+        for (int it = 0; it < CPT / 2; ++it) {
+          const long long e = e0 + (long long)it * (2 * MCD_THREADS) + 2 * tid;
+          epos[2 * it] = e; epos[2 * it + 1] = e + 1;
+          valid[2 * it] = e < n; valid[2 * it + 1] = (e + 1) < n;
+        }
+        if (!(key_round && hist_round)) {                           // KEY_HIST needs no residuals
+#pragma unroll
+          for (int it = 0; it < CPT / 2; ++it) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+              double2 v = make_double2(0.0, 0.0);
+              if (valid[2 * it]) v = ld_stream2(rsb + (long long)d * s.rs_stride + epos[2 * it]);
+              r[2 * it][d] = v.x; r[2 * it + 1][d] = v.y;
+            }
+          }
+        }
+        if (key_round) {
+          if (mb.keys) {
+#pragma unroll
+            for (int it = 0; it < CPT; ++it) {
+              int key = 0;
+              if (valid[it]) key = ld_stream_s32(mb.keys + kbase + epos[it]);
+              bits[it] = (unsigned long long)(unsigned int)key;
+            }
+          } else {
+#pragma unroll
+            for (int it = 0; it < CPT; ++it)
+              bits[it] = (unsigned long long)(unsigned int)counter_key(mb.call_mix, (unsigned long long)(mb.stream_base + kbase + epos[it]));
+          }
+        } else {
+#pragma unroll
+          for (int it = 0; it < CPT; ++it) {
+            double v[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) v[d] = r[it][d] - loc[d];
+            const double dd = maha_tri<D>(v, lt);
+            bits[it] = dist_bits(dd);
+            if (valid[it] && !(dd == dd)) ++nnan;
+          }
+        }
+        if (hist_round) {
+#pragma unroll
+          for (int it = 0; it < CPT; ++it) {
+            if (valid[it]) {
+              if (bits[it] < lo_b) ++below;
+              else if (bits[it] < hi_b) atomicAdd(&sh_hist[(unsigned int)((bits[it] - lo_b) >> shift)], 1u);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int it = 0; it < CPT; ++it) {
+            const bool in = valid[it] && bits[it] < lo_b;
+            const bool cand = valid[it] && bits[it] >= lo_b && bits[it] < hi_b;
+            if (need_mom) Mom<D>::add(acc, r[it], cs, in);
+            const unsigned m = __ballot_sync(0xffffffffu, cand);
+            if (m) {                                                // per-warp region, warp-deterministic order, no atomics
+              const unsigned slot = wcount + __popc(m & ((1u << lane) - 1u));
+              if (cand && slot < (unsigned)MCD_CAPW) {
+                mb.cand_bits[cbase + slot] = bits[it];
+                mb.cand_pos[cbase + slot] = (unsigned int)epos[it];
+#pragma unroll
+                for (int d = 0; d < D; ++d) mb.cand_r[(cbase + slot) * D + d] = r[it][d];
+              }
+              wcount += __popc(m);
+            }
+          }
+        }
+      }
+      // ---- flush this CTA's share of cluster k ------------------------------------------------
+      if (hist_round) {
+        __syncthreads();
+        for (int i = tid; i < MCD_NB; i += MCD_THREADS) { const unsigned v = sh_hist[i]; if (v) atomicAdd(&mb.hist[k * MCD_NB + i], v); }
+        unsigned long long bl = (unsigned long long)warp_sum_i((int)below);
+        if (lane == 0 && bl) atomicAdd(&W->cnt_below[k], bl);
+        __syncthreads();
+      } else {
+        if (lane == 0) mb.cand_cnt[(long long)k * regions + region] = wcount;
+        if (need_mom) {
+          block_reduce_vec<NM>(acc, sh_red, sh_out);
+          if (tid < NM) mb.part[((long long)b * K + k) * NM + tid] = sh_out[tid];
+          __syncthreads();
+        }
+      }
+      const int nn = warp_sum_i((int)nnan);
+      if (lane == 0 && nn) atomicAdd(&W->cnt_nan[k], (unsigned long long)nn);
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) { atomicAdd(&mb.arrive[k], 1u); sh_eloc[k] = ep; }
+        __syncthreads();
+      }
+      if (n_done == K) break;
+      if (!any_new && ++idle > (1ull << 23)) break;               // watchdog (seconds): a leader died
+    }
   }
 }
 
