@@ -53,29 +53,50 @@ __device__ __forceinline__ int ld_stream_s32(const int* p) {
   return v;
 }
 
-// exp(x) for x <= 0 (the density exponents -q/2): n = rint(x / ln 2) by the 1.5 * 2^52 trick, two-step Cody-Waite
-// reduction, degree-13 Taylor polynomial in Horner form with the coefficients in the constant bank, scaling by
-// exponent arithmetic.  <= 2 ulp from the correctly rounded value over the whole range including the gradual
-// underflow below -708 (handled by a two-step scaling); about half the instructions of the library exp().
-__constant__ double c_exp_coef[12] = {
-  1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0,
-  1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5};
+// exp(x) for x <= 0 (the density exponents -q/2):  x = (32 n + j) ln2/32 + r,  exp(x) = 2^n * 2^(j/32) * exp(r).
+// k = 32 n + j by the 1.5 * 2^52 rounding trick, two-step Cody-Waite reduction (|r| <= ln2/64), degree-6 Taylor
+// polynomial, one table look-up (32 doubles, L1-resident), scaling by exponent arithmetic.  <= 2 ulp from the
+// correctly rounded value, including the gradual underflow below -708 (two-step scaling); 11 fp64 instructions.
+__device__ const double c_exp_tab[32] = {
+  1, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237,
+  1.0905077326652577, 1.1143867425958924, 1.1387886347566916, 1.1637248587775775,
+  1.189207115002721, 1.215247359980469, 1.241857812073484, 1.2690509571917332,
+  1.2968395546510096, 1.3252366431597413, 1.3542555469368927, 1.383909881963832,
+  1.4142135623730951, 1.4451808069770467, 1.4768261459394993, 1.5091644275934228,
+  1.5422108254079407, 1.5759808451078865, 1.6104903319492543, 1.6457554781539649,
+  1.681792830507429, 1.7186192981224779, 1.7562521603732995, 1.7947090750031072,
+  1.8340080864093424, 1.8741676341103, 1.9152065613971474, 1.9571441241754002};
 __device__ __forceinline__ double exp_neg(double x) {
   const double magic = 6755399441055744.0;
-  const double t = fma(x, 1.4426950408889634074, magic);
-  const int n = __double2loint(t);
-  const double nf = t - magic;
-  double r = fma(nf, -6.93147180369123816490e-01, x);
-  r = fma(nf, -1.90821492927058770002e-10, r);
-  double p = c_exp_coef[0];
-#pragma unroll
-  for (int i = 1; i < 12; ++i) p = fma(p, r, c_exp_coef[i]);
+  const double t = fma(x, 46.166241308446828384, magic);              // 32 / ln 2
+  const int k = __double2loint(t);
+  const double kf = t - magic;
+  double r = fma(kf, -2.16608493865351192653e-02, x);                 // ln2/32, high part (32 significant bits)
+  r = fma(kf, -5.96317165397058656257e-12, r);                        // ln2/32, low part
+  double p = fma(r, 1.0 / 720.0, 1.0 / 120.0);
+  p = fma(p, r, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
+  p *= __ldg(&c_exp_tab[k & 31]);
+  const int n = k >> 5;
   if (!(x >= -746.0)) return (x != x) ? x : 0.0;                      // underflow to zero (also -inf); NaN stays NaN
   if (n >= -1020) return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p));
   const double s1 = __hiloint2double((n + 1000 + 1023) << 20, 0);     // 2^(n + 1000), normal
   return (p * s1) * 9.33263618503218878990e-302;                      // * 2^-1000: the hardware rounds the subnormal
+}
+// sum of log(v[c]) over the valid cells of a thread: one log of the product when that cannot over- / underflow
+template <int CPT>
+__device__ __forceinline__ double sum_log(const double (&v)[CPT], const bool (&valid)[CPT]) {
+  double prod = 1.0; bool safe = true;
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) { const double u = valid[c] ? v[c] : 1.0; prod *= u; safe = safe && (u > 1e-70) && (u < 1e70); }
+  if (safe) return log(prod);
+  double a = 0.0;
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) if (valid[c]) a += log(v[c]);
+  return a;
 }
 
 // sum over the warp of NV doubles per lane with recursive halving: every step halves the number of values a lane

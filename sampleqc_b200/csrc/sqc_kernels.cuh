@@ -191,9 +191,9 @@ __global__ void __launch_bounds__(EST_THREADS, SQC_EST_MINB) k_estep(Dev s) {
         like[c] += p * (P * exp_neg(-0.5 * q));              // p_jk * dmvnorm(log=FALSE), :424
       }
     }
+    ll = sum_log<CPT>(like, valid);                          // :428
 #pragma unroll
     for (int c = 0; c < CPT; ++c) if (valid[c]) {
-      ll += log(like[c]);                                    // :428
       delta += (zn[c] != zo[c]);
       s.z[(long long)start + c * EST_THREADS + tid] = (uint8_t)zn[c];
     }
@@ -312,9 +312,7 @@ __global__ void __launch_bounds__(EST_THREADS, SQC_PART_MINB) k_partition(Dev s)
         like[c] += p * (P * exp_neg(-0.5 * maha_tri<D>(v, lt)));
       }
     }
-    double ll = 0.0;
-#pragma unroll
-    for (int c = 0; c < CPT; ++c) if (valid[c]) ll += log(like[c]);
+    double ll = sum_log<CPT>(like, valid);
     ll = warp_sum(ll);
     if (lane == 0) sh_w[w] = ll;
     __syncthreads();

