@@ -28,7 +28,10 @@ namespace sqc {
 #endif
 constexpr int EST_THREADS = 256;     // E-step / partition CTAs: one sample-aligned tile each
 // cells per thread of a tile, by dimension (register budget)
-template <int D> struct TileCfg { static constexpr int CPT = (D <= 4) ? 4 : 2; static constexpr int TILE = EST_THREADS * CPT; };
+#ifndef SQC_EST_CPT
+#define SQC_EST_CPT 4
+#endif
+template <int D> struct TileCfg { static constexpr int CPT = (D <= 4) ? SQC_EST_CPT : 2; static constexpr int TILE = EST_THREADS * CPT; };
 
 struct Control {
   int iter;          // EM iterations completed
@@ -57,7 +60,7 @@ struct Dev {
   double* mu0; double* alpha; double* beta; double* sigma; double* linv; double* ainv; double* logP; double* Pk;
   double* p_jk; double* logp_jk;
   // tile partials / reduced statistics
-  double* t_ll1; double* t_ll2; int* t_nk; double* t_sk; int* s_base; int* t_rel; unsigned int* done_ctr; double* t_col;
+  double* t_ll1; double* t_ll2; int* t_nk; double* t_sk; int* s_base; int* t_rel; unsigned int* done_ctr; unsigned int* mcd_sync; double* t_col;
   int* n_jk; double* s_jk;
   long long* clu_n; long long* clu_off;        // local cells per cluster, segment offsets in rs
   long long* clu_n_glob; long long* clu_prefix; // cells per cluster over all shards; key-stream offset of the local segment
@@ -254,6 +257,7 @@ __global__ void __launch_bounds__(EST_THREADS, SQC_PART_MINB) k_partition(Dev s)
   __shared__ double sh_w[NW];
   if (!s.ctl->cont) return;
   const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (t == 0 && tid < 2 * SQC_MAXK + 1) s.mcd_sync[tid] = 0u;      // epochs, arrivals and status word of the k_mcd launch that follows
   const int j = s.tile_sample[t], start = s.tile_start[t], len = s.tile_len[t];
   if (LIKE) stage_params<D>(s, j, sh_par);
   double xv[CPT][D]; int zo[CPT]; bool valid[CPT];
@@ -403,7 +407,8 @@ __global__ void k_init_alpha(Dev s) {
 //   position of a sample's first cell of component k inside the cluster-sorted segment), cluster sizes and
 //   segment offsets.  k_partition adds the counts of the earlier tiles of its own sample.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_post_stats(Dev s, int n_sample_blocks) {
+__device__ __forceinline__ void em_control_block(Dev& s);
+__global__ void __launch_bounds__(1024) k_post_stats(Dev s, int n_sample_blocks, int fuse_ctl) {
   __shared__ long long sh_scan[33];
   __shared__ int sh_last;
   if (!s.ctl->cont) return;
@@ -447,6 +452,9 @@ __global__ void __launch_bounds__(1024) k_post_stats(Dev s, int n_sample_blocks)
     for (int k = 0; k < K; ++k) { s.clu_n_glob[k] = s.clu_n[k]; s.clu_prefix[k] = run; run += s.clu_n[k]; }
     *s.done_ctr = 0u;
   }
+  // single GPU: the end-of-iteration bookkeeping rides along (one launch less); every other block of this launch
+  // has passed its loop-flag test by now
+  if (fuse_ctl) { __syncthreads(); em_control_block(s); }
 }
 
 // alpha_j from the (j,k) statistics: update_alpha_j :116-157 with the per-cell sums factored out
@@ -541,10 +549,9 @@ __global__ void k_update_p(Dev s) {
 
 // end-of-iteration bookkeeping (:499,:506,:511-521): deterministic sums of the tile log-likelihoods,
 // loop condition, optional tracking.  single block.
-__global__ void __launch_bounds__(1024) k_em_control(Dev s) {
+__device__ __forceinline__ void em_control_block(Dev& s) {       // one block of 1024 threads
   __shared__ double sh[32];
   Control* c = s.ctl;
-  if (!c->cont) return;
   const int it = c->iter;
   double a1 = 0.0, a2 = 0.0;
   for (int t = threadIdx.x; t < s.T; t += 1024) { a1 += s.t_ll1[t]; a2 += s.t_ll2[t]; }
@@ -557,13 +564,17 @@ __global__ void __launch_bounds__(1024) k_em_control(Dev s) {
     for (int e = threadIdx.x; e < s.J * s.K; e += 1024) { int j = e / s.K, k = e % s.K; s.track_p[(long long)it * s.J * s.K + j + s.J * k] = s.p_jk[e]; }
   }
   if (threadIdx.x == 0) {
-    // multi-GPU: like sums and z_delta are made global by the host-side exchange before this kernel
+    // multi-GPU: like sums and z_delta are made global by the host-side exchange before this point
     s.like1[it] = r1; s.like2[it] = r2;
     c->iter = it + 1;
     __threadfence();
     c->cont = (c->z_delta > 0) && (it + 1 < s.em_iters) && (c->status == 0);    // :490
     c->z_delta = 0;
   }
+}
+__global__ void __launch_bounds__(1024) k_em_control(Dev s) {
+  if (!s.ctl->cont) return;
+  em_control_block(s);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -326,8 +326,6 @@ template <int D> void launch_partition(sqc_session* S, int like) {
 }
 template <int D> void launch_mcd(sqc_session* S) {
   Launch L(S, SQC_KF_MCD);
-  CK(cudaMemsetAsync(S->mb.epoch, 0, 2 * SQC_MAXK * sizeof(unsigned int), S->st));     // cluster epochs / worker arrivals
-  CK(cudaMemsetAsync(&S->mb.work->status, 0, sizeof(int), S->st));
   void* args[] = {(void*)&S->dev, (void*)&S->mb};
   void* fn = S->world > 1 ? (void*)k_mcd<D, true> : (void*)k_mcd<D, false>;
   CK(cudaLaunchCooperativeKernel(fn, dim3(S->mcd_grid), dim3(MCD_THREADS), args, MCD_SMEM, S->st));
@@ -612,7 +610,8 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
     mb.cand_r = S->alloc<double>(nreg * MCD_CAPW * D, false);
     mb.cand_cnt = S->alloc<unsigned int>(nreg);
     mb.xc = S->xc.dev;
-    mb.epoch = S->alloc<unsigned int>(2 * SQC_MAXK); mb.arrive = mb.epoch + SQC_MAXK;
+    mb.epoch = S->alloc<unsigned int>(2 * SQC_MAXK + 4); mb.arrive = mb.epoch + SQC_MAXK; mb.status = (int*)(mb.epoch + 2 * SQC_MAXK);
+    s.mcd_sync = mb.epoch;
     mb.trace = getenv("SQC_MCD_TRACE") ? S->alloc<long long>(16 * 512) : nullptr;
     if (S->rng_mode == SQC_RNG_R_COMPAT) {
       S->mt_state = S->alloc<uint32_t>(640 * 5); S->keybuf = S->alloc<int>(2 * (size_t)S->N_total, false);
@@ -715,8 +714,8 @@ void run_robust(sqc_session* S) {
     if (S->em_iters >= 1) enqueue_keys(S, 1);
   }
   const int nsb = (J + 31) / 32;
-  auto post_stats = [&]() {
-    Launch L(S, SQC_KF_UPDATE); k_post_stats<<<nsb, 1024, 0, S->st>>>(s, nsb); L.done();
+  auto post_stats = [&](int fuse_ctl) {
+    Launch L(S, SQC_KF_UPDATE); k_post_stats<<<nsb, 1024, 0, S->st>>>(s, nsb, fuse_ctl); L.done();
     if (S->world > 1) xchg_cluster_layout(S, s);
   };
   auto m_step = [&](int call, int like) {
@@ -728,7 +727,7 @@ void run_robust(sqc_session* S) {
   };
   // initial labelling: p_jk (:481), alpha_j (:482), beta_k / Sigma_k (:483)
   do_estep(S, 1);
-  post_stats();
+  post_stats(0);
   { Launch L(S, SQC_KF_UPDATE); k_update_p<<<(J + 127) / 128, 128, 0, S->st>>>(s); L.done(); }
   m_step(0, 0);
   { Launch L(S, SQC_KF_UPDATE); k_ctl_start_loop<<<1, 32, 0, S->st>>>(s); L.done(); }
@@ -737,9 +736,11 @@ void run_robust(sqc_session* S) {
     do_update_alpha(S);                                                                 // :496
     m_step(it + 1, 1);                                                                  // like_1 :499, M-step :502, p_jk :504
     do_estep(S, 0);                                                                     // :506, :509, :519
-    post_stats();
-    if (S->world > 1) xchg_allreduce_like(S, s);
-    { Launch L(S, SQC_KF_UPDATE); k_em_control<<<1, 1024, 0, S->st>>>(s); L.done(); }
+    post_stats(S->world > 1 ? 0 : 1);                                                  // single GPU: :511-521 fused in
+    if (S->world > 1) {
+      xchg_allreduce_like(S, s);
+      { Launch L(S, SQC_KF_UPDATE); k_em_control<<<1, 1024, 0, S->st>>>(s); L.done(); }
+    }
   }
   CK(cudaEventRecord(S->ev_loop, S->st));
 }

@@ -68,7 +68,6 @@ struct McdWork {
   McdClu clu[SQC_MAXK];
   unsigned long long cnt_below[SQC_MAXK];   // HIST: local cells under the window
   unsigned long long cnt_nan[SQC_MAXK];
-  int status;                               // in-kernel error (identical on every rank: derived from exchanged data only)
 };
 
 struct GridBar { unsigned int count; unsigned int gen; };
@@ -86,6 +85,7 @@ struct McdBufs {
   long long stream_base;               // call * N_total: index of this call's first draw
   unsigned int* epoch;                 // K: state version of every cluster (0 at launch; the leader publishes 1, 2, ...)
   unsigned int* arrive;                // K: worker arrivals (0 at launch)
+  int* status;                         // in-kernel error word (0 at launch): identical on every rank, derived from exchanged data only
   long long* trace;                    // optional per-round timeline (debug): 16 words per round, word 0 of the buffer = rounds
   XchgDev xc;                          // peer windows (world <= 1: unused)
 };
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
       int err = 0;
       if (n <= 0) err = SQC_D_EMPTY_CLUSTER;                       // x_k.rows(0, -1), :307
       else if (c.h > n || c.h < 1) err = SQC_D_SUBSET_SIZE;        // randperm(N, h) with h > N, :72
-      if (err) { atomicCAS(&W->status, 0, err); c.phase = PH_DONE; }
+      if (err) { atomicCAS(&(*mb.status), 0, err); c.phase = PH_DONE; }
       else {
         c.q_chisq = dev_qchisq((double)c.h / (double)n, D);        // :101-102
         for (int d = 0; d < D; ++d) c.cshift[d] = s.beta[k * D + d];   // previous beta_k (zeros before the first call)
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         // every worker arrives once per epoch, whether or not it holds cells of this cluster
         const unsigned int want_arrivals = (unsigned)NWK * (unsigned)ep;
         unsigned long long spins = 0;
-        while (ld_acquire_u32(&mb.arrive[k]) < want_arrivals) { if (++spins > (1ull << 24)) { atomicCAS(&W->status, 0, SQC_D_SELECT); break; } }   // watchdog (seconds)
+        while (ld_acquire_u32(&mb.arrive[k]) < want_arrivals) { if (++spins > (1ull << 24)) { atomicCAS(&(*mb.status), 0, SQC_D_SELECT); break; } }   // watchdog (seconds)
         __threadfence();
       }
       __syncthreads();
@@ -348,13 +348,13 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         if (tid == 0) {
           cl.n_hist_rounds++;
           const int bin = sh_flag[1];
-          if (has_nan) { atomicCAS(&W->status, 0, SQC_D_NAN); cl.phase = PH_DONE; }          // sort_index(): detected NaN, :50
+          if (has_nan) { atomicCAS(&(*mb.status), 0, SQC_D_NAN); cl.phase = PH_DONE; }          // sort_index(): detected NaN, :50
           else if (bin < 0) {
             // the order statistic lies outside the window: widen to the whole side it is on
             const unsigned long long top = key_phase ? (1ull << 31) : 0x7ff0000000000001ull;
             if (want < 1) { cl.whi = cl.wlo; cl.wlo = 0ull; } else { cl.wlo = cl.whi; cl.whi = top; }
             cl.shift = window_shift(cl.wlo, cl.whi);
-            if (cl.whi <= cl.wlo || cl.n_hist_rounds > 40) { atomicCAS(&W->status, 0, SQC_D_SELECT); cl.phase = PH_DONE; }
+            if (cl.whi <= cl.wlo || cl.n_hist_rounds > 40) { atomicCAS(&(*mb.status), 0, SQC_D_SELECT); cl.phase = PH_DONE; }
           } else {
             const unsigned long long blo = cl.wlo + ((unsigned long long)bin << cl.shift);
             unsigned long long bhi = blo + (1ull << cl.shift);
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
             if (sh_u64[1] > (unsigned long long)MCD_CAND_CAP && cl.shift > 0 && cl.n_hist_rounds <= 40) {
               cl.wlo = blo; cl.whi = bhi; cl.shift = window_shift(blo, bhi);                 // refine inside the bin
             } else if (sh_u64[1] > (unsigned long long)MCD_CAND_CAP) {
-              atomicCAS(&W->status, 0, SQC_D_SELECT); cl.phase = PH_DONE;
+              atomicCAS(&(*mb.status), 0, SQC_D_SELECT); cl.phase = PH_DONE;
             } else {
               cl.blo = blo; cl.bhi = bhi; cl.below = below + (long long)sh_u64[0];
               cl.phase = key_phase ? PH_KEY_COLLECT : PH_DIST_COLLECT;
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
             if (fbin >= 0 && cl.shift > 0 && cl.n_hist_rounds <= 40) {
               cl.wlo = cl.blo; cl.whi = cl.bhi; cl.shift = window_shift(cl.wlo, cl.whi);
               cl.phase = key_phase ? PH_KEY_HIST : PH_DIST_HIST;
-            } else { atomicCAS(&W->status, 0, SQC_D_SELECT); cl.phase = PH_DONE; }
+            } else { atomicCAS(&(*mb.status), 0, SQC_D_SELECT); cl.phase = PH_DONE; }
           } else {
             const double h = (double)cl.h;
             bool go_final = false, done = false;
@@ -561,13 +561,13 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
               done = true;
             }
             if (!done) {
-              if (sh_out[0] != h) { atomicCAS(&W->status, 0, SQC_D_SELECT); done = true; }
+              if (sh_out[0] != h) { atomicCAS(&(*mb.status), 0, SQC_D_SELECT); done = true; }
               const bool cont = ((cl.det_old - cl.det_new) > 1e-10) & (cl.det_new > 0) & (cl.iters < s.mcd_iters);   // :84
               go_final = !cont;
               if (go_final && cl.iters == s.mcd_iters) atomicAdd(&s.ctl->mcd_hit, 1);   // :94-95
             }
             if (done) cl.phase = PH_DONE;
-            else if (!prepare_dist<D>(cl)) { atomicCAS(&W->status, 0, SQC_D_NOT_SPD); cl.phase = PH_DONE; }   // chol(), :19
+            else if (!prepare_dist<D>(cl)) { atomicCAS(&(*mb.status), 0, SQC_D_NOT_SPD); cl.phase = PH_DONE; }   // chol(), :19
             else {
               cl.is_final = go_final ? 1 : 0;
               cl.phase = PH_DIST_HIST; cl.n_hist_rounds = 0;
@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
       atomicAdd((unsigned long long*)&s.ctl->mcd_cells, (unsigned long long)my_cells);
       atomicAdd((unsigned long long*)&s.ctl->mcd_bytes, (unsigned long long)my_bytes);
       if (k == 0) s.ctl->mcd_call += 1;
-      if (W->status) atomicCAS(&s.ctl->status, 0, W->status);
+      if ((*mb.status)) atomicCAS(&s.ctl->status, 0, (*mb.status));
     }
   } else {
     // =========================== worker: streams its share of every cluster whenever that cluster's state is renewed ===========================
