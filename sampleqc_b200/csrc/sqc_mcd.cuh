@@ -267,7 +267,6 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
       else if (c.h > n || c.h < 1) err = SQC_D_SUBSET_SIZE;        // randperm(N, h) with h > N, :72
       if (err) { atomicCAS(&(*mb.status), 0, err); c.phase = PH_DONE; }
       else {
-        c.q_chisq = dev_qchisq((double)c.h / (double)n, D);        // :101-102
         for (int d = 0; d < D; ++d) c.cshift[d] = s.beta[k * D + d];   // previous beta_k (zeros before the first call)
         // key window: the h-th smallest of n uniform keys sits at (h/n) 2^31 +- a few sigma
         const double p = (double)c.h / (double)n, two31 = 2147483648.0;
@@ -290,7 +289,13 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
     __threadfence();
     __syncthreads();
     int ep = 1;
-    if (tid == 0) st_release_u32(&mb.epoch[k], 1u);
+    if (tid == 0) {
+      st_release_u32(&mb.epoch[k], 1u);
+      // qchisq(h / n, D) of the consistency factor (:101-102) is first needed after the start rounds: evaluate it
+      // while the workers stream the first one
+      McdClu& c = W->clu[k];
+      if (c.phase != PH_DONE) c.q_chisq = dev_qchisq((double)c.h / (double)c.n, D);
+    }
     long long my_epochs = 0, my_cells = 0, my_bytes = 0;
     for (;;) {
       if (tid == 0) sh_flag[2] = (W->clu[k].phase != PH_DONE) ? 1 : 0;
@@ -610,11 +615,20 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
     for (;;) {
       if (tid < K) sh_ep[tid] = (int)ld_acquire_u32(&mb.epoch[tid]);
       __syncthreads();
-      int n_done = 0; bool any_new = false;
-      for (int k = 0; k < K; ++k) {
-        if (sh_done[k]) { ++n_done; continue; }
+      // serve ONE renewed cluster per poll, the smallest first: a small cluster that needs many C-steps then cycles at
+      // its own (short) period instead of waiting for a sweep over the big ones
+      if (tid == 0) {
+        int sel = -1, nd = 0;
+        for (int k = 0; k < K; ++k) {
+          if (sh_done[k]) { ++nd; continue; }
+          if (sh_ep[k] != sh_eloc[k] && (sel < 0 || s.clu_n[k] < s.clu_n[sel])) sel = k;
+        }
+        sh_flag[0] = sel; sh_flag[1] = nd;
+      }
+      __syncthreads();
+      int n_done = sh_flag[1]; bool any_new = false;
+      for (int k = sh_flag[0]; k >= 0 && k == sh_flag[0]; k = -1) {
         const int ep = sh_ep[k];
-        if (ep == sh_eloc[k]) continue;
         any_new = true;
         // snapshot of the cluster state (L2 loads: another SM wrote it)
         {

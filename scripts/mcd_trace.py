@@ -20,11 +20,9 @@ L = lib(); L.sqc_session_mcd_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
 L.sqc_session_mcd_trace(s._h, buf.ctypes.data_as(C.c_void_p), buf.size)
 R = int(buf[0]); t = buf.reshape(-1, 16)
 names = "KH KC DH DC DONE".split()
-print("round stream sync1  post  sync2 | finehist scan pass2 tie partials reduce+linalg | chunks ncand phases")
+print("leader 0 (cluster 0) timeline: epoch  wait_for_workers_us  post_us  phase  ncand  T")
 for r in range(1, R + 1):
-    t0, t1, t2, t3, ph, ch, t6, t7, t8, t9, t10, t11 = t[r][:12]
-    nc = ch >> 32; ch &= 0xffffffff
-    nxt = t[r + 1][0] if r < R else t3
-    phs = " ".join(names[(ph >> (3 * k)) & 7] for k in range(K))
-    u = lambda a, b: (b - a) / 1e3 if (a > 0 and b > 0) else 0.0
-    print(f"{r:4d} {u(t0,t1):6.1f} {u(t1,t2):5.1f} {u(t2,t3):5.1f} {u(t3,nxt):5.1f} | {u(t2,t8):6.1f} {u(t8,t6):5.1f} {u(t6,t9):5.1f} {u(t9,t7):5.1f} {u(t7,t10):6.1f} {u(t10,t3):6.1f} | {ch:6d} {nc:6d} {phs}  T={np.array([t[r][12]]).view(np.float64)[0]:.4f}")
+    t0, t1, t2, t3, ph, ch = t[r][:6]
+    nc = ch >> 32
+    print(f"{r:4d} {(t1-t0)/1e3:8.1f} {(t3-t1)/1e3:8.1f}  {names[ph & 7]:3s} {nc:6d}  T={np.array([t[r][12]]).view(np.float64)[0]:.4f}")
+print("total us", (t[R][3] - t[1][0]) / 1e3)
