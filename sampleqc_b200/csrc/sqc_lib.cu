@@ -337,7 +337,7 @@ template <int D> int mcd_max_grid(int n_sm) {
   int per = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_mcd<D, true>, MCD_THREADS, MCD_SMEM));
   if (per < 1) fail(SQC_ERR_CUDA, "k_mcd<%d> does not fit on an SM", D);
-  return n_sm;                                   // one CTA per SM
+  return std::min(n_sm, (MCD_NB - MCD_NF - 16) / MCD_WARPS);   // one CTA per SM (the prefix of grid x warps candidate regions sits behind the fine histogram)
 }
 template <int D> void launch_init_passes(sqc_session* S) {
   const Dev& s = S->dev;
@@ -605,13 +605,13 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
     mb.hist = S->alloc<unsigned int>((size_t)K * MCD_NB);
     mb.part = S->alloc<double>((size_t)S->mcd_grid * K * SQC_NMOM(D));
     const size_t nreg = (size_t)K * S->mcd_grid * MCD_WARPS;                 // candidate regions: one per (cluster, CTA, warp)
-    mb.cand_bits = S->alloc<unsigned long long>(nreg * MCD_CAPW, false);
-    mb.cand_pos = S->alloc<unsigned int>(nreg * MCD_CAPW, false);
-    mb.cand_r = S->alloc<double>(nreg * MCD_CAPW * D, false);
+    mb.cand_rec = S->alloc<unsigned long long>(nreg * MCD_CAPW * (2 + D), false);
     mb.cand_cnt = S->alloc<unsigned int>(nreg);
+    mb.fhist = S->alloc<unsigned int>((size_t)K * (MCD_NF + 4));
     mb.xc = S->xc.dev;
     mb.epoch = S->alloc<unsigned int>(2 * SQC_MAXK + 4); mb.arrive = mb.epoch + SQC_MAXK; mb.status = (int*)(mb.epoch + 2 * SQC_MAXK);
     s.mcd_sync = mb.epoch;
+    mb.trace_leader = getenv("SQC_MCD_TRACE") ? atoi(getenv("SQC_MCD_TRACE")) : 0;
     mb.trace = getenv("SQC_MCD_TRACE") ? S->alloc<long long>(16 * 512) : nullptr;
     if (S->rng_mode == SQC_RNG_R_COMPAT) {
       S->mt_state = S->alloc<uint32_t>(640 * 5); S->keybuf = S->alloc<int>(2 * (size_t)S->N_total, false);

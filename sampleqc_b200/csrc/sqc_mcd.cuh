@@ -43,6 +43,8 @@ constexpr int MCD_NB = 4096;                         // histogram bins per windo
 constexpr int MCD_NF = 1024;                         // fine bins inside the candidate bin (leader post; a 4 KB exchange on multi-GPU)
 constexpr int MCD_CAND_CAP = 8192;                   // a bin holding more cells than this is refined by another HIST round
 constexpr int MCD_CAPW = 32;                         // candidate slots per (CTA, warp, cluster) region
+constexpr int MCD_RPT = 8;                           // candidate regions per leader thread (grids up to 256 CTAs)
+constexpr int MCD_TCACHE = 64;                       // tie candidates whose residuals the leader keeps in shared memory
 constexpr int MCD_TINY = 512;                        // tie candidates (inside one fine bin) over all ranks
 constexpr size_t MCD_SMEM = (size_t)(MCD_NB + 8) * 4 + (size_t)MCD_TINY * 20 + 256;
 template <int D> struct McdCfg { static constexpr int CPT = (D <= 4) ? 8 : 4; static constexpr int CHUNK = MCD_THREADS * CPT; };
@@ -76,16 +78,16 @@ struct McdBufs {
   McdWork* work;
   unsigned int* hist;                  // K x MCD_NB
   double* part;                        // grid x K x NMOM(D) per-CTA moment partials
-  unsigned long long* cand_bits;       // K x regions x MCD_CAPW
-  unsigned int* cand_pos;              // K x regions x MCD_CAPW
-  double* cand_r;                      // K x regions x MCD_CAPW x D residuals of the candidates
+  unsigned long long* cand_rec;        // K x regions x MCD_CAPW records of 2 + D words: key bits, position, D residuals
   unsigned int* cand_cnt;              // K x regions
+  unsigned int* fhist;                 // K x (MCD_NF + 4): fine histogram of the candidates, built by the workers
   const int* keys;                     // R-compatible key stream of this call (N_total ints), or null
   unsigned long long call_mix;         // counter-mode key mix for this call
   long long stream_base;               // call * N_total: index of this call's first draw
   unsigned int* epoch;                 // K: state version of every cluster (0 at launch; the leader publishes 1, 2, ...)
   unsigned int* arrive;                // K: worker arrivals (0 at launch)
   int* status;                         // in-kernel error word (0 at launch): identical on every rank, derived from exchanged data only
+  int trace_leader;                    // which leader writes the trace
   long long* trace;                    // optional per-round timeline (debug): 16 words per round, word 0 of the buffer = rounds
   XchgDev xc;                          // peer windows (world <= 1: unused)
 };
@@ -236,6 +238,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
   unsigned int* sh_trank = sh_tref + MCD_TINY;                                         // MCD_TINY: owning rank
   __shared__ double sh_red[32 * NM];
   __shared__ double sh_out[NM];
+  __shared__ double sh_tr[MCD_TCACHE * D];      // residuals of the first tie candidates (leader)
   __shared__ long long sh_cstart[SQC_MAXK + 1];
   __shared__ long long sh_scan[33];
   __shared__ int sh_flag[6];
@@ -302,7 +305,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
       __syncthreads();
       if (!sh_flag[2]) break;
       ++my_epochs;
-      const bool tr = mb.trace && b == 0 && tid == 0 && my_epochs < 500;
+      const bool tr = mb.trace && b == mb.trace_leader && tid == 0 && my_epochs < 500;
       long long* trow = mb.trace + 16 * my_epochs;
       if (tr) { trow[0] = gtimer(); trow[4] = W->clu[k].phase; trow[5] = 0; for (int e = 6; e < 16; ++e) trow[e] = 0; }
       if (tid == 0) {
@@ -380,16 +383,18 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         const unsigned long long blo = cl.blo;
         const int fshift = cl.shift > 10 ? cl.shift - 10 : 0;        // MCD_NF = 1024 fine bins inside the candidate bin
         const unsigned int* ccnt = mb.cand_cnt + (long long)k * regions;
-        for (int i = tid; i < MCD_NF + 4; i += MCD_THREADS) sh_hist[i] = 0u;
-        if (tid == 0) { sh_flag[4] = 0; sh_flag[5] = 0; }
-        __syncthreads();
-        // 1. fine histogram of the candidates (regions in fixed order: thread t owns regions t, t + 512, ...)
-        for (int rg = tid; rg < regions; rg += MCD_THREADS) {
-          unsigned int cnum = ccnt[rg];
-          if (cnum > (unsigned)MCD_CAPW) { sh_hist[MCD_NF + 1] = 1u; cnum = MCD_CAPW; }     // region overflow -> refine
-          const long long cb = ((long long)k * regions + rg) * MCD_CAPW;
-          for (unsigned int sl = 0; sl < cnum; ++sl) atomicAdd(&sh_hist[(unsigned int)((mb.cand_bits[cb + sl] - blo) >> fshift)], 1u);
+        // per-CTA moment partials: issue the loads first, use them at the end (warp (m mod warps) owns moment m)
+        double part_pre[(NM + MCD_WARPS - 1) / MCD_WARPS];
+#pragma unroll
+        for (int q = 0; q < (NM + MCD_WARPS - 1) / MCD_WARPS; ++q) {
+          const int m = wid + q * MCD_WARPS;
+          double a2 = 0.0;
+          if (m < NM && need_mom) for (int bb = lane; bb < G; bb += 32) a2 += mb.part[((long long)bb * K + k) * NM + m];
+          part_pre[q] = a2;
         }
+        // 1. fine histogram of the candidates: built by the workers with atomics on mb.fhist
+        for (int i = tid; i < MCD_NF + 4; i += MCD_THREADS) { sh_hist[i] = mb.fhist[k * (MCD_NF + 4) + i]; mb.fhist[k * (MCD_NF + 4) + i] = 0u; }
+        if (tid == 0) { sh_flag[4] = 0; sh_flag[5] = 0; }
         __syncthreads();
         if (tr) trow[8] = gtimer();
         if constexpr (MULTI) xchg_sum_u32(mb.xc, k, sh_hist, MCD_NF + 2);
@@ -423,22 +428,44 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
           double cs[D];
 #pragma unroll
           for (int d = 0; d < D; ++d) cs[d] = cl.cshift[d];
-          for (int rg = tid; rg < regions; rg += MCD_THREADS) {
-            const unsigned int cnum = ccnt[rg];
-            const long long cb = ((long long)k * regions + rg) * MCD_CAPW;
-            for (unsigned int sl = 0; sl < cnum; ++sl) {
-              const unsigned long long bits = mb.cand_bits[cb + sl];
-              const int fb = (int)((bits - blo) >> fshift);
-              if (fb < fbin) {
-                if (need_mom) {
-                  double r[D];
+          // flat, canonical (region-major) index space over the candidates: prefix of the region counts in shared
+          // memory, then thread t takes candidates t, t + threads, ... (one record load each, all independent)
+          unsigned int* sh_pref = sh_hist + MCD_NF + 8;            // regions + 1 words behind the fine histogram
+          long long mine_c = 0;
+          unsigned int cn[MCD_RPT];
 #pragma unroll
-                  for (int d = 0; d < D; ++d) r[d] = mb.cand_r[(cb + sl) * D + d];
-                  Mom<D>::add(tot, r, cs, true);
+          for (int i = 0; i < MCD_RPT; ++i) { const int rg = tid * MCD_RPT + i; cn[i] = (rg < regions) ? min(ccnt[rg], (unsigned)MCD_CAPW) : 0u; mine_c += cn[i]; }
+          long long ncand_loc;
+          long long off_c = block_excl_scan<MCD_THREADS>(mine_c, sh_scan, &ncand_loc);
+#pragma unroll
+          for (int i = 0; i < MCD_RPT; ++i) { const int rg = tid * MCD_RPT + i; if (rg < regions) sh_pref[rg] = (unsigned int)off_c; off_c += cn[i]; }
+          if (tid == 0) sh_pref[regions] = (unsigned int)ncand_loc;
+          __syncthreads();
+          for (int f = tid; f < (int)ncand_loc; f += MCD_THREADS) {
+            int lo = 0, hi = regions;                               // the region with sh_pref[rg] <= f < sh_pref[rg + 1]
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sh_pref[mid] <= (unsigned)f) lo = mid; else hi = mid; }
+            const int rg = lo; const unsigned int sl = (unsigned)f - sh_pref[rg];   // (empty regions share a prefix with their successor: the largest index wins, which is the owner)
+            const unsigned long long* rec = mb.cand_rec + (((long long)k * regions + rg) * MCD_CAPW + sl) * (2 + D);
+            unsigned long long wv[2 + D];
+#pragma unroll
+            for (int e = 0; e < 2 + D; ++e) wv[e] = rec[e];
+            const unsigned long long bits = wv[0];
+            const int fb = (int)((bits - blo) >> fshift);
+            if (fb < fbin) {
+              if (need_mom) {
+                double r[D];
+#pragma unroll
+                for (int d = 0; d < D; ++d) r[d] = __longlong_as_double((long long)wv[2 + d]);
+                Mom<D>::add(tot, r, cs, true);
+              }
+            } else if (fb == fbin) {
+              const int t = atomicAdd(&sh_flag[4], 1);
+              if (t < MCD_TINY) {
+                sh_tkey[t] = bits; sh_tpos[t] = (unsigned int)wv[1]; sh_tref[t] = (unsigned int)(rg * MCD_CAPW + sl); sh_trank[t] = (unsigned)myrank;
+                if (t < MCD_TCACHE) {
+#pragma unroll
+                  for (int d = 0; d < D; ++d) sh_tr[t * D + d] = __longlong_as_double((long long)wv[2 + d]);
                 }
-              } else if (fb == fbin) {
-                const int t = atomicAdd(&sh_flag[4], 1);
-                if (t < MCD_TINY) { sh_tkey[t] = bits; sh_tpos[t] = mb.cand_pos[cb + sl]; sh_tref[t] = (unsigned int)(rg * MCD_CAPW + sl); sh_trank[t] = (unsigned)myrank; }
               }
             }
           }
@@ -508,23 +535,20 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
               const long long cb = (long long)k * regions * MCD_CAPW + (long long)(sh_tref[best] & 0x7fffffffu);
               double r[D];
 #pragma unroll
-              for (int d = 0; d < D; ++d) r[d] = mb.cand_r[cb * D + d];
+              for (int d = 0; d < D; ++d) r[d] = (best < MCD_TCACHE) ? sh_tr[best * D + d] : __longlong_as_double((long long)mb.cand_rec[cb * (2 + D) + 2 + d]);
               Mom<D>::add(tot, r, cs, true);
               lastk = sh_tkey[best]; lastp = sh_tpos[best]; first = false;
             }
           }
         }
         if (tr) trow[7] = gtimer();
-        // 4. per-CTA partials, fixed order: lane-strided over CTAs, then the warp tree
+        // 4. per-CTA partials (loaded at the start), fixed order: lane-strided over CTAs, then the warp tree
         if (ok && need_mom) {
 #pragma unroll
-          for (int m = 0; m < NM; ++m) {
-            if ((m % MCD_WARPS) == wid) {                            // warp (m mod warps) owns moment m
-              double a = 0.0;
-              for (int bb = lane; bb < G; bb += 32) a += mb.part[((long long)bb * K + k) * NM + m];
-              a = warp_sum(a);
-              if (lane == 0) tot[m] += a;
-            }
+          for (int q = 0; q < (NM + MCD_WARPS - 1) / MCD_WARPS; ++q) {
+            const double a = warp_sum(part_pre[q]);
+#pragma unroll
+            for (int m = 0; m < NM; ++m) if (m == wid + q * MCD_WARPS && lane == 0) tot[m] += a;
           }
         }
         __syncthreads();
@@ -731,11 +755,16 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
             const unsigned m = __ballot_sync(0xffffffffu, cand);
             if (m) {                                                // per-warp region, warp-deterministic order, no atomics
               const unsigned slot = wcount + __popc(m & ((1u << lane) - 1u));
-              if (cand && slot < (unsigned)MCD_CAPW) {
-                mb.cand_bits[cbase + slot] = bits[it];
-                mb.cand_pos[cbase + slot] = (unsigned int)epos[it];
+              if (cand) {
+                // fine bin inside the candidate bin (the leader only reads this histogram); region overflow is flagged there too
+                const int fsh = shift > 10 ? shift - 10 : 0;
+                atomicAdd(&mb.fhist[k * (MCD_NF + 4) + (slot < (unsigned)MCD_CAPW ? (unsigned int)((bits[it] - lo_b) >> fsh) : (unsigned)(MCD_NF + 1))], 1u);
+                if (slot < (unsigned)MCD_CAPW) {
+                  unsigned long long* rec = mb.cand_rec + (cbase + slot) * (2 + D);
+                  rec[0] = bits[it]; rec[1] = (unsigned long long)epos[it];
 #pragma unroll
-                for (int d = 0; d < D; ++d) mb.cand_r[(cbase + slot) * D + d] = r[it][d];
+                  for (int d = 0; d < D; ++d) rec[2 + d] = (unsigned long long)__double_as_longlong(r[it][d]);
+                }
               }
               wcount += __popc(m);
             }

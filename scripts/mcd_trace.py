@@ -1,6 +1,6 @@
 """per-round timeline of the last FastMCD kernel of a C3 fit (debug)"""
 import os, sys, ctypes as C
-os.environ["SQC_MCD_TRACE"] = "1"
+os.environ["SQC_MCD_TRACE"] = os.environ.get("TRACE_LEADER", "0")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from bench import workload
@@ -24,5 +24,7 @@ print("leader 0 (cluster 0) timeline: epoch  wait_for_workers_us  post_us  phase
 for r in range(1, R + 1):
     t0, t1, t2, t3, ph, ch = t[r][:6]
     nc = ch >> 32
-    print(f"{r:4d} {(t1-t0)/1e3:8.1f} {(t3-t1)/1e3:8.1f}  {names[ph & 7]:3s} {nc:6d}  T={np.array([t[r][12]]).view(np.float64)[0]:.4f}")
+    u = lambda a, b: (b - a) / 1e3 if (a > 0 and b > 0) else 0.0
+    t6, t7, t8, t9, t10, t11 = t[r][6:12]
+    print(f"{r:4d} {(t1-t0)/1e3:8.1f} {(t3-t1)/1e3:8.1f}  {names[ph & 7]:3s} {nc:6d}  T={np.array([t[r][12]]).view(np.float64)[0]:.4f} | fhist {u(t1,t8):.1f} scan {u(t8,t6):.1f} pass2 {u(t6,t9):.1f} tie {u(t9,t7):.1f} partials {u(t7,t10):.1f} reduce {u(t10,t11):.1f} linalg {u(t11,t3):.1f}")
 print("total us", (t[R][3] - t[1][0]) / 1e3)
