@@ -173,7 +173,9 @@ class FitBuffers:
         }
         if self.variant == SQC_VARIANT_MLE:
             res["gamma_i"] = self.gamma_i
-        res["z"] = self.z.astype(np.float64).reshape(-1, 1)
+        # 1-based labels as an N x 1 column; kept int32 (Rcpp wraps the arma::uvec as double: as.integer() in R is free,
+        # a float64 copy of 10^7 labels here costs more than the D2H transfer)
+        res["z"] = self.z.reshape(-1, 1)
         if self.variant == SQC_VARIANT_MLE:
             res["p_k"] = self.p_k.reshape(-1, 1)
         res["p_jk"] = self.p_jk

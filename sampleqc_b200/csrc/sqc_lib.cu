@@ -461,7 +461,15 @@ void check_args(const sqc_fit_args* a, int variant) {
   if (a->rng_mode != SQC_RNG_R_COMPAT && a->rng_mode != SQC_RNG_COUNTER) fail(SQC_ERR_BAD_ARG, "unknown rng_mode");
 }
 
+double now_ms();
+struct PhaseTimer {
+  bool on; double t0; const char* what[16]; double dt[16]; int n = 0;
+  PhaseTimer() : on(getenv("SQC_TIMING") != nullptr), t0(0) { if (on) t0 = now_ms(); }
+  void mark(const char* w) { if (!on || n >= 16) return; const double t = now_ms(); what[n] = w; dt[n++] = t - t0; t0 = t; }
+  void dump(const char* head) { if (!on) return; fprintf(stderr, "[sqc timing] %s:", head); for (int i = 0; i < n; ++i) fprintf(stderr, " %s %.2f", what[i], dt[i]); fprintf(stderr, "\n"); }
+};
 sqc_session* session_create(const sqc_fit_args* a, int variant) {
+  PhaseTimer pt;
   check_args(a, variant);
   std::unique_ptr<sqc_session> up(new sqc_session());
   sqc_session* S = up.get();
@@ -487,6 +495,7 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
     if (S->track) est += (double)em * (J * (D + K) + K * D * (D + 1)) * 8.0;
     S->first_chunk_bytes = (size_t)est;
   }
+  pt.mark("setup");
   // ---- upload x first (asynchronous from pinned memory), scan the sample layout on the host meanwhile ----
   Dev& s = S->dev;
   s.x = S->alloc<double>((size_t)N * D, false);
@@ -520,6 +529,7 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
       for (int j = 0; j < J; ++j) n_j[j] += cnt[t][j];
     }
   }
+  pt.mark("x_enqueue+scan");
   S->sorted = sorted;
   if (!sorted) {                                    // stable counting sort by sample
     std::vector<long long> start(J + 1, 0);
@@ -546,7 +556,9 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
   s.z = S->alloc<uint8_t>(N);
   auto up_i = [&](const std::vector<int>& v) { int* p = S->alloc<int>(v.size(), false); CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, S->st)); return p; };
   s.tile_start = up_i(t_start); s.tile_len = up_i(t_len); s.tile_sample = up_i(t_sample); s.sample_tile_begin = up_i(s_tb); s.sample_n = up_i(s_n);
+  pt.mark("tiles");
   CK(cudaStreamSynchronize(S->st));                 // the host vectors above go out of scope
+  pt.mark("sync_x_upload");
   s.mu0 = S->alloc<double>(D); s.alpha = S->alloc<double>((size_t)J * D); s.beta = S->alloc<double>((size_t)K * D);
   s.sigma = S->alloc<double>((size_t)K * D * D); s.linv = S->alloc<double>((size_t)K * D * D); s.ainv = S->alloc<double>((size_t)K * D * D);
   s.logP = S->alloc<double>(K); s.Pk = S->alloc<double>(K);
@@ -627,12 +639,15 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
   } else {
     mle_alloc(*S, a, S->ml);
   }
+  pt.mark("allocs+labels");
   // ---- centring: mu_0 = colMeans(x) (:478), x <- x - mu_0 (centre_x), alpha_j = per-sample means ----
   S->stats = sqc_run_stats{};
   do_init_passes(S);
   CK(cudaMemcpyAsync(S->alpha0, s.alpha, (size_t)J * D * sizeof(double), cudaMemcpyDeviceToDevice, S->st));
   CK(cudaStreamSynchronize(S->st));
   CK(cudaEventCreate(&S->ev_run0)); CK(cudaEventCreate(&S->ev_init)); CK(cudaEventCreate(&S->ev_loop));
+  pt.mark("init_passes");
+  pt.dump("create");
   return up.release();
 }
 
