@@ -234,7 +234,7 @@ struct sqc_session {
   int em_iters = 0, mcd_iters = 0, rng_mode = 0, track = 0, rank = 0, world = 1;
   double mcd_alpha = 0.5; unsigned seed = 0;
   cudaStream_t st = nullptr, st_rng = nullptr;
-  cudaEvent_t ev_key_ready[2] = {nullptr, nullptr}, ev_key_free[2] = {nullptr, nullptr};
+  cudaEvent_t ev_key_ready[2] = {nullptr, nullptr}, ev_key_free[2] = {nullptr, nullptr}, ev_pre_mcd = nullptr;
   std::vector<void*> allocs;
   Dev dev{};
   McdBufs mb{};
@@ -279,6 +279,7 @@ struct sqc_session {
     if (ev_init) cudaEventDestroy(ev_init);
     if (ev_loop) cudaEventDestroy(ev_loop);
     for (int i = 0; i < 2; ++i) { if (ev_key_ready[i]) cudaEventDestroy(ev_key_ready[i]); if (ev_key_free[i]) cudaEventDestroy(ev_key_free[i]); }
+    if (ev_pre_mcd) cudaEventDestroy(ev_pre_mcd);
     if (st_rng && st_rng != st) cudaStreamDestroy(st_rng);
     if (st) cudaStreamDestroy(st);
   }
@@ -328,6 +329,9 @@ template <int D> void launch_mcd(sqc_session* S) {
   Launch L(S, SQC_KF_MCD);
   void* args[] = {(void*)&S->dev, (void*)&S->mb};
   void* fn = S->world > 1 ? (void*)k_mcd<D, true> : (void*)k_mcd<D, false>;
+  // cooperative launch = guaranteed co-residency of the leader / worker CTAs that wait on each other's flags.  (A plain
+  // launch was tried so that the key-stream kernels could run beside it; they still did not — the two kernels want
+  // different shared-memory carve-outs — so the guarantee is kept.)
   CK(cudaLaunchCooperativeKernel(fn, dim3(S->mcd_grid), dim3(MCD_THREADS), args, MCD_SMEM, S->st));
   L.done();
 }
@@ -631,6 +635,7 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
       else CK(cudaStreamCreateWithFlags(&S->st_rng, cudaStreamNonBlocking));
       if (getenv("SQC_MT_BLOCKS")) S->mt_target_blocks = std::max(1, atoi(getenv("SQC_MT_BLOCKS")));
       for (int i = 0; i < 2; ++i) { CK(cudaEventCreateWithFlags(&S->ev_key_ready[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&S->ev_key_free[i], cudaEventDisableTiming)); }
+      CK(cudaEventCreateWithFlags(&S->ev_pre_mcd, cudaEventDisableTiming));
       S->mt_seq = S->alloc<uint32_t>(MT_SEQ_WORDS + (size_t)(SQC_MT_JUMP_ROWS + 2) * MT_N);
       S->mt_table = S->alloc<uint32_t>((size_t)SQC_MT_JUMP_ROWS * MT_N, false);
       CK(cudaMemcpyAsync(S->mt_table, sqc_mt_jump_table, sizeof sqc_mt_jump_table, cudaMemcpyHostToDevice, S->st));
@@ -687,10 +692,13 @@ void mt_generate(cudaStream_t stream, const uint32_t* st_in, uint32_t* st_out, u
 // Keys of update_beta_scale_k call `call` (every call consumes exactly N_total draws).
 // They do not depend on the data, so they are produced on a side stream, up to two calls ahead of the EM
 // loop; state_after[c] lives in slot c % 3 so that the state after the last EXECUTED call survives.
-void enqueue_keys(sqc_session* S, int call) {
+void enqueue_keys(sqc_session* S, int call, cudaEvent_t after) {
   if (S->rng_mode != SQC_RNG_R_COMPAT) return;
   const int kb = call & 1;
+  // the buffer of call was last read by the M-step of call - 2 (key_free), and the generation is meant to run beside
+  // the M-step kernel of call - 1, which leaves room for it (`after` is recorded right before that launch)
   CK(cudaStreamWaitEvent(S->st_rng, S->ev_key_free[kb], 0));
+  if (after) CK(cudaStreamWaitEvent(S->st_rng, after, 0));
   uint32_t* base = S->mt_state;
   mt_generate(S->st_rng, base + 640 * ((call + 2) % 3), base + 640 * (call % 3), base + 640 * 3, base + 640 * 4, S->mt_seq, S->mt_table,
               S->keybuf + (size_t)kb * S->N_total, S->N_total, S->dev.ctl, S, S->mt_target_blocks);
@@ -698,6 +706,8 @@ void enqueue_keys(sqc_session* S, int call) {
 }
 void use_keys(sqc_session* S, int call) {
   if (S->rng_mode == SQC_RNG_R_COMPAT) {
+    // the keys of the NEXT call are generated while this call's M-step kernel runs
+    if (call + 1 <= S->em_iters) { CK(cudaEventRecord(S->ev_pre_mcd, S->st)); enqueue_keys(S, call + 1, S->ev_pre_mcd); }
     CK(cudaStreamWaitEvent(S->st, S->ev_key_ready[call & 1], 0));
     S->mb.keys = S->keybuf + (size_t)(call & 1) * S->N_total;
   } else S->mb.keys = nullptr;
@@ -707,7 +717,6 @@ void use_keys(sqc_session* S, int call) {
 void release_keys(sqc_session* S, int call) {
   if (S->rng_mode != SQC_RNG_R_COMPAT) return;
   CK(cudaEventRecord(S->ev_key_free[call & 1], S->st));
-  if (call + 2 <= S->em_iters) enqueue_keys(S, call + 2);
 }
 
 void run_robust(sqc_session* S) {
@@ -725,8 +734,7 @@ void run_robust(sqc_session* S) {
     CK(cudaEventRecord(S->ev_key_free[0], S->st)); CK(cudaEventRecord(S->ev_key_free[1], S->st));   // after k_ctl_reset
     CK(cudaStreamWaitEvent(S->st_rng, S->ev_key_free[0], 0));
     { Launch L(S, SQC_KF_RNG); k_mt_seed<<<1, 32, 0, S->st_rng>>>(S->mt_state + 640 * 2, S->seed); L.done(); }
-    enqueue_keys(S, 0);
-    if (S->em_iters >= 1) enqueue_keys(S, 1);
+    enqueue_keys(S, 0, nullptr);
   }
   const int nsb = (J + 31) / 32;
   auto post_stats = [&](int fuse_ctl) {

@@ -50,11 +50,14 @@ __global__ void __launch_bounds__(256) k_mt_seq(const uint32_t* st, uint32_t* se
 //     window[j] = XOR_{i : bit i of the row} seq[i + j + 1],   j = 0 .. 623.
 // Register-tiled: a thread owns 8 consecutive outputs and walks the taps 32 at a time; the 39 sequence words a
 // table word can touch are fetched with ten 128-bit shared-memory loads and reused for all (tap, output) pairs,
-// so shared-memory traffic is ~1 byte per pair instead of 4.  The taps are split over 6 groups of 3 warps
-// (the tap bits are warp-uniform: no divergence); the 6 partial windows are XOR-ed through shared memory.
+// so shared-memory traffic is ~1 byte per pair instead of 4.  The taps are split over MT_JG groups of 3 warps
+// (the tap bits are warp-uniform: no divergence); the partial windows are XOR-ed through shared memory.
 constexpr int MT_JT = 96;                                 // threads per tap group (78 own outputs, 3 warps)
-constexpr int MT_JG = 6;                                  // tap groups: 624 / 6 = 104 table words each
-constexpr int MT_JUMP_THREADS = MT_JT * MT_JG;            // 576
+#ifndef SQC_MT_JG
+#define SQC_MT_JG 6
+#endif
+constexpr int MT_JG = SQC_MT_JG;                          // tap groups (624 / MT_JG table words each)
+constexpr int MT_JUMP_THREADS = MT_JT * MT_JG;
 constexpr int MT_SEQ_PAD = MT_SEQ_WORDS + 64;             // the last tiles read a few words past the sequence
 constexpr size_t MT_SMEM = (size_t)(MT_SEQ_PAD + MT_N + MT_JG * MT_N) * sizeof(uint32_t);
 __global__ void __launch_bounds__(MT_JUMP_THREADS) k_mt_jump(const uint32_t* st_in, const uint32_t* seq, const uint32_t* table, uint32_t* windows,
