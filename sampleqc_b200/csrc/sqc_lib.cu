@@ -241,7 +241,7 @@ struct sqc_session {
   MleBufs ml{};
   Xchg xc{};
   uint8_t* z0 = nullptr; double* alpha0 = nullptr; double* gamma0 = nullptr;
-  int mt_target_blocks = 146;
+  int mt_target_blocks = 49;
   unsigned long long* xg_gather = nullptr; double* xg_vec = nullptr;
   uint32_t* mt_state = nullptr; uint32_t* mt_seq = nullptr; uint32_t* mt_table = nullptr; int* keybuf = nullptr;
   double* o_buf = nullptr; int* o_z = nullptr; int* o_korder = nullptr; OutPtrs optr{};
@@ -660,15 +660,20 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
 // Waves of at most SQC_MT_JUMP_ROWS + 1 blocks; each wave = one sequential 33-chunk kernel + one
 // block-parallel kernel; tmp[2] hold the states between waves.
 void mt_generate(cudaStream_t stream, const uint32_t* st_in, uint32_t* st_out, uint32_t* tmp0, uint32_t* tmp1, uint32_t* seq,
-                 const uint32_t* table, int* out, long long n, const Control* ctl, sqc_session* S, int target_blocks = 146) {
+                 const uint32_t* table, int* out, long long n, const Control* ctl, sqc_session* S, int target_blocks = 49) {
   long long done = 0; int w = 0;
   const uint32_t* cur = st_in;
   if (n <= 0) { CK(cudaMemcpyAsync(st_out, st_in, 625 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream)); return; }
-  // block length = mult * 110 chunks.  One wave serves up to 149 blocks; the shortest blocks (mult = 1) give the
-  // shortest latency and are used whenever a wave is filled; target_blocks < 146 asks for longer blocks (tests).
+  // block length = mult * 110 chunks; a wave serves up to 148 / mult + 1 blocks.  Longer blocks need fewer GF(2)
+  // correlations (the expensive part, which competes with the E-step for the SMs) at the price of a longer
+  // sequential tail; measured best at C3: ~49 blocks of 330 chunks (mult = 3).  Never more than 3: the generation
+  // of one call has to fit beside one EM iteration.  target_blocks >= 146 asks for the shortest blocks.
   int mult = 1;
-  if (target_blocks < SQC_MT_JUMP_ROWS - 2)
-    mult = (int)std::max<long long>(1, std::min<long long>(SQC_MT_JUMP_ROWS / 2, (n / MT_BLOCK_WORDS + target_blocks / 2) / target_blocks));
+  if (target_blocks < SQC_MT_JUMP_ROWS - 2) {
+    mult = (int)std::max<long long>(1, (n / MT_BLOCK_WORDS + target_blocks / 2) / target_blocks);
+    if (S) mult = std::min(mult, 3);
+    mult = std::min(mult, SQC_MT_JUMP_ROWS / 2);
+  }
   const long long blk_words = MT_BLOCK_WORDS * mult;
   const long long wave_words = (long long)(SQC_MT_JUMP_ROWS / mult + 1) * blk_words;
   while (done < n) {
