@@ -39,6 +39,9 @@ namespace sqc {
 #endif
 constexpr int MCD_THREADS = SQC_MCD_THREADS;         // one fat CTA per SM: one histogram per SM
 constexpr int MCD_WARPS = MCD_THREADS / 32;
+#ifndef SQC_MCD_DIRECT
+#define SQC_MCD_DIRECT 1          // 0: always take the HIST round (debug / A-B)
+#endif
 constexpr int MCD_NB = 4096;                         // histogram bins per window
 constexpr int MCD_NF = 1024;                         // fine bins inside the candidate bin (leader post; a 4 KB exchange on multi-GPU)
 constexpr int MCD_CAND_CAP = 8192;                   // a bin holding more cells than this is refined by another HIST round
@@ -58,7 +61,8 @@ struct McdClu {
   unsigned long long wlo, whi;         // histogram window (sortable bits)
   unsigned long long blo, bhi;         // candidate bin (sortable bits)
   unsigned long long t_prev;           // last resolved threshold (distance bits), 0 = none
-  int shift, phase, is_final, iters, n_hist_rounds, pad;
+  int shift, phase, is_final, iters, n_hist_rounds, direct;   // direct: COLLECT round entered without a HIST round (predicted band)
+  double last_rel, dens;               // relative change of the threshold over the last C-step; candidates per unit of relative width
   double det_old, det_new, q_chisq;
   double cshift[SQC_MAXD];             // moment shift
   double loc[SQC_MAXD];
@@ -263,7 +267,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
       const long long n = s.clu_n_glob[k];
       c.n = n; c.n_loc = s.clu_n[k]; c.off = s.clu_off[k]; c.prefix = s.clu_prefix[k];
       c.h = (long long)(int)((double)(unsigned long long)(n + D + 1) * s.mcd_alpha);   // :306 truncation
-      c.iters = 0; c.is_final = 0; c.t_prev = 0ull; c.n_hist_rounds = 0; c.below = 0;
+      c.iters = 0; c.is_final = 0; c.t_prev = 0ull; c.n_hist_rounds = 0; c.below = 0; c.direct = 0; c.last_rel = 1.0; c.dens = 0.0;
       c.det_old = 0.0; c.det_new = 0.0;
       int err = 0;
       if (n <= 0) err = SQC_D_EMPTY_CLUSTER;                       // x_k.rows(0, -1), :307
@@ -379,7 +383,9 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         }
       } else {
         // ---- COLLECT post: exact members of the candidate bin, then the moments ---------------
+        const bool direct = cl.direct != 0;                          // no HIST round before: `below` comes from the workers' counts
         const bool need_mom = (phase == PH_KEY_COLLECT) || !cl.is_final;
+        const bool have_part = need_mom || direct;
         const unsigned long long blo = cl.blo;
         const int fshift = cl.shift > 10 ? cl.shift - 10 : 0;        // MCD_NF = 1024 fine bins inside the candidate bin
         const unsigned int* ccnt = mb.cand_cnt + (long long)k * regions;
@@ -389,15 +395,20 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         for (int q = 0; q < (NM + MCD_WARPS - 1) / MCD_WARPS; ++q) {
           const int m = wid + q * MCD_WARPS;
           double a2 = 0.0;
-          if (m < NM && need_mom) for (int bb = lane; bb < G; bb += 32) a2 += mb.part[((long long)bb * K + k) * NM + m];
+          if (m < NM && have_part) for (int bb = lane; bb < G; bb += 32) a2 += mb.part[((long long)bb * K + k) * NM + m];
           part_pre[q] = a2;
         }
         // 1. fine histogram of the candidates: built by the workers with atomics on mb.fhist
         for (int i = tid; i < MCD_NF + 4; i += MCD_THREADS) { sh_hist[i] = mb.fhist[k * (MCD_NF + 4) + i]; mb.fhist[k * (MCD_NF + 4) + i] = 0u; }
         if (tid == 0) { sh_flag[4] = 0; sh_flag[5] = 0; }
+        if (direct && wid == 0) {                                    // cells strictly under the band: moment 0 of the partials (exact: counts < 2^53)
+          const double cb = warp_sum(part_pre[0]);
+          const unsigned long long cnt = (unsigned long long)cb;
+          if (lane == 0) { sh_hist[MCD_NF + 2] = (unsigned int)cnt; sh_hist[MCD_NF + 3] = (unsigned int)(cnt >> 32); }
+        }
         __syncthreads();
         if (tr) trow[8] = gtimer();
-        if constexpr (MULTI) xchg_sum_u32(mb.xc, k, sh_hist, MCD_NF + 2);
+        if constexpr (MULTI) xchg_sum_u32(mb.xc, k, sh_hist, MCD_NF + 4);
         const bool overflow = sh_hist[MCD_NF + 1] != 0;
         constexpr int PER = (MCD_NF + MCD_THREADS - 1) / MCD_THREADS;
         unsigned int hv[PER]; long long mine = 0;
@@ -405,7 +416,8 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         for (int i = 0; i < PER; ++i) { hv[i] = (tid * PER + i < MCD_NF) ? sh_hist[tid * PER + i] : 0u; mine += hv[i]; }
         long long ncand_all;
         long long run = block_excl_scan<MCD_THREADS>(mine, sh_scan, &ncand_all);
-        const long long take = cl.h - cl.below;                      // candidates (over all ranks) that belong to the h-subset
+        const long long below_all = direct ? ((long long)sh_hist[MCD_NF + 2] + ((long long)sh_hist[MCD_NF + 3] << 32)) : cl.below;
+        const long long take = cl.h - below_all;                     // candidates (over all ranks) that belong to the h-subset
         if (tid == 0) sh_flag[1] = -1;
         __syncthreads();
         if (take >= 1 && take <= ncand_all) {
@@ -557,7 +569,13 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         if constexpr (MULTI) { if (ok && need_mom) xchg_sum_f64(mb.xc, k, sh_out, NM); }
         if (tr) trow[11] = gtimer();
         if (tid == 0) {
-          if (!ok) {
+          if (!ok && direct) {
+            // the predicted band missed the h-th distance (or caught too many cells): take the regular HIST round
+            cl.direct = 0; cl.last_rel = 1.0;
+            cl.phase = PH_DIST_HIST; cl.n_hist_rounds = 0;
+            const double t = __longlong_as_double((long long)cl.t_prev);
+            set_dist_window(cl, t * 0.25, t * 8.0);
+          } else if (!ok) {
             // too many candidates in one place (region overflow or a crowded fine bin): refine with another HIST round
             if (fbin >= 0 && cl.shift > 0 && cl.n_hist_rounds <= 40) {
               cl.wlo = cl.blo; cl.whi = cl.bhi; cl.shift = window_shift(cl.wlo, cl.whi);
@@ -578,6 +596,13 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
               cl.det_old = cl.det_new;
               cl.det_new = small_det(cl.scale, D);
               cl.iters++;
+              {
+                const double tn = __longlong_as_double((long long)thr);
+                cl.last_rel = cl.t_prev ? fabs(tn - __longlong_as_double((long long)cl.t_prev)) / tn : 1.0;
+                // candidates per unit of relative width of the bin just resolved (bit distance / 2^52 ~ relative distance)
+                const double relw = (double)(cl.bhi - cl.blo) * 2.220446049250313e-16;
+                cl.dens = relw > 0.0 ? (double)ncand_all / relw : 1e300;
+              }
               cl.t_prev = thr;
               if (tr) trow[12] = (long long)thr;
               atomicAdd((unsigned long long*)&s.ctl->mcd_csteps, 1ull);
@@ -599,8 +624,20 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
             else if (!prepare_dist<D>(cl)) { atomicCAS(&(*mb.status), 0, SQC_D_NOT_SPD); cl.phase = PH_DONE; }   // chol(), :19
             else {
               cl.is_final = go_final ? 1 : 0;
-              cl.phase = PH_DIST_HIST; cl.n_hist_rounds = 0;
-              if (cl.t_prev) {
+              cl.phase = PH_DIST_HIST; cl.n_hist_rounds = 0; cl.direct = 0;
+              // once the threshold has settled (it moves less from one C-step to the next), skip the HIST round: predict a
+              // band around the last threshold that should hold the next one and few enough cells; the COLLECT round
+              // counts the cells under the band itself.  A miss costs one regular round.
+              const double wband = 2.0 * cl.last_rel + 5e-4;
+              if (cl.t_prev && cl.last_rel < 0.02 && cl.dens * 2.0 * wband <= 3000.0 && SQC_MCD_DIRECT) {
+                const double t = __longlong_as_double((long long)cl.t_prev);
+                cl.blo = dist_bits(t * (1.0 - wband)); cl.bhi = dist_bits(t * (1.0 + wband));
+                int fs = 0;
+                while (fs < 62 && ((cl.bhi - cl.blo) >> fs) >= (unsigned long long)MCD_NF) ++fs;
+                cl.shift = fs + 10;                                 // the workers bin candidates with shift - 10
+                cl.below = 0; cl.direct = 1;
+                cl.phase = PH_DIST_COLLECT;
+              } else if (cl.t_prev) {
                 // the trimmed scatter of the first C-step shrinks the scale (distances grow by up to
                 // 1 / c(p)); later C-steps move the threshold by little.  Wide, cheap window either way.
                 const double t = __longlong_as_double((long long)cl.t_prev);
@@ -682,7 +719,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
       for (int d = 0; d < D; ++d) { loc[d] = cl.loc[d]; cs[d] = cl.cshift[d]; }
 #pragma unroll
       for (int e = 0; e < SQC_TRI(D); ++e) lt[e] = cl.linv[e];
-      const bool need_mom = (phase == PH_KEY_COLLECT) || (phase == PH_DIST_COLLECT && !cl.is_final);
+      const bool need_mom = (phase == PH_KEY_COLLECT) || (phase == PH_DIST_COLLECT && (!cl.is_final || cl.direct));
       const double* rsb = s.rs + cl.off;
       const long long kbase = cl.prefix;                            // key-stream offset of the local segment's first cell
       if (hist_round) { for (int i = tid; i < MCD_NB; i += MCD_THREADS) sh_hist[i] = 0u; }
