@@ -42,6 +42,9 @@ constexpr int MCD_WARPS = MCD_THREADS / 32;
 #ifndef SQC_MCD_DIRECT
 #define SQC_MCD_DIRECT 1          // 0: always take the HIST round (debug / A-B)
 #endif
+#ifndef SQC_MCD_DIRECT_CAP
+#define SQC_MCD_DIRECT_CAP 3000.0 // expected candidates a direct round may catch
+#endif
 constexpr int MCD_NB = 4096;                         // histogram bins per window
 constexpr int MCD_NF = 1024;                         // fine bins inside the candidate bin (leader post; a 4 KB exchange on multi-GPU)
 constexpr int MCD_CAND_CAP = 8192;                   // a bin holding more cells than this is refined by another HIST round
@@ -263,7 +266,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
   if (b < K) {
     const int k = b;
     if (tid == 0) {
-      McdClu& c = W->clu[k];
+      McdClu& c = sh_clu;                                        // the leader keeps its cluster's state in shared memory
       const long long n = s.clu_n_glob[k];
       c.n = n; c.n_loc = s.clu_n[k]; c.off = s.clu_off[k]; c.prefix = s.clu_prefix[k];
       c.h = (long long)(int)((double)(unsigned long long)(n + D + 1) * s.mcd_alpha);   // :306 truncation
@@ -293,27 +296,35 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
   if (b < K) {
     // =========================== leader of cluster k: waits for the workers, post-processes, publishes ===========================
     const int k = b;
-    __threadfence();
     __syncthreads();
+    // publish = copy the state to global memory, fence, release the epoch (the workers snapshot it from there)
+    auto publish = [&](int epoch_no) {
+      const unsigned long long* src = (const unsigned long long*)&sh_clu;
+      unsigned long long* dst = (unsigned long long*)&W->clu[k];
+      for (int i = tid; i < (int)(sizeof(McdClu) / 8); i += MCD_THREADS) dst[i] = src[i];
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) st_release_u32(&mb.epoch[k], (unsigned)epoch_no);
+    };
     int ep = 1;
+    publish(1);
     if (tid == 0) {
-      st_release_u32(&mb.epoch[k], 1u);
       // qchisq(h / n, D) of the consistency factor (:101-102) is first needed after the start rounds: evaluate it
       // while the workers stream the first one
-      McdClu& c = W->clu[k];
+      McdClu& c = sh_clu;
       if (c.phase != PH_DONE) c.q_chisq = dev_qchisq((double)c.h / (double)c.n, D);
     }
     long long my_epochs = 0, my_cells = 0, my_bytes = 0;
     for (;;) {
-      if (tid == 0) sh_flag[2] = (W->clu[k].phase != PH_DONE) ? 1 : 0;
+      if (tid == 0) sh_flag[2] = (sh_clu.phase != PH_DONE) ? 1 : 0;
       __syncthreads();
       if (!sh_flag[2]) break;
       ++my_epochs;
       const bool tr = mb.trace && b == mb.trace_leader && tid == 0 && my_epochs < 500;
       long long* trow = mb.trace + 16 * my_epochs;
-      if (tr) { trow[0] = gtimer(); trow[4] = W->clu[k].phase; trow[5] = 0; for (int e = 6; e < 16; ++e) trow[e] = 0; }
+      if (tr) { trow[0] = gtimer(); trow[4] = sh_clu.phase; trow[5] = 0; for (int e = 6; e < 16; ++e) trow[e] = 0; }
       if (tid == 0) {
-        const int ph = W->clu[k].phase; const long long n = W->clu[k].n_loc;
+        const int ph = sh_clu.phase; const long long n = sh_clu.n_loc;
         const bool keyr = (ph == PH_KEY_HIST || ph == PH_KEY_COLLECT);
         my_cells += n; my_bytes += n * ((ph == PH_KEY_HIST ? 0 : 8 * D) + ((keyr && mb.keys) ? 4 : 0));
         // every worker arrives once per epoch, whether or not it holds cells of this cluster
@@ -325,7 +336,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
       __syncthreads();
       if (tr) { trow[1] = gtimer(); trow[2] = trow[1]; }
       {
-      McdClu& cl = W->clu[k];
+      McdClu& cl = sh_clu;
       const int phase = cl.phase;
       const bool key_phase = (phase == PH_KEY_HIST || phase == PH_KEY_COLLECT);
       if (phase == PH_KEY_HIST || phase == PH_DIST_HIST) {
@@ -395,7 +406,13 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         for (int q = 0; q < (NM + MCD_WARPS - 1) / MCD_WARPS; ++q) {
           const int m = wid + q * MCD_WARPS;
           double a2 = 0.0;
-          if (m < NM && have_part) for (int bb = lane; bb < G; bb += 32) a2 += mb.part[((long long)bb * K + k) * NM + m];
+          if (m < NM && have_part) {
+            double pv[8];                                            // all loads in flight together (grids up to 256 CTAs)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const int bb = lane + 32 * i; pv[i] = (bb < G) ? mb.part[((long long)bb * K + k) * NM + m] : 0.0; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a2 += pv[i];
+          }
           part_pre[q] = a2;
         }
         // 1. fine histogram of the candidates: built by the workers with atomics on mb.fhist
@@ -629,7 +646,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
               // band around the last threshold that should hold the next one and few enough cells; the COLLECT round
               // counts the cells under the band itself.  A miss costs one regular round.
               const double wband = 2.0 * cl.last_rel + 5e-4;
-              if (cl.t_prev && cl.last_rel < 0.02 && cl.dens * 2.0 * wband <= 3000.0 && SQC_MCD_DIRECT) {
+              if (cl.t_prev && cl.last_rel < 0.02 && cl.dens * 2.0 * wband <= SQC_MCD_DIRECT_CAP && SQC_MCD_DIRECT) {
                 const double t = __longlong_as_double((long long)cl.t_prev);
                 cl.blo = dist_bits(t * (1.0 - wband)); cl.bhi = dist_bits(t * (1.0 + wband));
                 int fs = 0;
@@ -651,10 +668,9 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
       }
       }
       if (tr) { trow[3] = gtimer(); mb.trace[0] = my_epochs; }
-      __threadfence();
       __syncthreads();
       ++ep;
-      if (tid == 0) st_release_u32(&mb.epoch[k], (unsigned)ep);
+      publish(ep);
     }
     if (tid == 0) {
       atomicAdd((unsigned long long*)&s.ctl->mcd_passes, (unsigned long long)my_epochs);
