@@ -36,8 +36,11 @@ struct MleBufs {
 
 template <int D> struct MlePar { static constexpr int SZ = D + SQC_TRI(D) + 1; };
 
+#ifndef SQC_MLE_MINB
+#define SQC_MLE_MINB 3
+#endif
 template <int D, int MODE>
-__global__ void __launch_bounds__(EST_THREADS) k_mle_pass(Dev s, MleBufs m) {
+__global__ void __launch_bounds__(EST_THREADS, SQC_MLE_MINB) k_mle_pass(Dev s, MleBufs m) {
   constexpr int CPT = TileCfg<D>::CPT, TILE = TileCfg<D>::TILE, SZ = MlePar<D>::SZ, NW = EST_THREADS / 32;
   constexpr int NM = (MODE == MLE_A) ? (1 + D) : SQC_NMOM(D);
   extern __shared__ double sh_dyn[];
