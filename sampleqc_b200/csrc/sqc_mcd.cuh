@@ -42,6 +42,9 @@ constexpr int MCD_WARPS = MCD_THREADS / 32;
 #ifndef SQC_MCD_DIRECT
 #define SQC_MCD_DIRECT 1          // 0: always take the HIST round (debug / A-B)
 #endif
+#ifndef SQC_MCD_DIRECT_KEYCAP
+#define SQC_MCD_DIRECT_KEYCAP 12000.0   // same for the random-key start round (the leader walks them in ~20 us)
+#endif
 #ifndef SQC_MCD_DIRECT_CAP
 #define SQC_MCD_DIRECT_CAP 3000.0 // expected candidates a direct round may catch
 #endif
@@ -65,6 +68,7 @@ struct McdClu {
   unsigned long long blo, bhi;         // candidate bin (sortable bits)
   unsigned long long t_prev;           // last resolved threshold (distance bits), 0 = none
   int shift, phase, is_final, iters, n_hist_rounds, direct;   // direct: COLLECT round entered without a HIST round (predicted band)
+  int key_shift, pad2;                 // shift of the +-8 sigma key window while a direct key round is tried
   double last_rel, dens;               // relative change of the threshold over the last C-step; candidates per unit of relative width
   double det_old, det_new, q_chisq;
   double cshift[SQC_MAXD];             // moment shift
@@ -287,6 +291,18 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         c.wlo = (unsigned long long)lo; c.whi = (unsigned long long)hi;
         c.shift = window_shift(c.wlo, c.whi);
         c.phase = PH_KEY_HIST;
+        // the key threshold is predictable: go straight to a COLLECT round over the band p 2^31 +- 4 sigma when that
+        // band holds few enough keys (expected 8 sigma_rank = 8 sqrt(n p (1 - p))); a miss falls back to KEY_HIST
+        const double exp_cand = 8.0 * sqrt((double)n * p * (1.0 - p));
+        const double blo = p * two31 - 4.0 * sig - 1.0, bhi = p * two31 + 4.0 * sig + 1.0;
+        if (SQC_MCD_DIRECT && n > 65536 && exp_cand <= SQC_MCD_DIRECT_KEYCAP && blo > 0.0 && bhi < two31) {
+          c.blo = (unsigned long long)blo; c.bhi = (unsigned long long)bhi;
+          int fs = 0;
+          while (fs < 62 && ((c.bhi - c.blo) >> fs) >= (unsigned long long)MCD_NF) ++fs;
+          c.key_shift = c.shift;                                  // kept for the fallback
+          c.shift = fs + 10; c.direct = 1; c.below = 0;
+          c.phase = PH_KEY_COLLECT;
+        }
       }
       W->cnt_below[k] = 0ull; W->cnt_nan[k] = 0ull;
     }
@@ -586,7 +602,11 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         if constexpr (MULTI) { if (ok && need_mom) xchg_sum_f64(mb.xc, k, sh_out, NM); }
         if (tr) trow[11] = gtimer();
         if (tid == 0) {
-          if (!ok && direct) {
+          if (!ok && direct && key_phase) {
+            // the +-4 sigma key band missed (about once in 10^4 cluster starts): regular KEY_HIST round over +-8 sigma
+            cl.direct = 0; cl.shift = cl.key_shift;
+            cl.phase = PH_KEY_HIST; cl.n_hist_rounds = 0;
+          } else if (!ok && direct) {
             // the predicted band missed the h-th distance (or caught too many cells): take the regular HIST round
             cl.direct = 0; cl.last_rel = 1.0;
             cl.phase = PH_DIST_HIST; cl.n_hist_rounds = 0;

@@ -143,3 +143,15 @@ def test_device_exp_matches_libm():
     assert np.all(np.abs(got - want) <= 3 * np.maximum(np.spacing(want), 4.95e-324))
     sp = api.device_expneg(np.array([-np.inf, -1e6, np.nan]))
     assert sp[0] == 0.0 and sp[1] == 0.0 and np.isnan(sp[2])
+
+
+@pytest.mark.parametrize("rng_mode", [0, 1])
+def test_robust_large_clusters(oracle, rng_mode):
+    """clusters above 65 536 cells: the predicted-band (direct COLLECT) rounds of the key start and of the settled
+    C-steps, several chunks per worker, the block-parallel key stream"""
+    from sampleqc_b200 import api
+    N, J, K = 400_000, 20, 2
+    sim, iz, _ = _case(N, J, 4, K, seed=21)
+    ref = oracle.fit_sampleqc_robust_cpp(sim.x, iz, sim.groups, 3, J, K, N, 4, 0.5, 50, 0, rng_mode=rng_mode)
+    got = api.fit_sampleqc_robust_cpp(sim.x, iz, sim.groups, 3, J, K, N, 4, 0.5, 50, 0, rng_mode=rng_mode)
+    _compare_robust(ref, got, N)
