@@ -9,7 +9,10 @@ time with the cell matrix resident in HBM; `e2e` is the same metric through the 
 (fit_sampleqc_robust_cpp -> sqc_fit_robust) with pinned HOST buffers, H2D and D2H copies inside the timed
 region.  `--impl reference` times the CPU restatement of the reference (oracle/, single-threaded like the
 reference's src/, which has no OpenMP pragma) on a bounded sample of the same workload.
-Under torchrun (N > 1) cells are sharded by sample, one rank per GPU.
+Under torchrun (N > 1) cells are sharded by sample, one rank per GPU, and the fit is ONE mixture over all ranks'
+cells (global parameters agreed through the in-kernel NVLink exchange).  Default `--scaling weak`: every GPU holds
+one workload-sized shard (N x 10 M cells x N x 1000 samples in total; per-GPU work fixed); `--scaling strong`
+splits the one workload over the GPUs instead (latency-bound at 10 M cells).
 """
 from __future__ import annotations
 
@@ -87,8 +90,10 @@ def workload(name: str, scale: float = 1.0):
         d = np.load(cache)
         return np.asfortranarray(d["x"]), d["groups"], d["init_z"], {k: int(d[k]) for k in ("D", "J", "K", "N")}
     sim, iz, _, prm = make_config(name, scale=scale)
-    try:
-        np.savez(cache, x=sim.x, groups=sim.groups, init_z=iz, **{k: prm[k] for k in ("D", "J", "K", "N")})
+    try:                                                          # ranks may race: write aside, then rename
+        tmp = f"{cache}.{os.getpid()}.npz"
+        np.savez(tmp, x=sim.x, groups=sim.groups, init_z=iz, **{k: prm[k] for k in ("D", "J", "K", "N")})
+        os.replace(tmp, cache)
     except Exception:
         pass
     return sim.x, sim.groups, iz, {k: prm[k] for k in ("D", "J", "K", "N")}
@@ -133,6 +138,8 @@ def main():
     ap.add_argument("--workload", default="C3")
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--rng", default="r_compat", choices=["r_compat", "counter"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = every GPU holds one copy-sized shard of the workload (N x the cells and samples), strong = the workload split over the GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
@@ -141,9 +148,12 @@ def main():
 
     x, groups, init_z, prm = workload(a.workload, a.scale)
     D, J, K, N = prm["D"], prm["J"], prm["K"], prm["N"]
+    weak = world > 1 and a.scaling == "weak"
+    N_job, J_job = (world * N, world * J) if weak else (N, J)      # the whole job's cells / samples
     config = {"workload": f"{a.workload}: {N} cells x {J} samples, D={D}, K={K}, robust EM (hard-assignment EM + FastMCD), "
-                          f"em_iters={EM_ITERS} mcd_alpha={MCD_ALPHA} mcd_iters={MCD_ITERS} seed={SEED}",
-              "rng_mode": a.rng, "sharding": f"by sample over {world} GPU(s)", "l2": "inputs larger than L2 (x + residual columns = %.0f MB)" % (2 * N * D * 8 / 1e6)}
+                          f"em_iters={EM_ITERS} mcd_alpha={MCD_ALPHA} mcd_iters={MCD_ITERS} seed={SEED}"
+                          + (f"; weak scaling: one such shard per GPU, the fit is ONE mixture over {N_job} cells x {J_job} samples" if weak else ""),
+              "rng_mode": a.rng, "sharding": f"by sample over {world} GPU(s)", "l2": "inputs larger than L2 (x + residual columns = %.0f MB per GPU)" % (2 * N * D * 8 / 1e6 / (1 if weak or world == 1 else world))}
 
     if a.impl == "reference":
         if rank != 0:
@@ -161,6 +171,8 @@ def main():
                           "e2e": {"value": v, "unit": "cell-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
+        os.environ["NCCL_DEBUG_FILE"] = os.environ.get("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
     import torch
     from sampleqc_b200 import api
     torch.cuda.set_device(local)
@@ -171,12 +183,19 @@ def main():
     rng_mode = api.SQC_RNG_R_COMPAT if a.rng == "r_compat" else api.SQC_RNG_COUNTER
 
     # ---- shard by sample --------------------------------------------------------------------------
-    j0, j1, i0, i1 = shard_by_sample(groups, J, world)[rank]
-    xs, gs, zs = np.asfortranarray(x[i0:i1]), (groups[i0:i1] - j0).astype(np.int32), init_z[i0:i1]
+    if weak:
+        # every rank holds the workload's recipe once: samples rank*J .. (rank+1)*J of the job.  Ranks > 0 perturb the
+        # cells slightly so that no two cells of the job are identical (same mixture, distinct data)
+        j0, j1, i0, i1 = rank * J, (rank + 1) * J, rank * N, (rank + 1) * N
+        xs = np.asfortranarray(x if rank == 0 else x + 1e-3 * np.random.default_rng(4000 + rank).standard_normal(x.shape))
+        gs, zs = groups.astype(np.int32), init_z
+    else:
+        j0, j1, i0, i1 = shard_by_sample(groups, J, world)[rank]
+        xs, gs, zs = np.asfortranarray(x[i0:i1]), (groups[i0:i1] - j0).astype(np.int32), init_z[i0:i1]
     kw = dict(variant=api.SQC_VARIANT_ROBUST, init_z=zs, mcd_alpha=MCD_ALPHA, mcd_iters=MCD_ITERS, seed=SEED, rng_mode=rng_mode, device=local)
     if world > 1:
         from sampleqc_b200 import multigpu
-        kw.update(multigpu.exchange_kwargs(dist, local, rank, world, i0, N))
+        kw.update(multigpu.exchange_kwargs(dist, local, rank, world, i0, N_job))
     sess = api.Session(xs, gs, D, j1 - j0, K, i1 - i0, EM_ITERS, **kw)
     sess.profile(True)
 
@@ -211,7 +230,7 @@ def main():
     if dist is not None:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dev_ms = float(tt.item())
-    value = N * n_iter * a.steps / (dev_ms / 1e3)
+    value = N_job * n_iter * a.steps / (dev_ms / 1e3)
 
     # ---- dominant kernel: roofline ------------------------------------------------------------------
     hbm, peak_src = peaks()
@@ -261,7 +280,7 @@ def main():
             nonlocal e2e_iters
             if world > 1:
                 from sampleqc_b200 import multigpu
-                fit = multigpu.fit_robust_sharded(dist, local, rank, world, xp, zp, gp, D, j1 - j0, K, i1 - i0, i0, N, EM_ITERS, MCD_ALPHA, MCD_ITERS, SEED, rng_mode, out=obufs)
+                fit = multigpu.fit_robust_sharded(dist, local, rank, world, xp, zp, gp, D, j1 - j0, K, i1 - i0, i0, N_job, EM_ITERS, MCD_ALPHA, MCD_ITERS, SEED, rng_mode, out=obufs)
             else:
                 fit = api.fit_sampleqc_robust_cpp(xp, zp, gp, D, J, K, N, EM_ITERS, MCD_ALPHA, MCD_ITERS, SEED, rng_mode=rng_mode, device=local, out=obufs)
             e2e_iters = fit["n_iter"]
@@ -278,7 +297,11 @@ def main():
         if dist is not None:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         d2h = sum(fit[k].nbytes for k in ("mu_0", "alpha_j", "beta_k", "sigma_k", "p_jk", "like_1", "like_2")) + (i1 - i0) * 4 + 625 * 4
-        e2e = {"value": N * e2e_iters * n_e2e / float(te.item()), "unit": "cell-iters/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+        if dist is not None:                                      # whole-job bytes: sum over the ranks
+            tb = torch.tensor([h2d, d2h], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tb)
+            h2d, d2h = int(tb[0].item()), int(tb[1].item())
+        e2e = {"value": N_job * e2e_iters * n_e2e / float(te.item()), "unit": "cell-iters/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": 1e3 * float(te.item()) / n_e2e, "steps": n_e2e, "timer": "host wall clock around the blocking C-ABI call, max over ranks"}
 
     if rank != 0:
@@ -286,7 +309,7 @@ def main():
             dist.destroy_process_group()
         return
     out = {"metric": METRIC, "value": value, "unit": "cell-iters/s", "n_gpus": world, "steps": a.steps, "warmup": n_warm,
-           "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+           "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak" if (weak or world == 1) else "strong", "vs_baseline": None, "dtype": "f64",
            "data": "synthetic", "config": config, "em_iterations_per_step": n_iter, "clocks": clocks, "e2e": e2e,
            "gpu_launches": int(launches), "roofline": roofline}
     if not a.no_cpu_baseline:

@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <stdexcept>
@@ -244,6 +245,8 @@ struct sqc_session {
   int mt_target_blocks = 49;
   unsigned long long* xg_gather = nullptr; double* xg_vec = nullptr;
   uint32_t* mt_state = nullptr; uint32_t* mt_seq = nullptr; uint32_t* mt_table = nullptr; int* keybuf = nullptr;
+  // distributed key stream (multi-GPU, R-compatible keys): this rank generates draws [rank * key_q, (rank + 1) * key_q) of every call
+  long long key_q = 0, key_mine = 0; uint32_t* mt_rows = nullptr; uint32_t* mt_jwin = nullptr; const int* key_peer[XCHG_MAX_WORLD] = {};
   double* o_buf = nullptr; int* o_z = nullptr; int* o_korder = nullptr; OutPtrs optr{};
   size_t o_doubles = 0;
   int mcd_grid = 0, n_sm = 0;
@@ -290,6 +293,7 @@ void mle_alloc(sqc_session&, const sqc_fit_args*, sqc::MleBufs&);
 void mle_run(sqc_session*);
 void mle_fetch(sqc_session*, sqc_fit_out*);
 void xchg_allreduce_host(sqc_session* S, double* buf, int n);
+void key_stream_setup(sqc_session* S);
 void xchg_cluster_layout(sqc_session* S, Dev& s);
 void xchg_allreduce_like(sqc_session* S, Dev& s);
 void xchg_allreduce_mle(sqc_session* S, Dev& s, MleBufs& m, int ll_only, double* like, int slot);
@@ -630,7 +634,9 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
     mb.trace_leader = getenv("SQC_MCD_TRACE") ? atoi(getenv("SQC_MCD_TRACE")) : 0;
     mb.trace = getenv("SQC_MCD_TRACE") ? S->alloc<long long>(16 * 512) : nullptr;
     if (S->rng_mode == SQC_RNG_R_COMPAT) {
-      S->mt_state = S->alloc<uint32_t>(640 * 5); S->keybuf = S->alloc<int>(2 * (size_t)S->N_total, false);
+      S->mt_state = S->alloc<uint32_t>(640 * 7);
+      if (S->world > 1 && S->N_total >= 624LL * 8 * S->world && !getenv("SQC_KEYS_REPLICATED")) key_stream_setup(S);
+      else S->keybuf = S->alloc<int>(2 * (size_t)S->N_total, false);
       if (getenv("SQC_RNG_INLINE") && atoi(getenv("SQC_RNG_INLINE"))) S->st_rng = S->st;      // debug: no side stream
       else CK(cudaStreamCreateWithFlags(&S->st_rng, cudaStreamNonBlocking));
       if (getenv("SQC_MT_BLOCKS")) S->mt_target_blocks = std::max(1, atoi(getenv("SQC_MT_BLOCKS")));
@@ -654,6 +660,68 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
   pt.mark("init_passes");
   pt.dump("create");
   return up.release();
+}
+
+// ---- distributed key stream (multi-GPU, SQC_RNG_R_COMPAT) --------------------------------------------------------
+// R's stream is one sequence, so a call's N_total keys cost every rank O(N_total) when each generates them all.
+// Instead rank r generates draws [r Q, (r + 1) Q) of every call into a buffer the peers map (cudaIpc), and the M-step
+// kernel reads a cell's key from its owner over NVLink (4 B per cell in the one or two key rounds of a call).  The
+// buffers' IPC handles travel through the exchange window itself, so the C ABI is unchanged.
+struct KeyBufLocal { int* p = nullptr; size_t ints = 0; };
+KeyBufLocal& key_buf_local(int device) { static KeyBufLocal b[64]; return b[device & 63]; }
+struct HandleKey { unsigned char b[64]; bool operator<(const HandleKey& o) const { return memcmp(b, o.b, 64) < 0; } };
+std::map<HandleKey, void*>& key_peer_maps(int device) { static std::map<HandleKey, void*> m[64]; return m[device & 63]; }
+
+void key_stream_setup(sqc_session* S) {
+  const int W = S->world, r = S->rank;
+  if (!mtpoly::self_check()) fail(SQC_ERR_COMM, "distributed key stream: jump polynomial derivation failed its self-check");
+  const long long per = (S->N_total + W - 1) / W;
+  S->key_q = ((per + MT_N - 1) / MT_N) * MT_N;
+  S->key_mine = std::max<long long>(0, std::min<long long>(S->key_q, S->N_total - (long long)r * S->key_q));
+  // own buffer (two calls in flight), kept per device for the life of the process: its IPC handle stays valid
+  KeyBufLocal& kb = key_buf_local(S->device);
+  if (kb.ints < 2 * (size_t)S->key_q) {
+    if (kb.p) { CK(cudaDeviceSynchronize()); cudaFree(kb.p); kb.p = nullptr; kb.ints = 0; }
+    CK(cudaMalloc((void**)&kb.p, 2 * (size_t)S->key_q * sizeof(int)));
+    kb.ints = 2 * (size_t)S->key_q;
+  }
+  S->keybuf = kb.p;
+  cudaIpcMemHandle_t h;
+  if (cudaIpcGetMemHandle(&h, kb.p) != cudaSuccess) fail(SQC_ERR_COMM, "cudaIpcGetMemHandle (key buffer) failed");
+  // all-gather of the 64-byte handles through the window
+  unsigned long long* d_in = S->alloc<unsigned long long>(8); unsigned long long* d_out = S->alloc<unsigned long long>(8 * XCHG_MAX_WORLD);
+  CK(cudaMemcpyAsync(d_in, &h, 64, cudaMemcpyHostToDevice, S->st));
+  k_xchg_gather_u64<<<1, 256, 0, S->st>>>(S->xc.dev, XCHG_CH_HOST + 0, d_in, d_out, 8, nullptr);
+  std::vector<unsigned char> hs((size_t)64 * W);
+  CK(cudaMemcpyAsync(hs.data(), d_out, hs.size(), cudaMemcpyDeviceToHost, S->st));
+  CK(cudaStreamSynchronize(S->st));
+  auto& maps = key_peer_maps(S->device);
+  for (int q = 0; q < W; ++q) {
+    if (q == r) { S->key_peer[q] = kb.p; continue; }
+    HandleKey hk; memcpy(hk.b, hs.data() + (size_t)64 * q, 64);
+    auto it = maps.find(hk);
+    if (it == maps.end()) {
+      cudaIpcMemHandle_t ph; memcpy(&ph, hk.b, 64);
+      void* p = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&p, ph, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) fail(SQC_ERR_COMM, "cudaIpcOpenMemHandle (key buffer of rank %d) failed: %s", q, cudaGetErrorString(e));
+      it = maps.emplace(hk, p).first;
+    }
+    S->key_peer[q] = (const int*)it->second;
+  }
+  // jump polynomials: row 0 = call to call (floor(N_total / 624) chunks), row 1 = start of the call to this rank's share
+  static std::map<unsigned long long, std::vector<uint32_t>> rows;      // derived once per distance
+  auto row = [&](unsigned long long words) -> const std::vector<uint32_t>& {
+    auto it = rows.find(words);
+    if (it == rows.end()) { std::vector<uint32_t> v(MT_N); mtpoly::xpow(words - 1ull, v.data()); it = rows.emplace(words, std::move(v)).first; }
+    return it->second;
+  };
+  S->mt_rows = S->alloc<uint32_t>(2 * MT_N); S->mt_jwin = S->alloc<uint32_t>(2 * MT_N);
+  CK(cudaMemcpyAsync(S->mt_rows, row((unsigned long long)(S->N_total / MT_N) * MT_N).data(), MT_N * sizeof(uint32_t), cudaMemcpyHostToDevice, S->st));
+  if (r > 0 && S->key_mine > 0)
+    CK(cudaMemcpyAsync(S->mt_rows + MT_N, row((unsigned long long)r * (unsigned long long)S->key_q).data(), MT_N * sizeof(uint32_t), cudaMemcpyHostToDevice, S->st));
+  CK(cudaStreamSynchronize(S->st));                                      // the rows live in a static map, but keep the copies simple
+  CK(cudaFuncSetAttribute(k_mt_jump_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_SMEM));
 }
 
 // n keys of R's stream: reads the state st_in (625 words), leaves the state after the n draws in st_out.
@@ -705,6 +773,18 @@ void enqueue_keys(sqc_session* S, int call, cudaEvent_t after) {
   CK(cudaStreamWaitEvent(S->st_rng, S->ev_key_free[kb], 0));
   if (after) CK(cudaStreamWaitEvent(S->st_rng, after, 0));
   uint32_t* base = S->mt_state;
+  if (S->key_q) {
+    // state in front of the call -> (state after the call, state in front of this rank's share) by jump polynomials,
+    // then only this rank's share of the keys
+    const uint32_t* in = base + 640 * ((call + 2) % 3);
+    const bool has_rank = S->rank > 0 && S->key_mine > 0;
+    { Launch L(S, SQC_KF_RNG); k_mt_seq<<<1, 256, 0, S->st_rng>>>(in, S->mt_seq, S->dev.ctl); L.done(); }
+    { Launch L(S, SQC_KF_RNG); k_mt_jump_rows<<<has_rank ? 2 : 1, MT_JUMP_THREADS, MT_SMEM, S->st_rng>>>(S->mt_seq, S->mt_rows, S->mt_jwin, S->dev.ctl); L.done(); }
+    { Launch L(S, SQC_KF_RNG); k_mt_fix<<<1, 256, 0, S->st_rng>>>(in, S->mt_jwin, base + 640 * (call % 3), base + 640 * 5, S->N_total, has_rank ? 1 : 0, S->dev.ctl); L.done(); }
+    if (S->key_mine > 0)
+      mt_generate(S->st_rng, base + 640 * 5, base + 640 * 6, base + 640 * 3, base + 640 * 4, S->mt_seq, S->mt_table,
+                  S->keybuf + (size_t)kb * S->key_q, S->key_mine, S->dev.ctl, S, S->mt_target_blocks);
+  } else
   mt_generate(S->st_rng, base + 640 * ((call + 2) % 3), base + 640 * (call % 3), base + 640 * 3, base + 640 * 4, S->mt_seq, S->mt_table,
               S->keybuf + (size_t)kb * S->N_total, S->N_total, S->dev.ctl, S, S->mt_target_blocks);
   CK(cudaEventRecord(S->ev_key_ready[kb], S->st_rng));
@@ -714,6 +794,15 @@ void use_keys(sqc_session* S, int call) {
     // the keys of the NEXT call are generated while this call's M-step kernel runs
     if (call + 1 <= S->em_iters) { CK(cudaEventRecord(S->ev_pre_mcd, S->st)); enqueue_keys(S, call + 1, S->ev_pre_mcd); }
     CK(cudaStreamWaitEvent(S->st, S->ev_key_ready[call & 1], 0));
+    if (S->key_q) {
+      // every rank's share of this call must be complete before any rank's M-step kernel reads it: one tiny exchange
+      // behind the wait orders them (the peers' reads end before this kernel's last exchange of the call, so the
+      // buffer may be refilled once the kernel is done - the same event that frees it locally)
+      { Launch L(S, SQC_KF_UPDATE); k_xchg_sum_f64<<<1, 32, 0, S->st>>>(S->xc.dev, XCHG_CH_HOST + 0, S->xg_vec + 8, 1, &S->dev.ctl->cont); L.done(); }
+      S->mb.keys = S->keybuf + (size_t)(call & 1) * S->key_q;
+      for (int q = 0; q < S->world; ++q) S->mb.key_peer[q] = S->key_peer[q] + (size_t)(call & 1) * S->key_q;
+      S->mb.key_q = S->key_q; S->mb.key_qinv = 1.0 / (double)S->key_q;
+    } else
     S->mb.keys = S->keybuf + (size_t)(call & 1) * S->N_total;
   } else S->mb.keys = nullptr;
   S->mb.call_mix = counter_call_mix(S->seed, 0u);

@@ -93,6 +93,9 @@ struct McdBufs {
   unsigned int* cand_cnt;              // K x regions
   unsigned int* fhist;                 // K x (MCD_NF + 4): fine histogram of the candidates, built by the workers
   const int* keys;                     // R-compatible key stream of this call (N_total ints), or null
+  const int* key_peer[XCHG_MAX_WORLD]; // distributed key stream (multi-GPU): rank r's share of this call's keys (peer memory)
+  long long key_q;                     // draws per rank of the distributed stream (0: `keys` holds the whole call)
+  double key_qinv;
   unsigned long long call_mix;         // counter-mode key mix for this call
   long long stream_base;               // call * N_total: index of this call's first draw
   unsigned int* epoch;                 // K: state version of every cluster (0 at launch; the leader publishes 1, 2, ...)
@@ -518,35 +521,65 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         __syncthreads();
         if (tr) trow[9] = gtimer();
         int ntie = min(sh_flag[4], MCD_TINY);
-        // 3. tie list over all ranks: all-gather, then sort by (key, rank, position)
-        if (MULTI && ok) {
-          // pack own list behind the fine histogram: [count, (key lo, key hi, pos) ...]
-          unsigned int* pk = sh_hist;
-          __syncthreads();
-          if (tid == 0) pk[0] = (unsigned)ntie;
-          for (int i = tid; i < ntie; i += MCD_THREADS) { pk[1 + 3 * i] = (unsigned)sh_tkey[i]; pk[2 + 3 * i] = (unsigned)(sh_tkey[i] >> 32); pk[3 + 3 * i] = sh_tpos[i]; }
-          __syncthreads();
-          const unsigned long long seq = xchg_publish(mb.xc, k, pk, 1 + 3 * ntie);
-          // own entries stay in place (with their references); append the peers'
-          if (tid == 0) {
-            int t = ntie;
-            for (int r = 0; r < world; ++r) {
-              if (r == myrank) continue;
-              const unsigned int* ps = xchg_peer_slot(mb.xc, k, seq, r);
-              const int cnt = (int)ld_relaxed_sys_u32(ps);
-              for (int i = 0; i < cnt && t < MCD_TINY; ++i, ++t) {
-                sh_tkey[t] = (unsigned long long)ld_relaxed_sys_u32(ps + 1 + 3 * i) | ((unsigned long long)ld_relaxed_sys_u32(ps + 2 + 3 * i) << 32);
-                sh_tpos[t] = ld_relaxed_sys_u32(ps + 3 + 3 * i); sh_tref[t] = 0xffffffffu; sh_trank[t] = (unsigned)r;
+        // 3. (multi-GPU) ONE exchange per COLLECT post: every rank pushes its moments without the tie members and its
+        //    tie list (key, position, residual) to all ranks; each rank then ranks the union and adds the members in
+        //    canonical (key, rank, position) order behind the rank-ordered sum of the moments — identical everywhere.
+        //    Message lines: [0] = number of ties, [1 .. NM] = moments, then (2 + D) lines per tie.
+        [[maybe_unused]] double msum = 0.0;
+        [[maybe_unused]] unsigned long long xseq = 0ull;
+        constexpr int TIE0 = 1 + NM, TIEL = 2 + D;
+        if constexpr (MULTI) {
+          if (ok) {
+            if (need_mom) {
+#pragma unroll
+              for (int q = 0; q < (NM + MCD_WARPS - 1) / MCD_WARPS; ++q) {
+                const double a = warp_sum(part_pre[q]);
+#pragma unroll
+                for (int m = 0; m < NM; ++m) if (m == wid + q * MCD_WARPS && lane == 0) tot[m] += a;
               }
             }
-            sh_flag[4] = t;
+            block_reduce_vec<NM>(tot, sh_red, sh_out);
+            xseq = xchg_begin(mb.xc, k);
+            if (tid == 0) xchg_put(mb.xc, k, xseq, 0, (unsigned)ntie, 0u);
+            if (tid < NM) xchg_put_f64(mb.xc, k, xseq, 1 + tid, sh_out[tid]);
+            for (int i = tid; i < ntie; i += MCD_THREADS) {
+              const long long cb = (long long)k * regions * MCD_CAPW + (long long)sh_tref[i];
+              const int l0 = TIE0 + i * TIEL;
+              xchg_put(mb.xc, k, xseq, l0, (unsigned)sh_tkey[i], (unsigned)(sh_tkey[i] >> 32));
+              xchg_put(mb.xc, k, xseq, l0 + 1, sh_tpos[i], 0u);
+#pragma unroll
+              for (int d = 0; d < D; ++d)
+                xchg_put_f64(mb.xc, k, xseq, l0 + 2 + d, (i < MCD_TCACHE) ? sh_tr[i * D + d] : __longlong_as_double((long long)mb.cand_rec[cb * (2 + D) + 2 + d]));
+            }
+            ulonglong2 hd[XCHG_MAX_WORLD];
+            xchg_wait_all(mb.xc, k, xseq, 0, hd);
+            if (tid < NM) {
+              ulonglong2 mv[XCHG_MAX_WORLD];
+              xchg_wait_all(mb.xc, k, xseq, 1 + tid, mv);
+#pragma unroll
+              for (int r = 0; r < XCHG_MAX_WORLD; ++r) if (r < world) msum += line_f64(mv[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < XCHG_MAX_WORLD; ++r) {
+              if (r >= world || r == myrank) continue;
+              const int cnt = min((int)(unsigned)hd[r].x, MCD_TINY);
+              for (int i = tid; i < cnt; i += MCD_THREADS) {
+                const ulonglong2 e0 = xchg_wait(mb.xc, k, xseq, r, TIE0 + i * TIEL), e1 = xchg_wait(mb.xc, k, xseq, r, TIE0 + i * TIEL + 1);
+                const int t = atomicAdd(&sh_flag[4], 1);
+                if (t < MCD_TINY) {
+                  sh_tkey[t] = (unsigned long long)(unsigned)e0.x | ((unsigned long long)(unsigned)e0.y << 32);
+                  sh_tpos[t] = (unsigned)e1.x; sh_tref[t] = (unsigned)i; sh_trank[t] = (unsigned)r;
+                }
+              }
+            }
+            __syncthreads();
+            ntie = min(sh_flag[4], MCD_TINY);
           }
-          __syncthreads();
-          ntie = min(sh_flag[4], MCD_TINY);
         }
         // tiny selection by rank counting: entry i is a member iff fewer than take2 entries precede it in (key, rank, pos) order
         const long long take2 = take - fbelow;
         unsigned long long thr = 0ull;
+        [[maybe_unused]] double ttot[MULTI ? NM : 1];
         if (ok) {
           for (int i = tid; i < ntie; i += MCD_THREADS) {
             const unsigned long long ki = sh_tkey[i]; const unsigned ri = sh_trank[i], pi = sh_tpos[i];
@@ -562,44 +595,68 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
           __syncthreads();
           thr = sh_u64[2];
           if (need_mom && tid == 0) {
-            // own tie members, in ascending list order of a canonical sort: accumulate in (key, pos) order
+            // tie members in ascending (key, rank, position) order, so that the summation order is deterministic
+            // (single GPU: all entries are this rank's; multi-GPU: the peers' residuals are read from the message)
             double cs[D];
 #pragma unroll
             for (int d = 0; d < D; ++d) cs[d] = cl.cshift[d];
-            // selection-sort walk over the (few) own members so that the summation order is deterministic
-            unsigned long long lastk = 0ull; unsigned lastp = 0u; bool first = true;
+            if constexpr (MULTI) {
+#pragma unroll
+              for (int m = 0; m < NM; ++m) ttot[m] = 0.0;
+            }
+            unsigned long long lastk = 0ull; unsigned lastp = 0u, lastr = 0u; bool first = true;
             for (;;) {
               int best = -1;
               for (int i = 0; i < ntie; ++i) {
-                if (sh_trank[i] != (unsigned)myrank || !(sh_tref[i] & 0x80000000u) || (sh_tref[i] & 0x7fffffffu) == 0x7fffffffu) continue;
-                const bool after = first || sh_tkey[i] > lastk || (sh_tkey[i] == lastk && sh_tpos[i] > lastp);
+                if (!(sh_tref[i] & 0x80000000u)) continue;
+                const bool after = first || sh_tkey[i] > lastk || (sh_tkey[i] == lastk && (sh_trank[i] > lastr || (sh_trank[i] == lastr && sh_tpos[i] > lastp)));
                 if (!after) continue;
-                if (best < 0 || sh_tkey[i] < sh_tkey[best] || (sh_tkey[i] == sh_tkey[best] && sh_tpos[i] < sh_tpos[best])) best = i;
+                if (best < 0 || sh_tkey[i] < sh_tkey[best] ||
+                    (sh_tkey[i] == sh_tkey[best] && (sh_trank[i] < sh_trank[best] || (sh_trank[i] == sh_trank[best] && sh_tpos[i] < sh_tpos[best])))) best = i;
               }
               if (best < 0) break;
-              const long long cb = (long long)k * regions * MCD_CAPW + (long long)(sh_tref[best] & 0x7fffffffu);
+              const unsigned ref = sh_tref[best] & 0x7fffffffu;
               double r[D];
+              if (!MULTI || sh_trank[best] == (unsigned)myrank) {
+                const long long cb = (long long)k * regions * MCD_CAPW + (long long)ref;
 #pragma unroll
-              for (int d = 0; d < D; ++d) r[d] = (best < MCD_TCACHE) ? sh_tr[best * D + d] : __longlong_as_double((long long)mb.cand_rec[cb * (2 + D) + 2 + d]);
-              Mom<D>::add(tot, r, cs, true);
-              lastk = sh_tkey[best]; lastp = sh_tpos[best]; first = false;
+                for (int d = 0; d < D; ++d) r[d] = (best < MCD_TCACHE) ? sh_tr[best * D + d] : __longlong_as_double((long long)mb.cand_rec[cb * (2 + D) + 2 + d]);
+              } else {
+                if constexpr (MULTI) {
+#pragma unroll
+                  for (int d = 0; d < D; ++d) r[d] = line_f64(xchg_wait(mb.xc, k, xseq, (int)sh_trank[best], TIE0 + (int)ref * TIEL + 2 + d));
+                }
+              }
+              if constexpr (MULTI) Mom<D>::add(ttot, r, cs, true); else Mom<D>::add(tot, r, cs, true);
+              lastk = sh_tkey[best]; lastp = sh_tpos[best]; lastr = sh_trank[best]; first = false;
             }
           }
         }
         if (tr) trow[7] = gtimer();
-        // 4. per-CTA partials (loaded at the start), fixed order: lane-strided over CTAs, then the warp tree
-        if (ok && need_mom) {
+        if constexpr (MULTI) {
+          // moments = rank-ordered sum of the ranks' moments + the tie members (thread 0 is also the reader below)
+          __syncthreads();
+          if (ok && tid < NM) sh_out[tid] = msum;
+          __syncthreads();
+          if (ok && need_mom && tid == 0) {
 #pragma unroll
-          for (int q = 0; q < (NM + MCD_WARPS - 1) / MCD_WARPS; ++q) {
-            const double a = warp_sum(part_pre[q]);
-#pragma unroll
-            for (int m = 0; m < NM; ++m) if (m == wid + q * MCD_WARPS && lane == 0) tot[m] += a;
+            for (int m = 0; m < NM; ++m) sh_out[m] += ttot[m];
           }
+          if (tr) trow[10] = gtimer();
+        } else {
+          // 4. per-CTA partials (loaded at the start), fixed order: lane-strided over CTAs, then the warp tree
+          if (ok && need_mom) {
+#pragma unroll
+            for (int q = 0; q < (NM + MCD_WARPS - 1) / MCD_WARPS; ++q) {
+              const double a = warp_sum(part_pre[q]);
+#pragma unroll
+              for (int m = 0; m < NM; ++m) if (m == wid + q * MCD_WARPS && lane == 0) tot[m] += a;
+            }
+          }
+          __syncthreads();
+          if (tr) trow[10] = gtimer();
+          block_reduce_vec<NM>(tot, sh_red, sh_out);
         }
-        __syncthreads();
-        if (tr) trow[10] = gtimer();
-        block_reduce_vec<NM>(tot, sh_red, sh_out);
-        if constexpr (MULTI) { if (ok && need_mom) xchg_sum_f64(mb.xc, k, sh_out, NM); }
         if (tr) trow[11] = gtimer();
         if (tid == 0) {
           if (!ok && direct && key_phase) {
@@ -788,7 +845,21 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
           }
         }
         if (key_round) {
-          if (mb.keys) {
+          if (MULTI && mb.keys && mb.key_q) {
+            // the call's stream is generated once per box: draw `pos` lives on rank pos / Q (NVLink read)
+#pragma unroll
+            for (int it = 0; it < CPT; ++it) {
+              int key = 0;
+              if (valid[it]) {
+                const long long pos = kbase + epos[it];
+                int own = (int)((double)pos * mb.key_qinv);
+                long long off = pos - (long long)own * mb.key_q;
+                if (off < 0) { --own; off += mb.key_q; } else if (off >= mb.key_q) { ++own; off -= mb.key_q; }
+                key = ld_stream_s32(mb.key_peer[own] + off);
+              }
+              bits[it] = (unsigned long long)(unsigned int)key;
+            }
+          } else if (mb.keys) {
 #pragma unroll
             for (int it = 0; it < CPT; ++it) {
               int key = 0;

@@ -3,14 +3,18 @@
 // Cells are sharded by sample: alpha_j, p_jk and the labels never leave their GPU; what
 // the ranks must agree on are a few small vectors per step (histograms of the exact selection, candidate
 // lists, K x (1 + D + D^2) moments, log-likelihood sums).  Those are exchanged INSIDE the kernels that
-// produce them: every rank owns a window in its HBM (cudaMalloc, exported with cudaIpcGetMemHandle and mapped
-// by all peers), publishes its vector there and a monotonically increasing sequence number behind it
-// (st.release.sys), then reads every peer's copy over NVLink (ld.acquire.sys on the flag, ld.relaxed.sys on
-// the data) and combines the copies in RANK ORDER — so all ranks hold bit-identical results and take
-// identical control-flow decisions without any host round trip or NCCL launch.  Messages are <= 32 KB:
-// what matters is latency, not the 900 GB/s links.  Slots are double-buffered by sequence parity: a rank can
-// publish exchange q + 1 only after it has read everybody's q, so a slot is never overwritten while a peer
-// may still read it.
+// produce them.  Every rank owns a window in its HBM (cudaMalloc, exported with cudaIpcGetMemHandle and mapped
+// by all peers).  Messages are <= 80 KB, so what matters is latency, not the 900 GB/s links; the protocol is
+// therefore a PUSH of self-validating lines:
+//   * a line is 16 bytes = two 64-bit words, each {32 data bits, 32-bit sequence number of the exchange};
+//   * the sender stores its lines straight into every peer's window (st.relaxed.sys.v2.u64, fire and forget,
+//     one NVLink crossing, no fence and no separate flag);
+//   * the receiver polls its OWN memory until both halves of a line carry the expected sequence number, so a
+//     line is complete the moment it is seen, whatever the order the stores arrive in.
+// All ranks combine the copies in RANK ORDER, so they hold bit-identical results and take identical
+// control-flow decisions without any host round trip or NCCL launch.  Lines live in (channel, sequence parity,
+// source rank) slots: a rank sends exchange q + 2 only after it has received everybody's q + 1, which they sent
+// after consuming q — so a slot is never overwritten while its owner may still read it.
 #pragma once
 #include <cstdint>
 #include <cstring>
@@ -24,8 +28,8 @@ namespace sqc {
 constexpr int XCHG_MAX_WORLD = 8;
 constexpr int XCHG_CHANNELS = SQC_MAXK + 4;          // one per cluster leader + host-stream level channels
 constexpr int XCHG_CH_HOST = SQC_MAXK;               // first host-stream channel
-constexpr int XCHG_SLOT_BYTES = 32 * 1024;
-constexpr size_t XCHG_WINDOW_BYTES = 4096 + (size_t)XCHG_CHANNELS * 2 * XCHG_SLOT_BYTES;
+constexpr int XCHG_LINE_CAP = 5632;                  // lines per slot: >= 1 + 45 + 512 * (2 + 8) (tie message of k_mcd at D = 8)
+constexpr size_t XCHG_WINDOW_BYTES = (size_t)XCHG_CHANNELS * 2 * XCHG_MAX_WORLD * XCHG_LINE_CAP * 16;
 
 struct XchgDev {
   int world, rank;
@@ -33,81 +37,78 @@ struct XchgDev {
   unsigned long long* next_seq;                      // XCHG_CHANNELS counters in LOCAL memory (same value on all ranks)
 };
 
-__device__ __forceinline__ unsigned long long* xw_flag(unsigned char* base, int ch) { return (unsigned long long*)base + ch; }
-__device__ __forceinline__ unsigned char* xw_slot(unsigned char* base, int ch, unsigned long long seq) {
-  return base + 4096 + ((size_t)ch * 2 + (size_t)(seq & 1ull)) * XCHG_SLOT_BYTES;
+// slot of `src`'s message of exchange `seq` on channel `ch`, inside the window at `base`
+__device__ __forceinline__ ulonglong2* xw_line(unsigned char* base, int ch, unsigned long long seq, int src) {
+  return (ulonglong2*)base + (((size_t)ch * 2 + (size_t)(seq & 1ull)) * XCHG_MAX_WORLD + (size_t)src) * XCHG_LINE_CAP;
 }
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
-  unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
+__device__ __forceinline__ void st_line(ulonglong2* p, unsigned int w0, unsigned int w1, unsigned int f) {
+  const unsigned long long a = (unsigned long long)w0 | ((unsigned long long)f << 32), b = (unsigned long long)w1 | ((unsigned long long)f << 32);
+  asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
 }
-__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ ulonglong2 ld_line(const ulonglong2* p) {
+  ulonglong2 v; asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory"); return v;
 }
-__device__ __forceinline__ unsigned int ld_relaxed_sys_u32(const unsigned int* p) {
-  unsigned int v; asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
-  unsigned long long v; asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v;
-}
+__device__ __forceinline__ bool line_ready(const ulonglong2& v, unsigned int f) { return (unsigned int)(v.x >> 32) == f && (unsigned int)(v.y >> 32) == f; }
+__device__ __forceinline__ double line_f64(const ulonglong2& v) { return __hiloint2double((int)(unsigned int)v.y, (int)(unsigned int)v.x); }
 
-// Block-wide: publish n_words 32-bit words from `src` (shared or global) on channel ch, wait for every rank.
-// Returns the sequence number; afterwards xchg_peer_slot(x, ch, seq, r) is readable for every rank r.
-__device__ inline unsigned long long xchg_publish(const XchgDev& x, int ch, const unsigned int* src, int n_words) {
+// Block-wide: number of the next exchange on channel ch (identical on every rank: all ranks run the same exchanges)
+__device__ inline unsigned long long xchg_begin(const XchgDev& x, int ch) {
   __shared__ unsigned long long sh_seq;
   if (threadIdx.x == 0) sh_seq = ++x.next_seq[ch];
   __syncthreads();
-  const unsigned long long seq = sh_seq;
-  unsigned int* dst = (unsigned int*)xw_slot(x.peer[x.rank], ch, seq);
-  for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = src[i];
-  __syncthreads();                                   // the block's stores happen-before thread 0's release (cumulativity)
-  if (threadIdx.x == 0) { __threadfence_system(); st_release_sys_u64(xw_flag(x.peer[x.rank], ch), seq); }
-  if ((int)threadIdx.x < x.world) {
-    const unsigned long long* f = xw_flag(x.peer[threadIdx.x], ch);
-    while (ld_acquire_sys_u64(f) < seq) { }
-  }
-  __syncthreads();
-  return seq;
+  return sh_seq;
 }
-__device__ __forceinline__ const unsigned int* xchg_peer_slot(const XchgDev& x, int ch, unsigned long long seq, int r) {
-  return (const unsigned int*)xw_slot(x.peer[r], ch, seq);
+// one line to every rank (own window included: the receive path is the same for all sources)
+__device__ __forceinline__ void xchg_put(const XchgDev& x, int ch, unsigned long long seq, int line, unsigned int w0, unsigned int w1) {
+#pragma unroll
+  for (int r = 0; r < XCHG_MAX_WORLD; ++r) if (r < x.world) st_line(xw_line(x.peer[r], ch, seq, x.rank) + line, w0, w1, (unsigned int)seq);
 }
-__device__ __forceinline__ uint4 ld_relaxed_sys_v4(const unsigned int* p) {      // 16-byte aligned; not volatile: loads may overlap
-  uint4 v; asm("ld.relaxed.sys.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+__device__ __forceinline__ void xchg_put_f64(const XchgDev& x, int ch, unsigned long long seq, int line, double v) {
+  xchg_put(x, ch, seq, line, (unsigned int)__double2loint(v), (unsigned int)__double2hiint(v));
+}
+// wait for line `line` of rank r's message (local polling; a peer that never sends traps the kernel after ~20 s)
+__device__ __forceinline__ ulonglong2 xchg_wait(const XchgDev& x, int ch, unsigned long long seq, int r, int line) {
+  const ulonglong2* p = xw_line(x.peer[x.rank], ch, seq, r) + line;
+  ulonglong2 v = ld_line(p);
+  unsigned int spins = 0;
+  while (!line_ready(v, (unsigned int)seq)) { if (++spins > (1u << 25)) __trap(); v = ld_line(p); }
   return v;
 }
-// sum of 32-bit counters over ranks, in place (block-wide).  n is rounded up to a multiple of 4 words (the slots
-// are 16-byte aligned and larger than any message); every thread issues all its remote 128-bit loads before it
-// uses any of them, so one exchange costs about one NVLink round trip.
-__device__ inline void xchg_sum_u32(const XchgDev& x, int ch, unsigned int* buf, int n) {
-  const unsigned long long seq = xchg_publish(x, ch, buf, n);
-  const int n4 = (n + 3) >> 2;
-  for (int i = threadIdx.x; i < n4; i += blockDim.x) {
-    uint4 v[XCHG_MAX_WORLD];
+// the same line of every rank: all loads are issued before the first is examined
+__device__ __forceinline__ void xchg_wait_all(const XchgDev& x, int ch, unsigned long long seq, int line, ulonglong2 (&v)[XCHG_MAX_WORLD]) {
 #pragma unroll
-    for (int r = 0; r < XCHG_MAX_WORLD; ++r) if (r < x.world) v[r] = ld_relaxed_sys_v4(xchg_peer_slot(x, ch, seq, r) + 4 * i);
-    uint4 a = make_uint4(0u, 0u, 0u, 0u);
+  for (int r = 0; r < XCHG_MAX_WORLD; ++r) if (r < x.world) v[r] = ld_line(xw_line(x.peer[x.rank], ch, seq, r) + line);
 #pragma unroll
-    for (int r = 0; r < XCHG_MAX_WORLD; ++r) if (r < x.world) { a.x += v[r].x; a.y += v[r].y; a.z += v[r].z; a.w += v[r].w; }
-    if (4 * i + 0 < n) buf[4 * i + 0] = a.x;
-    if (4 * i + 1 < n) buf[4 * i + 1] = a.y;
-    if (4 * i + 2 < n) buf[4 * i + 2] = a.z;
-    if (4 * i + 3 < n) buf[4 * i + 3] = a.w;
+  for (int r = 0; r < XCHG_MAX_WORLD; ++r) if (r < x.world && !line_ready(v[r], (unsigned int)seq)) v[r] = xchg_wait(x, ch, seq, r, line);
+}
+
+// sum of 32-bit counters over ranks, in place (block-wide).  A thread sends and later overwrites the same words.
+__device__ __noinline__ void xchg_sum_u32(const XchgDev& x, int ch, unsigned int* buf, int n) {
+  const unsigned long long seq = xchg_begin(x, ch);
+  const int nl = (n + 1) >> 1;
+  for (int i = threadIdx.x; i < nl; i += blockDim.x) xchg_put(x, ch, seq, i, buf[2 * i], (2 * i + 1 < n) ? buf[2 * i + 1] : 0u);
+  for (int i = threadIdx.x; i < nl; i += blockDim.x) {
+    ulonglong2 v[XCHG_MAX_WORLD];
+    xchg_wait_all(x, ch, seq, i, v);
+    unsigned int a0 = 0u, a1 = 0u;
+#pragma unroll
+    for (int r = 0; r < XCHG_MAX_WORLD; ++r) if (r < x.world) { a0 += (unsigned int)v[r].x; a1 += (unsigned int)v[r].y; }
+    buf[2 * i] = a0;
+    if (2 * i + 1 < n) buf[2 * i + 1] = a1;
   }
   __syncthreads();
 }
-// sum of doubles over ranks in rank order (bit-identical on every rank), in place (block-wide)
-__device__ inline void xchg_sum_f64(const XchgDev& x, int ch, double* buf, int n) {
-  const unsigned long long seq = xchg_publish(x, ch, (const unsigned int*)buf, 2 * n);
-  const int n2 = (n + 1) >> 1;
-  for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-    uint4 v[XCHG_MAX_WORLD];
+// sum of doubles over ranks in rank order (bit-identical on every rank), in place (block-wide); one double per line
+__device__ __noinline__ void xchg_sum_f64(const XchgDev& x, int ch, double* buf, int n) {
+  const unsigned long long seq = xchg_begin(x, ch);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) xchg_put_f64(x, ch, seq, i, buf[i]);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    ulonglong2 v[XCHG_MAX_WORLD];
+    xchg_wait_all(x, ch, seq, i, v);
+    double a = 0.0;
 #pragma unroll
-    for (int r = 0; r < XCHG_MAX_WORLD; ++r) if (r < x.world) v[r] = ld_relaxed_sys_v4(xchg_peer_slot(x, ch, seq, r) + 4 * i);
-    double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-    for (int r = 0; r < XCHG_MAX_WORLD; ++r) if (r < x.world) { a0 += __hiloint2double((int)v[r].y, (int)v[r].x); a1 += __hiloint2double((int)v[r].w, (int)v[r].z); }
-    buf[2 * i] = a0;
-    if (2 * i + 1 < n) buf[2 * i + 1] = a1;
+    for (int r = 0; r < XCHG_MAX_WORLD; ++r) if (r < x.world) a += line_f64(v[r]);
+    buf[i] = a;
   }
   __syncthreads();
 }
@@ -120,10 +121,12 @@ __global__ void k_xchg_sum_f64(XchgDev x, int ch, double* buf, int n, const int*
 // all-gather of n 64-bit words per rank: out[r * n + i]
 __global__ void k_xchg_gather_u64(XchgDev x, int ch, const unsigned long long* in, unsigned long long* out, int n, const int* cont) {
   if (cont && !*cont) return;
-  const unsigned long long seq = xchg_publish(x, ch, (const unsigned int*)in, 2 * n);
+  const unsigned long long seq = xchg_begin(x, ch);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) xchg_put(x, ch, seq, i, (unsigned int)in[i], (unsigned int)(in[i] >> 32));
   for (int i = threadIdx.x; i < n * x.world; i += blockDim.x) {
     const int r = i / n, e = i % n;
-    out[i] = ld_relaxed_sys_u64((const unsigned long long*)xchg_peer_slot(x, ch, seq, r) + e);
+    const ulonglong2 v = xchg_wait(x, ch, seq, r, e);
+    out[i] = (unsigned long long)(unsigned int)v.x | ((unsigned long long)(unsigned int)v.y << 32);
   }
 }
 

@@ -9,7 +9,7 @@ rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = i
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
-for (N, J, Kt, K, D, em, rng) in [(40000, 12, 4, 4, 3, 12, 0), (200000, 31, 4, 3, 3, 10, 1), (1_000_000, 100, 4, 4, 3, 8, 0)]:
+for (N, J, Kt, K, D, em, rng) in [(40000, 12, 4, 4, 3, 12, 0), (200000, 31, 4, 3, 3, 10, 1), (1_000_000, 100, 4, 4, 3, 8, 0), (3_000_001, 150, 4, 4, 3, 4, 0)]:
     sim = simulate_qcs(N, J, Kt, D, seed=7)
     iz, ig = init_clusts(sim.x, sim.groups, J, K, seed=7)
     j0, j1, i0, i1 = multigpu.shard_by_sample(sim.groups, J, world)[rank]
@@ -34,6 +34,9 @@ for (N, J, Kt, K, D, em, rng) in [(40000, 12, 4, 4, 3, 12, 0), (200000, 31, 4, 3
             print(f"   {key:8s} vs oracle {d1:.2e}   vs 1 GPU {d2:.2e}")
             ok &= d1 < 1e-8
         zm = int(np.sum(full["z"] != ref["z"])); print("   z mismatches", zm); ok &= zm == 0 and full["n_iter"] == ref["n_iter"]
+        if rng == 0:                                   # R's .Random.seed after the fit (the key stream is generated in shares)
+            same = bool(np.array_equal(full["rng_state"], ref["rng_state"])) and full["rng_draws"] == ref["rng_draws"]
+            print("   rng_state identical:", same); ok &= same
     # MLE
     loc = multigpu.fit_mle_sharded(dist, local, rank, world, xs, np.asfortranarray(ig[i0:i1]), gs, D, j1 - j0, K, i1 - i0, i0, N, 4, 0)
     full = multigpu.assemble(dist, rank, world, loc, (j0, j1, i0, i1), J, N)

@@ -112,6 +112,8 @@ def main():
         if (C >> i) & 1:
             phi |= 1 << (L - i)
     print(f"phi: degree {phi.bit_length() - 1}, weight {phi.bit_count()}  ({time.time() - t0:.1f}s)")
+    taps = [i for i in range(DEG + 1) if (phi >> i) & 1]
+    print(f"phi taps: top {taps[-1]}, next {taps[-2]} (gap {taps[-1] - taps[-2]}), lowest {taps[:3]}")
     XB = polypowx(B, phi, DEG)
     g = polypowx(B - 1, phi, DEG)
     table = []
@@ -146,6 +148,11 @@ def main():
         for p in range(P):
             f.write("{" + ",".join("0x%08xu" % v for v in words[p]) + "},\n")
         f.write("};\n")
+        # the characteristic polynomial itself: the library derives further jump polynomials (x^e mod phi for the
+        # call-to-call and rank offsets of the distributed key stream) on the host at session creation
+        f.write(f"// phi_MT19937 (degree {DEG}, weight {phi.bit_count()}): exponents of its terms, ascending\n")
+        f.write(f"#define SQC_MT_PHI_TERMS {len(taps)}\n")
+        f.write(f"static const int sqc_mt_phi_terms[{len(taps)}] = {{" + ",".join(str(t) for t in taps) + "};\n")
     print("wrote", out, f"({os.path.getsize(out) / 1e6:.2f} MB)")
 
 
