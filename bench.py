@@ -171,7 +171,7 @@ def main():
                           "e2e": {"value": v, "unit": "cell-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO"):
+    if os.environ.get("NCCL_DEBUG"):                              # (NCCL prints its version banner to stdout at WARN / VERSION / INFO)
         os.environ["NCCL_DEBUG_FILE"] = os.environ.get("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
     import torch
     from sampleqc_b200 import api

@@ -234,8 +234,8 @@ struct sqc_session {
   long long N = 0, N_total = 0;
   int em_iters = 0, mcd_iters = 0, rng_mode = 0, track = 0, rank = 0, world = 1;
   double mcd_alpha = 0.5; unsigned seed = 0;
-  cudaStream_t st = nullptr, st_rng = nullptr;
-  cudaEvent_t ev_key_ready[2] = {nullptr, nullptr}, ev_key_free[2] = {nullptr, nullptr}, ev_pre_mcd = nullptr;
+  cudaStream_t st = nullptr, st_rng = nullptr, st_rng2 = nullptr;
+  cudaEvent_t ev_key_ready[2] = {nullptr, nullptr}, ev_key_free[2] = {nullptr, nullptr}, ev_pre_mcd = nullptr, ev_post_mcd = nullptr, ev_chain[2] = {nullptr, nullptr};
   std::vector<void*> allocs;
   Dev dev{};
   McdBufs mb{};
@@ -243,16 +243,17 @@ struct sqc_session {
   Xchg xc{};
   uint8_t* z0 = nullptr; double* alpha0 = nullptr; double* gamma0 = nullptr;
   int mt_target_blocks = 49;
+  bool rng_after_mcd = false;          // generate the next call's keys behind (not beside) the M-step kernel
   unsigned long long* xg_gather = nullptr; double* xg_vec = nullptr;
   uint32_t* mt_state = nullptr; uint32_t* mt_seq = nullptr; uint32_t* mt_table = nullptr; int* keybuf = nullptr;
   // distributed key stream (multi-GPU, R-compatible keys): this rank generates draws [rank * key_q, (rank + 1) * key_q) of every call
-  long long key_q = 0, key_mine = 0; uint32_t* mt_rows = nullptr; uint32_t* mt_jwin = nullptr; const int* key_peer[XCHG_MAX_WORLD] = {};
+  long long key_q = 0, key_mine = 0; uint32_t* mt_rows = nullptr; uint32_t* mt_jwin = nullptr; uint32_t* mt_seq2 = nullptr; const int* key_peer[XCHG_MAX_WORLD] = {};
   double* o_buf = nullptr; int* o_z = nullptr; int* o_korder = nullptr; OutPtrs optr{};
   size_t o_doubles = 0;
   int mcd_grid = 0, n_sm = 0;
   bool sorted = true; std::vector<long long> perm;      // perm[i] = original index of the cell stored at i
   bool profile = false;
-  struct Ev { cudaEvent_t a, b; int fam; };
+  struct Ev { cudaEvent_t a, b; int fam; const char* tag = nullptr; };
   std::vector<Ev> evs; size_t ev_used = 0;
   cudaEvent_t ev_run0 = nullptr, ev_init = nullptr, ev_loop = nullptr;
   sqc_run_stats stats{};
@@ -283,6 +284,9 @@ struct sqc_session {
     if (ev_loop) cudaEventDestroy(ev_loop);
     for (int i = 0; i < 2; ++i) { if (ev_key_ready[i]) cudaEventDestroy(ev_key_ready[i]); if (ev_key_free[i]) cudaEventDestroy(ev_key_free[i]); }
     if (ev_pre_mcd) cudaEventDestroy(ev_pre_mcd);
+    for (int i = 0; i < 2; ++i) if (ev_chain[i]) cudaEventDestroy(ev_chain[i]);
+    if (ev_post_mcd) cudaEventDestroy(ev_post_mcd);
+    if (st_rng2 && st_rng2 != st) cudaStreamDestroy(st_rng2);
     if (st_rng && st_rng != st) cudaStreamDestroy(st_rng);
     if (st) cudaStreamDestroy(st);
   }
@@ -294,22 +298,20 @@ void mle_run(sqc_session*);
 void mle_fetch(sqc_session*, sqc_fit_out*);
 void xchg_allreduce_host(sqc_session* S, double* buf, int n);
 void key_stream_setup(sqc_session* S);
-void xchg_cluster_layout(sqc_session* S, Dev& s);
-void xchg_allreduce_like(sqc_session* S, Dev& s);
 void xchg_allreduce_mle(sqc_session* S, Dev& s, MleBufs& m, int ll_only, double* like, int slot);
 
 // per-launch accounting: count every launch, time it with events when profiling is on
 struct Launch {
-  sqc_session* S; int fam; sqc_session::Ev* ev = nullptr;
-  Launch(sqc_session* s, int f) : S(s), fam(f) {
+  sqc_session* S; int fam; sqc_session::Ev* ev = nullptr; cudaStream_t on;
+  Launch(sqc_session* s, int f, cudaStream_t stream_ = nullptr, const char* tag = nullptr) : S(s), fam(f), on(stream_) {
     S->stats.n_gpu_launches++; S->stats.family_launches[fam]++;
     if (S->profile) {
       if (S->ev_used == S->evs.size()) { sqc_session::Ev e; CK(cudaEventCreate(&e.a)); CK(cudaEventCreate(&e.b)); e.fam = f; S->evs.push_back(e); }
-      ev = &S->evs[S->ev_used++]; ev->fam = f;
+      ev = &S->evs[S->ev_used++]; ev->fam = f; ev->tag = tag;
       CK(cudaEventRecord(ev->a, stream()));
     }
   }
-  cudaStream_t stream() const { return fam == SQC_KF_RNG ? S->st_rng : S->st; }
+  cudaStream_t stream() const { return on ? on : (fam == SQC_KF_RNG ? S->st_rng : S->st); }
   void done() { if (ev) CK(cudaEventRecord(ev->b, stream())); CK(cudaGetLastError()); }
 };
 
@@ -360,52 +362,65 @@ template <int D> void launch_init_passes(sqc_session* S) {
 // ---- host-stream level exchanges (multi-GPU) -----------------------------------------------------
 // after k_post_stats: global cluster sizes and the key-stream offset of the local segment of every cluster
 // (the stream of one call runs over clusters in order, inside a cluster in cell order,
-// and lower ranks hold the lower cell indices)
-__global__ void k_layout_finish(Dev s, XchgDev x, const unsigned long long* gathered) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
+// and lower ranks hold the lower cell indices); the tile partial sums of the log-likelihoods become global sums
+// (slot 0 of t_ll1 / t_ll2), z_delta and the status are agreed on.
+// The per-iteration host-stream exchanges in ONE kernel (one CTA): cluster sizes of every rank -> global sizes and
+// key-stream offsets (k_layout_finish), and with_like: (like_1, like_2, z_delta, n_zero, status) summed in rank order,
+// then the end-of-iteration control (k_like_global + k_em_control).
+__global__ void __launch_bounds__(1024) k_iter_exchange(Dev s, XchgDev x, int with_like) {
+  __shared__ double sh[32];
+  __shared__ unsigned long long sh_n[XCHG_MAX_WORLD * SQC_MAXK];
+  __shared__ double sh_d[XCHG_MAX_WORLD * 5];
+  __shared__ double sh_g[5];
+  if (!s.ctl->cont) return;
+  const int tid = threadIdx.x, K = s.K, W = x.world, ch = XCHG_CH_HOST + 1;
+  double r1 = 0.0, r2 = 0.0;
+  if (with_like) {
+    double a1 = 0.0, a2 = 0.0;
+    for (int t = tid; t < s.T; t += 1024) { a1 += s.t_ll1[t]; a2 += s.t_ll2[t]; }
+    r1 = block_sum<1024>(a1, sh);
+    r2 = block_sum<1024>(a2, sh);
+  }
+  const unsigned long long seq = xchg_begin(x, ch);
+  if (tid < K) { const unsigned long long v = (unsigned long long)s.clu_n[tid]; xchg_put(x, ch, seq, tid, (unsigned int)v, (unsigned int)(v >> 32)); }
+  if (tid == 0 && with_like) {                     // (block_sum leaves the total in thread 0)
+    xchg_put_f64(x, ch, seq, K + 0, r1); xchg_put_f64(x, ch, seq, K + 1, r2); xchg_put_f64(x, ch, seq, K + 2, (double)s.ctl->z_delta);
+    xchg_put_f64(x, ch, seq, K + 3, (double)s.ctl->n_zero); xchg_put_f64(x, ch, seq, K + 4, (double)s.ctl->status);
+  }
+  if (tid < K * W) {
+    const int r = tid / K, k = tid % K;
+    const ulonglong2 v = xchg_wait(x, ch, seq, r, k);
+    sh_n[r * K + k] = (unsigned long long)(unsigned int)v.x | ((unsigned long long)(unsigned int)v.y << 32);
+  } else if (with_like && tid >= 512 && tid < 512 + 5 * W) {
+    const int r = (tid - 512) / 5, e = (tid - 512) % 5;
+    sh_d[r * 5 + e] = line_f64(xchg_wait(x, ch, seq, r, K + e));
+  }
+  __syncthreads();
+  if (tid == 0) {
     long long run = 0;
-    for (int k = 0; k < s.K; ++k) {
+    for (int k = 0; k < K; ++k) {
       long long tot = 0, before = 0;
-      for (int r = 0; r < x.world; ++r) { const long long v = (long long)gathered[r * s.K + k]; tot += v; if (r < x.rank) before += v; }
+      for (int r = 0; r < W; ++r) { const long long v = (long long)sh_n[r * K + k]; tot += v; if (r < x.rank) before += v; }
       s.clu_n_glob[k] = tot; s.clu_prefix[k] = run + before; run += tot;
     }
   }
-}
-// before k_em_control: the tile partial sums become global sums (slot 0 of t_ll1 / t_ll2), z_delta, n_zero and
-// the status are agreed on.  vec = {like_1, like_2, z_delta, n_zero, status flags...}
-__global__ void __launch_bounds__(1024) k_like_local(Dev s, double* vec) {
-  __shared__ double sh[32];
-  if (!s.ctl->cont) return;
-  double a1 = 0.0, a2 = 0.0;
-  for (int t = threadIdx.x; t < s.T; t += 1024) { a1 += s.t_ll1[t]; a2 += s.t_ll2[t]; }
-  const double r1 = block_sum<1024>(a1, sh);
-  const double r2 = block_sum<1024>(a2, sh);
-  if (threadIdx.x == 0) {
-    vec[0] = r1; vec[1] = r2; vec[2] = (double)s.ctl->z_delta; vec[3] = (double)s.ctl->n_zero;
-    vec[4] = (double)s.ctl->status;                     // summed only to detect "somebody failed"; the code itself stays on its rank
+  if (!with_like) return;
+  if (tid < 5) { double g = 0.0; for (int r = 0; r < W; ++r) g += sh_d[r * 5 + tid]; sh_g[tid] = g; }
+  __syncthreads();
+  if (tid == 0) {
+    s.ctl->z_delta = (int)sh_g[2];
+    if (sh_g[4] != 0.0 && s.ctl->status == 0) s.ctl->status = SQC_D_PEER;            // a peer failed (its own message says why)
   }
+  for (int t = tid; t < s.T; t += 1024) { s.t_ll1[t] = (t == 0) ? sh_g[0] : 0.0; s.t_ll2[t] = (t == 0) ? sh_g[1] : 0.0; }
+  __syncthreads();
+  em_control_block(s);
 }
-__global__ void k_like_global(Dev s, const double* vec, const double* loc) {
-  if (!s.ctl->cont) return;
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    // the single-GPU k_em_control sums t_ll1 / t_ll2 over tiles: leave the global sums in tile 0 and zero the rest
-    s.ctl->z_delta = (int)vec[2];
-    if (vec[4] != 0.0 && s.ctl->status == 0) s.ctl->status = SQC_D_PEER;            // a peer failed (its own message says why)
-  }
-  for (int t = threadIdx.x + blockIdx.x * blockDim.x; t < s.T; t += blockDim.x * gridDim.x) { s.t_ll1[t] = (t == 0) ? vec[0] : 0.0; s.t_ll2[t] = (t == 0) ? vec[1] : 0.0; }
+void xchg_iteration(sqc_session* S, Dev& s, int with_like) {
+  Launch L(S, SQC_KF_UPDATE, nullptr, "iter_exchange"); k_iter_exchange<<<1, 1024, 0, S->st>>>(s, S->xc.dev, with_like); L.done();
 }
 
 void xchg_allreduce_host(sqc_session* S, double* buf, int n) {
   Launch L(S, SQC_KF_UPDATE); k_xchg_sum_f64<<<1, 256, 0, S->st>>>(S->xc.dev, XCHG_CH_HOST + 0, buf, n, nullptr); L.done();
-}
-void xchg_cluster_layout(sqc_session* S, Dev& s) {
-  { Launch L(S, SQC_KF_UPDATE); k_xchg_gather_u64<<<1, 256, 0, S->st>>>(S->xc.dev, XCHG_CH_HOST + 1, (const unsigned long long*)s.clu_n, S->xg_gather, s.K, &s.ctl->cont); L.done(); }
-  { Launch L(S, SQC_KF_UPDATE); k_layout_finish<<<1, 32, 0, S->st>>>(s, S->xc.dev, S->xg_gather); L.done(); }
-}
-void xchg_allreduce_like(sqc_session* S, Dev& s) {
-  { Launch L(S, SQC_KF_UPDATE); k_like_local<<<1, 1024, 0, S->st>>>(s, S->xg_vec); L.done(); }
-  { Launch L(S, SQC_KF_UPDATE); k_xchg_sum_f64<<<1, 256, 0, S->st>>>(S->xc.dev, XCHG_CH_HOST + 2, S->xg_vec, 5, &s.ctl->cont); L.done(); }
-  { Launch L(S, SQC_KF_UPDATE); k_like_global<<<8, 256, 0, S->st>>>(s, S->xg_vec, nullptr); L.done(); }
 }
 void xchg_allreduce_mle(sqc_session* S, Dev& s, MleBufs& m, int ll_only, double* like, int slot) {
   if (!ll_only) { Launch L(S, SQC_KF_UPDATE); k_xchg_sum_f64<<<1, 256, 0, S->st>>>(S->xc.dev, XCHG_CH_HOST + 2, m.mom, s.K * SQC_NMOM(s.D), nullptr); L.done(); }
@@ -634,11 +649,12 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
     mb.trace_leader = getenv("SQC_MCD_TRACE") ? atoi(getenv("SQC_MCD_TRACE")) : 0;
     mb.trace = getenv("SQC_MCD_TRACE") ? S->alloc<long long>(16 * 512) : nullptr;
     if (S->rng_mode == SQC_RNG_R_COMPAT) {
-      S->mt_state = S->alloc<uint32_t>(640 * 7);
+      S->mt_state = S->alloc<uint32_t>(640 * 8);
       if (S->world > 1 && S->N_total >= 624LL * 8 * S->world && !getenv("SQC_KEYS_REPLICATED")) key_stream_setup(S);
       else S->keybuf = S->alloc<int>(2 * (size_t)S->N_total, false);
       if (getenv("SQC_RNG_INLINE") && atoi(getenv("SQC_RNG_INLINE"))) S->st_rng = S->st;      // debug: no side stream
       else CK(cudaStreamCreateWithFlags(&S->st_rng, cudaStreamNonBlocking));
+      if (getenv("SQC_RNG_AFTER_MCD")) S->rng_after_mcd = atoi(getenv("SQC_RNG_AFTER_MCD")) != 0;
       if (getenv("SQC_MT_BLOCKS")) S->mt_target_blocks = std::max(1, atoi(getenv("SQC_MT_BLOCKS")));
       for (int i = 0; i < 2; ++i) { CK(cudaEventCreateWithFlags(&S->ev_key_ready[i], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&S->ev_key_free[i], cudaEventDisableTiming)); }
       CK(cudaEventCreateWithFlags(&S->ev_pre_mcd, cudaEventDisableTiming));
@@ -716,7 +732,11 @@ void key_stream_setup(sqc_session* S) {
     if (it == rows.end()) { std::vector<uint32_t> v(MT_N); mtpoly::xpow(words - 1ull, v.data()); it = rows.emplace(words, std::move(v)).first; }
     return it->second;
   };
-  S->mt_rows = S->alloc<uint32_t>(2 * MT_N); S->mt_jwin = S->alloc<uint32_t>(2 * MT_N);
+  S->mt_rows = S->alloc<uint32_t>(2 * MT_N); S->mt_jwin = S->alloc<uint32_t>(2 * MT_N); S->mt_seq2 = S->alloc<uint32_t>(MT_SEQ_WORDS + 64);
+  if (getenv("SQC_RNG_INLINE") && atoi(getenv("SQC_RNG_INLINE"))) S->st_rng2 = S->st;
+  else CK(cudaStreamCreateWithFlags(&S->st_rng2, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&S->ev_chain[i], cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&S->ev_post_mcd, cudaEventDisableTiming));
   CK(cudaMemcpyAsync(S->mt_rows, row((unsigned long long)(S->N_total / MT_N) * MT_N).data(), MT_N * sizeof(uint32_t), cudaMemcpyHostToDevice, S->st));
   if (r > 0 && S->key_mine > 0)
     CK(cudaMemcpyAsync(S->mt_rows + MT_N, row((unsigned long long)r * (unsigned long long)S->key_q).data(), MT_N * sizeof(uint32_t), cudaMemcpyHostToDevice, S->st));
@@ -749,14 +769,14 @@ void mt_generate(cudaStream_t stream, const uint32_t* st_in, uint32_t* st_out, u
     const bool last = done + m >= n;
     uint32_t* nxt = last ? st_out : ((w & 1) ? tmp1 : tmp0);
     const int nb = (int)((MT_N + m + blk_words - 1) / blk_words);  // upper bound on the blocks touched (mti <= 624)
-    if (S) { Launch L(S, SQC_KF_RNG); k_mt_seq<<<1, 256, 0, stream>>>(cur, seq, ctl); L.done(); }
+    if (S) { Launch L(S, SQC_KF_RNG, stream, "seq"); k_mt_seq<<<1, 256, 0, stream>>>(cur, seq, ctl); L.done(); }
     else k_mt_seq<<<1, 256, 0, stream>>>(cur, seq, ctl);
     uint32_t* windows = seq + MT_SEQ_WORDS;                        // (SQC_MT_JUMP_ROWS + 1) x 624 behind the sequence
     if (nb > 1) {
-      if (S) { Launch L(S, SQC_KF_RNG); k_mt_jump<<<nb - 1, MT_JUMP_THREADS, MT_SMEM, stream>>>(cur, seq, table, windows, m, mult, ctl); L.done(); }
+      if (S) { Launch L(S, SQC_KF_RNG, stream, "jump"); k_mt_jump<<<nb - 1, MT_JUMP_THREADS, MT_SMEM, stream>>>(cur, seq, table, windows, m, mult, ctl); L.done(); }
       else k_mt_jump<<<nb - 1, MT_JUMP_THREADS, MT_SMEM, stream>>>(cur, seq, table, windows, m, mult, ctl);
     }
-    if (S) { Launch L(S, SQC_KF_RNG); k_mt_gen<<<nb, MT_GEN_THREADS, 0, stream>>>(cur, nxt, seq, windows, out + done, m, mult, ctl); L.done(); }
+    if (S) { Launch L(S, SQC_KF_RNG, stream, "gen"); k_mt_gen<<<nb, MT_GEN_THREADS, 0, stream>>>(cur, nxt, seq, windows, out + done, m, mult, ctl); L.done(); }
     else k_mt_gen<<<nb, MT_GEN_THREADS, 0, stream>>>(cur, nxt, seq, windows, out + done, m, mult, ctl);
     cur = nxt; done += m; ++w;
   }
@@ -774,39 +794,63 @@ void enqueue_keys(sqc_session* S, int call, cudaEvent_t after) {
   if (after) CK(cudaStreamWaitEvent(S->st_rng, after, 0));
   uint32_t* base = S->mt_state;
   if (S->key_q) {
-    // state in front of the call -> (state after the call, state in front of this rank's share) by jump polynomials,
-    // then only this rank's share of the keys
-    const uint32_t* in = base + 640 * ((call + 2) % 3);
-    const bool has_rank = S->rank > 0 && S->key_mine > 0;
-    { Launch L(S, SQC_KF_RNG); k_mt_seq<<<1, 256, 0, S->st_rng>>>(in, S->mt_seq, S->dev.ctl); L.done(); }
-    { Launch L(S, SQC_KF_RNG); k_mt_jump_rows<<<has_rank ? 2 : 1, MT_JUMP_THREADS, MT_SMEM, S->st_rng>>>(S->mt_seq, S->mt_rows, S->mt_jwin, S->dev.ctl); L.done(); }
-    { Launch L(S, SQC_KF_RNG); k_mt_fix<<<1, 256, 0, S->st_rng>>>(in, S->mt_jwin, base + 640 * (call % 3), base + 640 * 5, S->N_total, has_rank ? 1 : 0, S->dev.ctl); L.done(); }
+    // distributed stream: only this rank's share, from the state enqueue_chain left in slot 5 + (call & 1)
+    CK(cudaStreamWaitEvent(S->st_rng, S->ev_chain[kb], 0));
     if (S->key_mine > 0)
-      mt_generate(S->st_rng, base + 640 * 5, base + 640 * 6, base + 640 * 3, base + 640 * 4, S->mt_seq, S->mt_table,
+      mt_generate(S->st_rng, base + 640 * (5 + kb), base + 640 * 7, base + 640 * 3, base + 640 * 4, S->mt_seq, S->mt_table,
                   S->keybuf + (size_t)kb * S->key_q, S->key_mine, S->dev.ctl, S, S->mt_target_blocks);
   } else
   mt_generate(S->st_rng, base + 640 * ((call + 2) % 3), base + 640 * (call % 3), base + 640 * 3, base + 640 * 4, S->mt_seq, S->mt_table,
               S->keybuf + (size_t)kb * S->N_total, S->N_total, S->dev.ctl, S, S->mt_target_blocks);
   CK(cudaEventRecord(S->ev_key_ready[kb], S->st_rng));
 }
+// distributed stream: the state in front of `call` (slot (call + 2) % 3) -> the state after it (slot call % 3) and the
+// state in front of this rank's share (slot 5 + (call & 1)), by jump polynomials.  Data-independent and tiny (one or
+// two CTAs, but ~0.2 ms of latency), so it runs on its own stream one call ahead of the generation.
+void enqueue_chain(sqc_session* S, int call, cudaEvent_t after) {
+  uint32_t* base = S->mt_state;
+  if (after) CK(cudaStreamWaitEvent(S->st_rng2, after, 0));
+  const uint32_t* in = base + 640 * ((call + 2) % 3);
+  const bool has_rank = S->rank > 0 && S->key_mine > 0;
+  { Launch L(S, SQC_KF_RNG, S->st_rng2, "chain_seq"); k_mt_seq<<<1, 256, 0, S->st_rng2>>>(in, S->mt_seq2, S->dev.ctl); L.done(); }
+  { Launch L(S, SQC_KF_RNG, S->st_rng2, "chain_jump"); k_mt_jump_rows<<<has_rank ? 2 : 1, MT_JUMP_THREADS, MT_SMEM, S->st_rng2>>>(S->mt_seq2, S->mt_rows, S->mt_jwin, S->dev.ctl); L.done(); }
+  { Launch L(S, SQC_KF_RNG, S->st_rng2, "chain_fix"); k_mt_fix<<<1, 256, 0, S->st_rng2>>>(in, S->mt_jwin, base + 640 * (call % 3), base + 640 * (5 + (call & 1)), S->N_total, has_rank ? 1 : 0, S->dev.ctl); L.done(); }
+  CK(cudaEventRecord(S->ev_chain[call & 1], S->st_rng2));
+}
+void enqueue_next_keys(sqc_session* S, int call) {
+  if (S->rng_mode != SQC_RNG_R_COMPAT || call + 1 > S->em_iters) return;
+  CK(cudaEventRecord(S->ev_pre_mcd, S->st));
+  enqueue_keys(S, call + 1, S->ev_pre_mcd);
+}
 void use_keys(sqc_session* S, int call) {
   if (S->rng_mode == SQC_RNG_R_COMPAT) {
-    // the keys of the NEXT call are generated while this call's M-step kernel runs
-    if (call + 1 <= S->em_iters) { CK(cudaEventRecord(S->ev_pre_mcd, S->st)); enqueue_keys(S, call + 1, S->ev_pre_mcd); }
     CK(cudaStreamWaitEvent(S->st, S->ev_key_ready[call & 1], 0));
     if (S->key_q) {
       // every rank's share of this call must be complete before any rank's M-step kernel reads it: one tiny exchange
       // behind the wait orders them (the peers' reads end before this kernel's last exchange of the call, so the
       // buffer may be refilled once the kernel is done - the same event that frees it locally)
-      { Launch L(S, SQC_KF_UPDATE); k_xchg_sum_f64<<<1, 32, 0, S->st>>>(S->xc.dev, XCHG_CH_HOST + 0, S->xg_vec + 8, 1, &S->dev.ctl->cont); L.done(); }
+      { Launch L(S, SQC_KF_UPDATE, nullptr, "key_fence"); k_xchg_sum_f64<<<1, 32, 0, S->st>>>(S->xc.dev, XCHG_CH_HOST + 0, S->xg_vec + 8, 1, &S->dev.ctl->cont); L.done(); }
       S->mb.keys = S->keybuf + (size_t)(call & 1) * S->key_q;
       for (int q = 0; q < S->world; ++q) S->mb.key_peer[q] = S->key_peer[q] + (size_t)(call & 1) * S->key_q;
       S->mb.key_q = S->key_q; S->mb.key_qinv = 1.0 / (double)S->key_q;
     } else
     S->mb.keys = S->keybuf + (size_t)(call & 1) * S->N_total;
+    // the keys of the NEXT call are generated while this call's M-step kernel runs (released only now: kernels that
+    // slip onto the SMs during a wait above would hold up the cooperative launch that follows)
+    if (!S->rng_after_mcd) enqueue_next_keys(S, call);
   } else S->mb.keys = nullptr;
   S->mb.call_mix = counter_call_mix(S->seed, 0u);
   S->mb.stream_base = (long long)call * S->N_total;
+}
+// behind the M-step kernel: the state chain of call + 2 (tiny; a CTA of it in front of the cooperative launch would
+// delay that launch by its whole 0.15 ms)
+void after_mcd_keys(sqc_session* S, int call) {
+  if (S->rng_mode != SQC_RNG_R_COMPAT) return;
+  if (S->rng_after_mcd) enqueue_next_keys(S, call);
+  if (S->key_q && call + 2 <= S->em_iters) {
+    CK(cudaEventRecord(S->ev_post_mcd, S->st));
+    enqueue_chain(S, call + 2, S->ev_post_mcd);             // its share-state slot was last read by the keys of `call`
+  }
 }
 void release_keys(sqc_session* S, int call) {
   if (S->rng_mode != SQC_RNG_R_COMPAT) return;
@@ -826,25 +870,33 @@ void run_robust(sqc_session* S) {
   CK(cudaMemsetAsync(s.like2, 0, (size_t)(std::max(S->em_iters, 0) + 1) * sizeof(double), S->st));
   if (S->mt_state) {                                                                    // set_seed_cpp, :475
     CK(cudaEventRecord(S->ev_key_free[0], S->st)); CK(cudaEventRecord(S->ev_key_free[1], S->st));   // after k_ctl_reset
-    CK(cudaStreamWaitEvent(S->st_rng, S->ev_key_free[0], 0));
-    { Launch L(S, SQC_KF_RNG); k_mt_seed<<<1, 32, 0, S->st_rng>>>(S->mt_state + 640 * 2, S->seed); L.done(); }
+    if (S->key_q) {
+      CK(cudaStreamWaitEvent(S->st_rng2, S->ev_key_free[0], 0));
+      { Launch L(S, SQC_KF_RNG, S->st_rng2, "seed"); k_mt_seed<<<1, 32, 0, S->st_rng2>>>(S->mt_state + 640 * 2, S->seed); L.done(); }
+      enqueue_chain(S, 0, nullptr);
+      if (1 <= S->em_iters) enqueue_chain(S, 1, nullptr);
+    } else {
+      CK(cudaStreamWaitEvent(S->st_rng, S->ev_key_free[0], 0));
+      { Launch L(S, SQC_KF_RNG); k_mt_seed<<<1, 32, 0, S->st_rng>>>(S->mt_state + 640 * 2, S->seed); L.done(); }
+    }
     enqueue_keys(S, 0, nullptr);
   }
   const int nsb = (J + 31) / 32;
   auto post_stats = [&](int fuse_ctl) {
     Launch L(S, SQC_KF_UPDATE); k_post_stats<<<nsb, 1024, 0, S->st>>>(s, nsb, fuse_ctl); L.done();
-    if (S->world > 1) xchg_cluster_layout(S, s);
   };
   auto m_step = [&](int call, int like) {
     do_partition(S, like);
     use_keys(S, call);
     do_mcd(S);
+    after_mcd_keys(S, call);
     release_keys(S, call);
     do_after_mstep(S, like);                     // derived constants; inside the loop also p_jk (:504)
   };
   // initial labelling: p_jk (:481), alpha_j (:482), beta_k / Sigma_k (:483)
   do_estep(S, 1);
   post_stats(0);
+  if (S->world > 1) xchg_iteration(S, s, 0);
   { Launch L(S, SQC_KF_UPDATE); k_update_p<<<(J + 127) / 128, 128, 0, S->st>>>(s); L.done(); }
   m_step(0, 0);
   { Launch L(S, SQC_KF_UPDATE); k_ctl_start_loop<<<1, 32, 0, S->st>>>(s); L.done(); }
@@ -854,10 +906,7 @@ void run_robust(sqc_session* S) {
     m_step(it + 1, 1);                                                                  // like_1 :499, M-step :502, p_jk :504
     do_estep(S, 0);                                                                     // :506, :509, :519
     post_stats(S->world > 1 ? 0 : 1);                                                  // single GPU: :511-521 fused in
-    if (S->world > 1) {
-      xchg_allreduce_like(S, s);
-      { Launch L(S, SQC_KF_UPDATE); k_em_control<<<1, 1024, 0, S->st>>>(s); L.done(); }
-    }
+    if (S->world > 1) xchg_iteration(S, s, 1);     // cluster layout of the next M-step + like / z_delta / status + loop control
   }
   CK(cudaEventRecord(S->ev_loop, S->st));
 }
@@ -871,6 +920,7 @@ void session_run(sqc_session* S) {
   CK(cudaMemcpyAsync(&S->h_ctl, S->dev.ctl, sizeof(Control), cudaMemcpyDeviceToHost, S->st));
   CK(cudaStreamSynchronize(S->st));
   if (S->st_rng) CK(cudaStreamSynchronize(S->st_rng));
+  if (S->st_rng2) CK(cudaStreamSynchronize(S->st_rng2));
   S->ran = true;
   float ms = 0;
   CK(cudaEventElapsedTime(&ms, S->ev_run0, S->ev_init)); S->stats.init_ms = ms;
@@ -880,6 +930,19 @@ void session_run(sqc_session* S) {
   for (size_t i = 0; i < S->ev_used; ++i) {
     CK(cudaEventElapsedTime(&ms, S->evs[i].a, S->evs[i].b));
     S->stats.family_ms[S->evs[i].fam] += ms;
+  }
+  if (const char* tl = S->ev_used ? getenv("SQC_TIMELINE") : nullptr) {                          // debug: one CSV row per launch (ms since the run began)
+    static const char* fam_names[] = {"estep", "partition", "mcd", "update", "rng", "init", "mle_pass", "final"};
+    char path[512]; snprintf(path, sizeof path, "%s.rank%d.csv", tl, S->rank);
+    if (FILE* f = fopen(path, "w")) {
+      fprintf(f, "launch,family,tag,t0_ms,t1_ms\n");
+      for (size_t i = 0; i < S->ev_used; ++i) {
+        float t0 = 0, t1 = 0;
+        cudaEventElapsedTime(&t0, S->ev_run0, S->evs[i].a); cudaEventElapsedTime(&t1, S->ev_run0, S->evs[i].b);
+        fprintf(f, "%zu,%s,%s,%.4f,%.4f\n", i, fam_names[S->evs[i].fam], S->evs[i].tag ? S->evs[i].tag : "", t0, t1);
+      }
+      fclose(f);
+    }
   }
   // algorithmic bytes: one pass = N (8 D + 5) bytes; E-step writes N more
   const double pass = (double)S->N * (8.0 * S->D + 5.0);

@@ -265,6 +265,10 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
   if (!s.ctl->cont) return;                    // uniform across the grid (and across ranks): nobody reaches a barrier
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, G = gridDim.x, b = blockIdx.x, K = s.K;
   const int world = (MULTI && mb.xc.world > 1) ? mb.xc.world : 1, myrank = world > 1 ? mb.xc.rank : 0;
+  // the candidate caps bound the per-rank work of a leader post and the load of the per-warp candidate regions: with the
+  // cells spread over `world` ranks the global count may be that much larger (an unbalanced cluster that overflows a
+  // region takes the regular fallback round)
+  const double cap_scale = (double)world;
   const int regions = G * MCD_WARPS, region = b * MCD_WARPS + wid;
   const int NWK = G - K;                       // worker CTAs; CTAs 0 .. K-1 are the cluster leaders
   McdWork* W = mb.work;
@@ -298,7 +302,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         // band holds few enough keys (expected 8 sigma_rank = 8 sqrt(n p (1 - p))); a miss falls back to KEY_HIST
         const double exp_cand = 8.0 * sqrt((double)n * p * (1.0 - p));
         const double blo = p * two31 - 4.0 * sig - 1.0, bhi = p * two31 + 4.0 * sig + 1.0;
-        if (SQC_MCD_DIRECT && n > 65536 && exp_cand <= SQC_MCD_DIRECT_KEYCAP && blo > 0.0 && bhi < two31) {
+        if (SQC_MCD_DIRECT && n > 65536 && exp_cand <= SQC_MCD_DIRECT_KEYCAP * cap_scale && blo > 0.0 && bhi < two31) {
           c.blo = (unsigned long long)blo; c.bhi = (unsigned long long)bhi;
           int fs = 0;
           while (fs < 62 && ((c.bhi - c.blo) >> fs) >= (unsigned long long)MCD_NF) ++fs;
@@ -401,9 +405,9 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
             const unsigned long long blo = cl.wlo + ((unsigned long long)bin << cl.shift);
             unsigned long long bhi = blo + (1ull << cl.shift);
             if (bhi > cl.whi) bhi = cl.whi;
-            if (sh_u64[1] > (unsigned long long)MCD_CAND_CAP && cl.shift > 0 && cl.n_hist_rounds <= 40) {
+            if (sh_u64[1] > (unsigned long long)MCD_CAND_CAP * (unsigned long long)world && cl.shift > 0 && cl.n_hist_rounds <= 40) {
               cl.wlo = blo; cl.whi = bhi; cl.shift = window_shift(blo, bhi);                 // refine inside the bin
-            } else if (sh_u64[1] > (unsigned long long)MCD_CAND_CAP) {
+            } else if (sh_u64[1] > (unsigned long long)MCD_CAND_CAP * (unsigned long long)world) {
               atomicCAS(&(*mb.status), 0, SQC_D_SELECT); cl.phase = PH_DONE;
             } else {
               cl.blo = blo; cl.bhi = bhi; cl.below = below + (long long)sh_u64[0];
@@ -723,7 +727,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
               // band around the last threshold that should hold the next one and few enough cells; the COLLECT round
               // counts the cells under the band itself.  A miss costs one regular round.
               const double wband = 2.0 * cl.last_rel + 5e-4;
-              if (cl.t_prev && cl.last_rel < 0.02 && cl.dens * 2.0 * wband <= SQC_MCD_DIRECT_CAP && SQC_MCD_DIRECT) {
+              if (cl.t_prev && cl.last_rel < 0.02 && cl.dens * 2.0 * wband <= SQC_MCD_DIRECT_CAP * cap_scale && SQC_MCD_DIRECT) {
                 const double t = __longlong_as_double((long long)cl.t_prev);
                 cl.blo = dist_bits(t * (1.0 - wband)); cl.bhi = dist_bits(t * (1.0 + wband));
                 int fs = 0;

@@ -9,7 +9,10 @@ rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = i
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ok = True
-for (N, J, Kt, K, D, em, rng) in [(40000, 12, 4, 4, 3, 12, 0), (200000, 31, 4, 3, 3, 10, 1), (1_000_000, 100, 4, 4, 3, 8, 0), (3_000_001, 150, 4, 4, 3, 4, 0)]:
+CASES = [(40000, 12, 4, 4, 3, 12, 0), (200000, 31, 4, 3, 3, 10, 1), (1_000_000, 100, 4, 4, 3, 8, 0), (3_000_001, 150, 4, 4, 3, 4, 0)]
+if os.environ.get("MGPU_QUICK"):
+    CASES = CASES[:2]
+for (N, J, Kt, K, D, em, rng) in CASES:
     sim = simulate_qcs(N, J, Kt, D, seed=7)
     iz, ig = init_clusts(sim.x, sim.groups, J, K, seed=7)
     j0, j1, i0, i1 = multigpu.shard_by_sample(sim.groups, J, world)[rank]
