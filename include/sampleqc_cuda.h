@@ -211,6 +211,11 @@ SQC_API int sqc_device_expneg(const double* x, double* out, int32_t n, int devic
 /* the R-compatible Mersenne-Twister key stream generated on the device (tests)               */
 SQC_API int sqc_device_rkeys(uint32_t seed, int64_t skip, int32_t* keys_out, int64_t n, int device,
                      char* err, size_t errlen);
+/* the same stream as ONE RANK of a multi-GPU fit produces it (tests; runs on one GPU): rank `rank` of `world` generates
+ * draws [rank Q, (rank + 1) Q) of each of `calls` consecutive calls of n_total draws (Q = *q_out, a multiple of 624);
+ * keys_out holds calls x Q ints, state_out (625 words, may be NULL) R's state after the last call.                     */
+SQC_API int sqc_device_rkeys_share(uint32_t seed, int64_t n_total, int world, int rank, int calls, int32_t* keys_out,
+                           int64_t* q_out, int32_t* state_out, int device, char* err, size_t errlen);
 
 #ifdef __cplusplus
 }

@@ -149,6 +149,20 @@ def device_rkeys(seed, skip, n, device=-1):
     return out
 
 
+def device_rkeys_share(seed, n_total, world, rank, calls, device=-1):
+    """rank `rank`'s share of the key stream of `calls` consecutive calls, as a multi-GPU fit generates it
+    (returns (calls x Q int32 array, Q, R's state after the last call))"""
+    per = -(-n_total // world)
+    q_guess = -(-per // 624) * 624
+    out = np.zeros((calls, q_guess), dtype=np.int32)
+    state = np.zeros(625, dtype=np.int32)
+    q = C.c_int64(0)
+    err = C.create_string_buffer(512)
+    check(lib().sqc_device_rkeys_share(seed, n_total, world, rank, calls, A.ptr_i(out), C.byref(q), A.ptr_i(state), device, err, 512), err)
+    assert q.value == q_guess
+    return out, int(q.value), state
+
+
 def device_expneg(x, device=-1):
     x = np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1))
     out = np.zeros_like(x)

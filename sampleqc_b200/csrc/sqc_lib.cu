@@ -1188,4 +1188,50 @@ int sqc_device_rkeys(uint32_t seed, int64_t skip, int32_t* keys_out, int64_t n, 
   }, err, errlen);
 }
 
+// test hook for the distributed key stream (what one rank of `world` does over `calls` consecutive calls of n_total draws):
+// keys_out = calls x Q ints (rank `rank`'s share of every call, Q = *q_out draws per rank), state_out = R's state after the
+// last call (identical on every rank).  Runs on one GPU: the pieces (host-derived jump polynomials, k_mt_jump_rows,
+// k_mt_fix, share generation) are the ones sqc_fit_robust uses with world > 1.
+int sqc_device_rkeys_share(uint32_t seed, int64_t n_total, int world, int rank, int calls, int32_t* keys_out, int64_t* q_out, int32_t* state_out,
+                           int device, char* err, size_t errlen) {
+  return guarded([&] {
+    if (!keys_out || !q_out || n_total < 624LL * 8 * world || world < 1 || world > XCHG_MAX_WORLD || rank < 0 || rank >= world || calls < 1) fail(SQC_ERR_BAD_ARG, "bad arguments");
+    int d; select_device(device, &d);
+    if (!mtpoly::self_check()) fail(SQC_ERR_COMM, "jump polynomial derivation failed its self-check");
+    const long long per = (n_total + world - 1) / world, Q = ((per + MT_N - 1) / MT_N) * MT_N;
+    const long long mine = std::max<long long>(0, std::min<long long>(Q, n_total - (long long)rank * Q));
+    *q_out = Q;
+    uint32_t *st = nullptr, *seq = nullptr, *seq2 = nullptr, *table = nullptr, *rows = nullptr, *jwin = nullptr; int* out = nullptr;
+    auto cleanup = [&] { cudaFree(st); cudaFree(seq); cudaFree(seq2); cudaFree(table); cudaFree(rows); cudaFree(jwin); cudaFree(out); };
+    try {
+      CK(cudaMalloc((void**)&st, 640 * 8 * sizeof(uint32_t)));
+      CK(cudaMalloc((void**)&seq, (MT_SEQ_WORDS + (size_t)(SQC_MT_JUMP_ROWS + 2) * MT_N) * sizeof(uint32_t))); CK(cudaMalloc((void**)&seq2, (MT_SEQ_WORDS + 64) * sizeof(uint32_t)));
+      CK(cudaMalloc((void**)&table, sizeof sqc_mt_jump_table)); CK(cudaMalloc((void**)&rows, 2 * MT_N * sizeof(uint32_t))); CK(cudaMalloc((void**)&jwin, 2 * MT_N * sizeof(uint32_t)));
+      CK(cudaMalloc((void**)&out, (size_t)std::max<long long>(mine, 1) * sizeof(int)));
+      CK(cudaMemcpy(table, sqc_mt_jump_table, sizeof sqc_mt_jump_table, cudaMemcpyHostToDevice));
+      std::vector<uint32_t> r0(MT_N), r1(MT_N);
+      mtpoly::xpow((unsigned long long)(n_total / MT_N) * MT_N - 1ull, r0.data());
+      CK(cudaMemcpy(rows, r0.data(), MT_N * sizeof(uint32_t), cudaMemcpyHostToDevice));
+      const bool has_rank = rank > 0 && mine > 0;
+      if (has_rank) { mtpoly::xpow((unsigned long long)rank * (unsigned long long)Q - 1ull, r1.data()); CK(cudaMemcpy(rows + MT_N, r1.data(), MT_N * sizeof(uint32_t), cudaMemcpyHostToDevice)); }
+      CK(cudaFuncSetAttribute(k_mt_jump, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_SMEM));
+      CK(cudaFuncSetAttribute(k_mt_jump_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_SMEM));
+      k_mt_seed<<<1, 32>>>(st + 640 * 2, seed);
+      for (int c = 0; c < calls; ++c) {
+        const uint32_t* in = st + 640 * ((c + 2) % 3);
+        k_mt_seq<<<1, 256>>>(in, seq2, nullptr);
+        k_mt_jump_rows<<<has_rank ? 2 : 1, MT_JUMP_THREADS, MT_SMEM>>>(seq2, rows, jwin, nullptr);
+        k_mt_fix<<<1, 256>>>(in, jwin, st + 640 * (c % 3), st + 640 * 5, n_total, has_rank ? 1 : 0, nullptr);
+        if (mine > 0) {
+          mt_generate(0, st + 640 * 5, st + 640 * 7, st + 640 * 3, st + 640 * 4, seq, table, out, mine, nullptr, nullptr, mine > 2000000 ? 20 : 1000);
+          CK(cudaMemcpy(keys_out + (size_t)c * Q, out, (size_t)mine * sizeof(int), cudaMemcpyDeviceToHost));
+        }
+      }
+      CK(cudaGetLastError());
+      if (state_out) CK(cudaMemcpy(state_out, st + 640 * ((calls - 1) % 3), 625 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    } catch (...) { cleanup(); throw; }
+    cleanup();
+  }, err, errlen);
+}
+
 }  // extern "C"

@@ -115,6 +115,26 @@ def test_device_special_functions(oracle):
     np.testing.assert_array_equal(api.device_rkeys(5, 624, 625), oracle.rkeys(5, 624, 625))
 
 
+@pytest.mark.parametrize("n_total,world,calls,seed", [(1_000_003, 3, 3, 11), (5_000_000, 8, 2, 0), (40_000, 2, 4, 3), (624 * 16, 2, 3, 5)])
+def test_distributed_key_stream_matches_r(oracle, n_total, world, calls, seed):
+    """multi-GPU fits generate R's key stream in per-rank shares (host-derived GF(2) jump polynomials move the
+    Mersenne-Twister state from call to call and to a rank's offset): the shares of all ranks, concatenated, are the
+    stream set.seed(seed) gives, call after call, and every rank ends with the same state"""
+    from sampleqc_b200 import api
+    want = oracle.rkeys(seed, 0, calls * n_total).reshape(calls, n_total)
+    states = []
+    for r in range(world):
+        got, q, st = api.device_rkeys_share(seed, n_total, world, r, calls)
+        lo, hi = r * q, min((r + 1) * q, n_total)
+        for c in range(calls):
+            np.testing.assert_array_equal(got[c, :max(hi - lo, 0)], want[c, lo:hi])
+        states.append(st)
+    for st in states[1:]:
+        np.testing.assert_array_equal(st, states[0])
+    # the state after the last call continues the stream: one more call from it through the single-stream generator
+    assert states[0][624] >= 1 and states[0][624] <= 624
+
+
 def test_outlier_mask_matches_oracle(oracle):
     from sampleqc_b200 import api
     N, J, K = 20000, 6, 3
