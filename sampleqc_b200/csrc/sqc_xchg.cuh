@@ -66,12 +66,16 @@ __device__ __forceinline__ void xchg_put(const XchgDev& x, int ch, unsigned long
 __device__ __forceinline__ void xchg_put_f64(const XchgDev& x, int ch, unsigned long long seq, int line, double v) {
   xchg_put(x, ch, seq, line, (unsigned int)__double2loint(v), (unsigned int)__double2hiint(v));
 }
-// wait for line `line` of rank r's message (local polling; a peer that never sends traps the kernel after ~20 s)
+// wait for line `line` of rank r's message: local polling, tight at first, then with a 1 us back-off; a peer that
+// never sends traps the kernel after about a minute (the host then reports SQC_ERR_CUDA instead of hanging)
 __device__ __forceinline__ ulonglong2 xchg_wait(const XchgDev& x, int ch, unsigned long long seq, int r, int line) {
   const ulonglong2* p = xw_line(x.peer[x.rank], ch, seq, r) + line;
   ulonglong2 v = ld_line(p);
   unsigned int spins = 0;
-  while (!line_ready(v, (unsigned int)seq)) { if (++spins > (1u << 25)) __trap(); v = ld_line(p); }
+  while (!line_ready(v, (unsigned int)seq)) {
+    if (++spins > (1u << 16)) { __nanosleep(1000); if (spins > (1u << 16) + 40000000u) __trap(); }
+    v = ld_line(p);
+  }
   return v;
 }
 // the same line of every rank: all loads are issued before the first is examined
