@@ -217,6 +217,11 @@ SQC_API int sqc_device_rkeys(uint32_t seed, int64_t skip, int32_t* keys_out, int
 SQC_API int sqc_device_rkeys_share(uint32_t seed, int64_t n_total, int world, int rank, int calls, int32_t* keys_out,
                            int64_t* q_out, int32_t* state_out, int device, char* err, size_t errlen);
 
+/* host-only (no GPU needed): x^e mod phi_MT19937 over GF(2), the jump polynomial that moves the Mersenne-Twister state
+ * e words ahead (624 words, bit i of word w = coefficient of x^(32 w + i)); SQC_ERR_COMM if the self-check against the
+ * offline-verified table fails                                                                                       */
+SQC_API int sqc_mt_jump_poly(uint64_t e, uint32_t* out624);
+
 #ifdef __cplusplus
 }
 #endif

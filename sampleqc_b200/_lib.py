@@ -17,7 +17,7 @@ EXPORTS = (
     "sqc_fit_robust", "sqc_fit_mle", "sqc_outlier_maha",
     "sqc_session_create", "sqc_session_run", "sqc_session_fetch", "sqc_session_stats", "sqc_session_profile",
     "sqc_session_destroy", "sqc_xchg_export", "sqc_xchg_release",
-    "sqc_trim", "sqc_abi_version", "sqc_device_count", "sqc_status_name", "sqc_device_qchisq", "sqc_device_rkeys", "sqc_device_rkeys_share", "sqc_device_expneg",
+    "sqc_trim", "sqc_abi_version", "sqc_device_count", "sqc_status_name", "sqc_device_qchisq", "sqc_device_rkeys", "sqc_device_rkeys_share", "sqc_device_expneg", "sqc_mt_jump_poly",
 )
 
 
@@ -69,6 +69,8 @@ def lib():
     L.sqc_device_rkeys.restype = C.c_int
     L.sqc_device_rkeys_share.argtypes = [C.c_uint32, C.c_int64, C.c_int, C.c_int, C.c_int, A.c_int32_p, C.POINTER(C.c_int64), A.c_int32_p, C.c_int, C.c_char_p, C.c_size_t]
     L.sqc_device_rkeys_share.restype = C.c_int
+    L.sqc_mt_jump_poly.argtypes = [C.c_uint64, C.c_void_p]
+    L.sqc_mt_jump_poly.restype = C.c_int
     if L.sqc_abi_version() != A.SQC_ABI_VERSION:
         raise RuntimeError("libsampleqc_cuda.so ABI version does not match sampleqc_b200._abi")
     _LIB = L

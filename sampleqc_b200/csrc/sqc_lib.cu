@@ -1234,4 +1234,12 @@ int sqc_device_rkeys_share(uint32_t seed, int64_t n_total, int world, int rank, 
   }, err, errlen);
 }
 
+// host-only test hook: the jump polynomial x^e mod phi_MT19937 the distributed key stream derives at session creation
+// (624 words, bit i of word w = coefficient of x^(32 w + i)); needs no GPU
+int sqc_mt_jump_poly(uint64_t e, uint32_t* out624) {
+  if (!out624) return SQC_ERR_BAD_ARG;
+  mtpoly::xpow((unsigned long long)e, out624);
+  return mtpoly::self_check() ? SQC_OK : SQC_ERR_COMM;
+}
+
 }  // extern "C"

@@ -121,3 +121,65 @@ def test_multigpu_host_logic_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"ok {r}" in o, o
+
+
+def test_mt_jump_polynomials_move_the_state(tmp_path):
+    """the distributed key stream moves R's Mersenne-Twister state e words ahead with x^(e-1) mod phi derived on the
+    host: check the derivation against an independent big-integer computation and against a directly generated stream
+    (window[j] = XOR over the polynomial's terms i of x[i + j + 1])"""
+    L = _lib()
+    lib = L.lib()
+    inc = open(os.path.join(ROOT, "sampleqc_b200", "csrc", "sqc_mt_jump.inc")).read()
+    terms = [int(t) for t in re.search(r"sqc_mt_phi_terms\[\d+\] = \{([^}]*)\}", inc).group(1).split(",")]
+    assert terms[-1] == 19937 and len(terms) == 135
+    phi = sum(1 << t for t in terms)
+
+    def mulmod(a, b):
+        r = 0
+        while a:
+            low = a & -a
+            r ^= b << (low.bit_length() - 1)
+            a ^= low
+        while r.bit_length() > 19937:
+            r ^= phi << (r.bit_length() - 1 - 19937)
+        return r
+
+    def xpow(e):
+        result, base = 1, 2
+        while e:
+            if e & 1:
+                result = mulmod(result, base)
+            base = mulmod(base, base)
+            e >>= 1
+        return result
+
+    def lib_poly(e):
+        out = np.zeros(624, dtype=np.uint32)
+        assert lib.sqc_mt_jump_poly(e, out.ctypes.data_as(C.c_void_p)) == 0
+        return sum(int(w) << (32 * i) for i, w in enumerate(out))
+
+    for e in (1, 623, 19936, 19937, 624 * 1602 - 1, 3_000_001, 80_000_000 - 1, (1 << 40) + 12345):
+        assert lib_poly(e) == xpow(e), e
+
+    # against a direct stream: x[0..623] = seeded array, x[n + 624] = x[n + 397] ^ twist(x[n], x[n + 1])
+    def stream(seed, n_words):
+        s = seed & 0xFFFFFFFF
+        for _ in range(50):
+            s = (69069 * s + 1) & 0xFFFFFFFF
+        s = (69069 * s + 1) & 0xFFFFFFFF
+        x = []
+        for _ in range(624):
+            s = (69069 * s + 1) & 0xFFFFFFFF
+            x.append(s)
+        for n in range(n_words - 624):
+            y = (x[n] & 0x80000000) | (x[n + 1] & 0x7FFFFFFF)
+            x.append(x[n + 397] ^ (y >> 1) ^ (0x9908B0DF if y & 1 else 0))
+        return np.array(x, dtype=np.uint32)
+
+    e = 624 * 40                                         # 40 chunks ahead
+    x = stream(3, e + 624 + 19937 + 8)
+    g = lib_poly(e - 1)
+    idx = np.array([i for i in range(19937) if (g >> i) & 1], dtype=np.int64)
+    js = np.arange(624)
+    win = np.bitwise_xor.reduce(x[idx[:, None] + js[None, :] + 1], axis=0)
+    np.testing.assert_array_equal(win, x[e:e + 624])
