@@ -147,6 +147,27 @@ typedef struct sqc_maha_args {
 SQC_API int sqc_outlier_maha(const sqc_maha_args* args, double* maha, uint8_t* outlier,
                      double* maha_cut, char* err, size_t errlen);
 
+/* ---- the step in front of the fit: .init_clusts (R/fit_sampleqc.R:277-331) --------------- */
+/* grp_medians (:286-289) of every sample and metric, and - when a mixture is given - the posterior and arg max of ALL
+ * N median-centred cells under it (what summaryMclustBIC(...)$z / $classification deliver, :303-316).  The fit of that
+ * mixture on the 1e4-cell subsample (mclust) stays with the caller.                                                  */
+typedef struct sqc_init_args {
+  uint32_t abi_version;
+  int32_t  D, J, K;          /* K is ignored when pro == NULL                                 */
+  int64_t  N;
+  const double*  x;          /* N x D column-major, un-centred                                */
+  const int32_t* groups;     /* N, 0-based, any order                                         */
+  const double*  pro;        /* K mixing proportions, or NULL: medians only                   */
+  const double*  mean;       /* K x D column-major                                            */
+  const double*  sigma;      /* D x D x K                                                     */
+  int32_t  device;
+} sqc_init_args;
+
+/* medians: J x D column-major (NaN for an empty sample); gamma: N x K column-major or NULL; z: N labels, 0-based
+ * (the first maximum of a row of gamma), or NULL                                                                    */
+SQC_API int sqc_init_clusts(const sqc_init_args* args, double* medians, double* gamma, int32_t* z,
+                    char* err, size_t errlen);
+
 /* ---- resident sessions (benchmarks, multi-GPU drivers) --------------------------------- */
 /* A session keeps the cell matrix resident in HBM so that the EM loop can be timed without the
  * host<->device copies, and exposes per-kernel device timings for the roofline report.       */

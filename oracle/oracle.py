@@ -132,3 +132,34 @@ def fast_mcd(xk, h, mcd_iters, seed):
     if st != 0:
         raise A.SampleQCError(st, err.value.decode(errors="replace"))
     return loc, scale, iters.value, q.value
+
+
+# ---- .init_clusts pieces (reference R/fit_sampleqc.R:277-331), plain numpy --------------------------------------
+def sample_medians(x, groups, J):
+    """grp_medians (:286-289): apply(x[groups == j, ], 2, median) for every sample; J x D"""
+    x = np.asarray(x, dtype=np.float64)
+    g = np.asarray(groups)
+    med = np.full((J, x.shape[1]), np.nan)
+    for j in range(J):
+        rows = x[g == j]
+        if rows.shape[0]:
+            med[j] = np.median(rows, axis=0)
+    return med
+
+
+def gmm_classify(x, groups, medians, pro, mean, sigma):
+    """posterior (mclust z) and its first maximum (classification - 1) of the median-centred cells (:290, :303-316);
+    mean K x D, sigma D x D x K"""
+    x = np.asarray(x, dtype=np.float64)
+    xc = x - np.asarray(medians)[np.asarray(groups)]
+    K, D = len(pro), x.shape[1]
+    mean = np.asarray(mean, dtype=np.float64).reshape(K, D)
+    sigma = np.asarray(sigma, dtype=np.float64).reshape(D, D, K, order="F")
+    ll = np.empty((x.shape[0], K))
+    for k in range(K):
+        L = np.linalg.cholesky(sigma[:, :, k])
+        w = np.linalg.solve(L, (xc - mean[k]).T)
+        ll[:, k] = np.log(pro[k]) - np.log(np.diag(L)).sum() - 0.5 * D * np.log(2.0 * np.pi) - 0.5 * (w * w).sum(axis=0)
+    m = ll.max(axis=1, keepdims=True)
+    e = np.exp(ll - m)
+    return e / e.sum(axis=1, keepdims=True), np.argmax(ll, axis=1).astype(np.int32)

@@ -86,6 +86,17 @@ class SqcMahaArgs(C.Structure):
     ]
 
 
+class SqcInitArgs(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_uint32),
+        ("D", C.c_int32), ("J", C.c_int32), ("K", C.c_int32),
+        ("N", C.c_int64),
+        ("x", c_double_p), ("groups", c_int32_p),
+        ("pro", c_double_p), ("mean", c_double_p), ("sigma", c_double_p),
+        ("device", C.c_int32),
+    ]
+
+
 class SqcRunStats(C.Structure):
     _fields_ = [
         ("n_iter", C.c_int32), ("n_gpu_launches", C.c_int32),

@@ -14,7 +14,7 @@ _LIB = None
 
 # every symbol include/sampleqc_cuda.h declares
 EXPORTS = (
-    "sqc_fit_robust", "sqc_fit_mle", "sqc_outlier_maha",
+    "sqc_fit_robust", "sqc_fit_mle", "sqc_outlier_maha", "sqc_init_clusts",
     "sqc_session_create", "sqc_session_run", "sqc_session_fetch", "sqc_session_stats", "sqc_session_profile",
     "sqc_session_destroy", "sqc_xchg_export", "sqc_xchg_release",
     "sqc_trim", "sqc_abi_version", "sqc_device_count", "sqc_status_name", "sqc_device_qchisq", "sqc_device_rkeys", "sqc_device_rkeys_share", "sqc_device_expneg", "sqc_mt_jump_poly",
@@ -37,6 +37,8 @@ def lib():
         f.restype = C.c_int
     L.sqc_outlier_maha.argtypes = [C.POINTER(A.SqcMahaArgs), A.c_double_p, A.c_uint8_p, A.c_double_p, C.c_char_p, C.c_size_t]
     L.sqc_outlier_maha.restype = C.c_int
+    L.sqc_init_clusts.argtypes = [C.POINTER(A.SqcInitArgs), A.c_double_p, A.c_double_p, A.c_int32_p, C.c_char_p, C.c_size_t]
+    L.sqc_init_clusts.restype = C.c_int
     L.sqc_session_create.argtypes = [fa, C.c_int, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]
     L.sqc_session_create.restype = C.c_int
     L.sqc_session_run.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]

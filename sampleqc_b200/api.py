@@ -73,6 +73,62 @@ def calc_outliers(x, groups, mu_0, alpha_j, beta_k, sigma_k, alpha=0.01, device=
     return maha, out.astype(bool), cut.value
 
 
+def sample_medians(x, groups, J, device=-1):
+    """grp_medians of .init_clusts (reference R/fit_sampleqc.R:286-289): J x D medians, computed on the device."""
+    xa = A.f64_colmajor(x)
+    N, D = xa.shape
+    ga = A.as_i32(groups)
+    a = A.SqcInitArgs()
+    a.abi_version, a.D, a.J, a.K, a.N = A.SQC_ABI_VERSION, D, J, 0, N
+    a.x, a.groups, a.device = A.ptr_d(xa), A.ptr_i(ga), int(device)
+    med = np.zeros((J, D), order="F")
+    err = C.create_string_buffer(512)
+    check(lib().sqc_init_clusts(C.byref(a), A.ptr_d(med), None, None, err, 512), err)
+    return med
+
+
+def gmm_classify(x, groups, J, pro, mean, sigma, want_gamma=True, device=-1):
+    """medians + classification of all cells under a mixture fitted on the median-centred subsample
+    (summaryMclustBIC(...)$z / $classification, reference R/fit_sampleqc.R:303-316).
+    mean: K x D, sigma: D x D x K.  Returns (medians J x D, gamma N x K or None, z 0-based int32)."""
+    xa = A.f64_colmajor(x)
+    N, D = xa.shape
+    ga = A.as_i32(groups)
+    pr = np.ascontiguousarray(np.asarray(pro, dtype=np.float64).reshape(-1))
+    K = pr.shape[0]
+    mu, sg = A.f64_colmajor(np.asarray(mean, dtype=np.float64).reshape(K, D)), A.f64_colmajor(sigma)
+    a = A.SqcInitArgs()
+    a.abi_version, a.D, a.J, a.K, a.N = A.SQC_ABI_VERSION, D, J, K, N
+    a.x, a.groups, a.pro, a.mean, a.sigma, a.device = A.ptr_d(xa), A.ptr_i(ga), A.ptr_d(pr), A.ptr_d(mu), A.ptr_d(sg), int(device)
+    med = np.zeros((J, D), order="F")
+    gamma = np.zeros((N, K), order="F") if want_gamma else None
+    z = np.zeros(N, dtype=np.int32)
+    err = C.create_string_buffer(512)
+    check(lib().sqc_init_clusts(C.byref(a), A.ptr_d(med), A.ptr_d(gamma) if want_gamma else None, A.ptr_i(z), err, 512), err)
+    return med, gamma, z
+
+
+def init_clusts(x, groups, J, K, N, fit_subsample, seed=0, n_sub=10_000, n_tries=5, device=-1):
+    """Mirror of .init_clusts (reference R/fit_sampleqc.R:277-331) with the O(N) work on the device.
+    `fit_subsample(x_sample_centred, K, attempt) -> (pro, mean K x D, sigma D x D x K)` is the caller's mixture fit on the
+    subsample (mclust "EVE" in the R package, :297-300).  Returns dict(init_gamma N x K, init_z 0-based)."""
+    if K == 1:                                                    # :279-283
+        return {"init_z": np.zeros(N, dtype=np.int32), "init_gamma": np.zeros((N, 1), order="F")}
+    xa = A.f64_colmajor(x)
+    ga = A.as_i32(groups)
+    rng = np.random.default_rng(seed)
+    med = sample_medians(xa, ga, J, device=device)                # :286-289
+    for attempt in range(n_tries):                                # :296-309
+        idx = rng.choice(N, size=min(N, n_sub), replace=False)
+        pro, mean, sigma = fit_subsample(xa[idx] - med[ga[idx]], K, attempt)
+        _, gamma, z = gmm_classify(xa, ga, J, pro, mean, sigma, device=device)
+        if np.unique(z).size == K:
+            return {"init_z": z, "init_gamma": gamma}
+    fake = np.exp(rng.standard_normal((N, K)))                    # random fallback, :318-326
+    gamma = np.asfortranarray(fake / fake.sum(axis=1, keepdims=True))
+    return {"init_z": np.argmax(gamma, axis=1).astype(np.int32), "init_gamma": gamma}
+
+
 class Session:
     """A resident fit: the cell matrix stays in HBM so the EM loop can be re-run and timed without the
     host<->device copies (sqc_session_* in include/sampleqc_cuda.h)."""

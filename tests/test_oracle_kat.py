@@ -146,3 +146,26 @@ def test_outlier_mask(oracle):
         np.testing.assert_allclose(maha[:, k], want, rtol=1e-10)
     np.testing.assert_array_equal(out, maha.min(axis=1) > cut)
     assert 0.0 < out.mean() < 0.5
+
+
+def test_init_clusts_oracle_pieces():
+    """numpy restatement of .init_clusts' O(N) pieces (reference R/fit_sampleqc.R:286-290, :303-316): medians as R's
+    median(), posterior against an independent implementation of the same mixture (sklearn)"""
+    from sklearn.mixture import GaussianMixture
+    from oracle import oracle as O
+    rng = np.random.default_rng(1)
+    x = rng.normal(size=(3001, 3)) * [1.0, 2.0, 0.5] + [3.0, 2.5, -3.0]
+    g = np.sort(rng.integers(0, 5, size=3001)).astype(np.int32)
+    med = O.sample_medians(x, g, 6)
+    assert np.isnan(med[5]).all()                                # no cells: median(numeric(0)) is NA
+    for j in range(5):
+        for d in range(3):
+            v = np.sort(x[g == j, d]); n = v.size
+            assert med[j, d] == (v[n // 2] if n % 2 else (v[n // 2 - 1] + v[n // 2]) / 2)
+    med5 = med[:5]
+    gm = GaussianMixture(3, covariance_type="full", random_state=0).fit(x - med5[g])
+    sigma = np.asfortranarray(np.transpose(gm.covariances_, (1, 2, 0)))
+    gamma, z = O.gmm_classify(x, g, med5, gm.weights_, gm.means_, sigma)
+    np.testing.assert_allclose(gamma, gm.predict_proba(x - med5[g]), rtol=1e-9, atol=1e-13)
+    np.testing.assert_array_equal(z, gm.predict(x - med5[g]))
+    np.testing.assert_allclose(gamma.sum(axis=1), 1.0, rtol=1e-14)
