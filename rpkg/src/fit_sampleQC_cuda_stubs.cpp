@@ -151,3 +151,26 @@ List calc_outliers_cuda(arma::mat x, arma::uvec groups, arma::vec mu_0, arma::ma
   for (int i = 0; i < N; ++i) outlier[i] = out[i] != 0;
   return List::create(Named("maha") = maha, Named("outlier") = outlier, Named("maha_cut") = cut);
 }
+
+// Optional accelerator for the O(N) parts of .init_clusts (reference R/fit_sampleqc.R:277-331): grp_medians (:286-289)
+// and — given the mixture mclust fitted on the 1e4-cell subsample — the posterior and classification of all N cells
+// (what summaryMclustBIC(...)$z / $classification deliver, :303-316).  pro: K, mean: K x D, sigma: D x D x K as
+// mclust's parameters$pro / t(parameters$mean) / parameters$variance$sigma.  Pass pro of length 0 for the medians only.
+// [[Rcpp::export]]
+List init_clusts_cuda(arma::mat x, arma::uvec groups, int J, arma::vec pro, arma::mat mean, arma::cube sigma) {
+  const int N = x.n_rows, D = x.n_cols, K = pro.n_elem;
+  std::vector<int32_t> g(N);
+  for (int i = 0; i < N; ++i) g[i] = (int32_t)groups(i) - 1;     // .init_clusts receives the 1-based groups
+  sqc_init_args a = {};
+  a.abi_version = SQC_ABI_VERSION; a.D = D; a.J = J; a.K = K; a.N = N;
+  a.x = x.memptr(); a.groups = g.data(); a.device = -1;
+  arma::mat medians(J, D), gamma;
+  std::vector<int32_t> z;
+  if (K > 0) { a.pro = pro.memptr(); a.mean = mean.memptr(); a.sigma = sigma.memptr(); gamma.set_size(N, K); z.resize(N); }
+  char err[512];
+  check_status(sqc_init_clusts(&a, medians.memptr(), K > 0 ? gamma.memptr() : nullptr, K > 0 ? z.data() : nullptr, err, sizeof err), err);
+  if (K == 0) return List::create(Named("grp_medians") = medians);
+  IntegerVector init_z(N);
+  for (int i = 0; i < N; ++i) init_z[i] = z[i];                   // 0-based, as init_z = classification - 1 (:314)
+  return List::create(Named("grp_medians") = medians, Named("init_gamma") = gamma, Named("init_z") = init_z);
+}
