@@ -304,19 +304,18 @@ def main():
         e2e = {"value": N_job * e2e_iters * n_e2e / float(te.item()), "unit": "cell-iters/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": 1e3 * float(te.item()) / n_e2e, "steps": n_e2e, "timer": "host wall clock around the blocking C-ABI call, max over ranks"}
 
+    if dist is not None:                                          # all ranks leave the group together
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
         return
     out = {"metric": METRIC, "value": value, "unit": "cell-iters/s", "n_gpus": world, "steps": a.steps, "warmup": n_warm,
            "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak" if (weak or world == 1) else "strong", "vs_baseline": None, "dtype": "f64",
            "data": "synthetic", "config": config, "em_iterations_per_step": n_iter, "clocks": clocks, "e2e": e2e,
            "gpu_launches": int(launches), "roofline": roofline}
-    if not a.no_cpu_baseline:
+    if not a.no_cpu_baseline and world == 1:                      # the CPU leg is reported at N = 1 only
         out["cpu_baseline"], _ = cpu_reference(x, groups, init_z, prm)
     print(json.dumps(out))
-    if dist is not None:
-        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
