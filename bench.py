@@ -129,6 +129,26 @@ def cpu_reference(x, groups, init_z, prm, budget_cells=1_000_000, em_iters=8):
                       "(the reference's src/ has no OpenMP pragma)"}, dt
 
 
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """stdout carries exactly ONE JSON line: anything libraries write to fd 1 (NCCL prints its version banner there
+    when a box-level nccl.conf asks for it) is sent to stderr instead; emit() writes to the real stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -143,6 +163,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     a = ap.parse_args()
+    guard_stdout()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     W = max(a.warmup, 0)
 
@@ -165,14 +186,12 @@ def main():
                 vals.append((cb, dt))
         v = float(np.mean([c["value"] for c, _ in vals]))
         cb = dict(vals[-1][0]); cb["value"] = v
-        print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "cell-iters/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": W,
+        emit(({"impl": "reference", "metric": METRIC, "value": v, "unit": "cell-iters/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": W,
                           "ms_per_step": 1e3 * float(np.mean([d for _, d in vals])), "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config, "cpu_baseline": cb,
                           "e2e": {"value": v, "unit": "cell-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
-    if os.environ.get("NCCL_DEBUG"):                              # (NCCL prints its version banner to stdout at WARN / VERSION / INFO)
-        os.environ["NCCL_DEBUG_FILE"] = os.environ.get("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
     import torch
     from sampleqc_b200 import api
     torch.cuda.set_device(local)
@@ -315,7 +334,7 @@ def main():
            "gpu_launches": int(launches), "roofline": roofline}
     if not a.no_cpu_baseline and world == 1:                      # the CPU leg is reported at N = 1 only
         out["cpu_baseline"], _ = cpu_reference(x, groups, init_z, prm)
-    print(json.dumps(out))
+    emit(out)
 
 
 if __name__ == "__main__":
