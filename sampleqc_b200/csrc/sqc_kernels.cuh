@@ -146,7 +146,7 @@ template <int D> __device__ __forceinline__ double maha_tri(const double (&v)[D]
 // Statistics per tile: n_k (int) and sum_k x (D doubles) -> reduced per sample by k_post_stats.
 // ---------------------------------------------------------------------------------------------
 template <int D, int MODE>
-__global__ void __launch_bounds__(EST_THREADS, SQC_EST_MINB) k_estep(Dev s) {
+__global__ void __launch_bounds__(EST_THREADS, (D <= 4) ? SQC_EST_MINB : 2) k_estep(Dev s) {        // D > 4: 2 CTAs / 128 registers (no spills), measured on C4
   constexpr int CPT = TileCfg<D>::CPT, SZ = ParK<D>::SZ, NW = EST_THREADS / 32;
   extern __shared__ double sh_dyn[];
   double* sh_par = sh_dyn;                                   // K * SZ
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(EST_THREADS, SQC_EST_MINB) k_estep(Dev s) {
 //   LIKE = 1: also the log-likelihood with the new alpha_j and the previous beta/Sigma/p_jk (:499).
 // ---------------------------------------------------------------------------------------------
 template <int D, int LIKE>
-__global__ void __launch_bounds__(EST_THREADS, SQC_PART_MINB) k_partition(Dev s) {
+__global__ void __launch_bounds__(EST_THREADS, (D <= 4) ? SQC_PART_MINB : 3) k_partition(Dev s) {   // D > 4: 3 CTAs / 80 registers, measured on C4
   constexpr int CPT = TileCfg<D>::CPT, SZ = ParK<D>::SZ, NW = EST_THREADS / 32;
   extern __shared__ double sh_dyn[];
   double* sh_par = sh_dyn;                                   // K * SZ
