@@ -183,3 +183,18 @@ def test_mt_jump_polynomials_move_the_state(tmp_path):
     js = np.arange(624)
     win = np.bitwise_xor.reduce(x[idx[:, None] + js[None, :] + 1], axis=0)
     np.testing.assert_array_equal(win, x[e:e + 624])
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): exactly one JSON line on stdout with the
+    contract's keys; here on the small C1 workload"""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "C1", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "EM cell-iters/s" and d["unit"] == "cell-iters/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
