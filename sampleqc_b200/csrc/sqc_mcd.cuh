@@ -12,15 +12,17 @@
 //   COLLECT  cells strictly under the bin that holds the h-th smallest key are accumulated into
 //            shifted moments (count, sum, upper-triangular scatter); the cells of that one bin are
 //            appended, without atomics, to per-warp candidate regions (deterministic order).  The
-//            cluster's leader CTA bins the candidates once more (4096 fine bins inside the bin), takes
+//            cluster's leader CTA bins the candidates once more (1024 fine bins inside the bin), takes
 //            every candidate under the fine bin that holds the h-th key, and sorts only the handful
 //            inside it by (key, rank, position) — ties resolved towards the lower cell index, the repo's
 //            definition of the reference's unspecified tie order.
 // Multi-GPU (cells sharded by sample): the leaders of all ranks exchange the histogram, the fine
-// histogram, the tie candidates and the moments through peer memory (sqc_xchg.cuh) and combine them
-// in rank order, so every rank walks through bit-identical cluster states.
+// histogram and then ONE message with their moments and tie candidates through peer memory
+// (sqc_xchg.cuh) and combine them in rank order, so every rank walks through bit-identical cluster
+// states; R-compatible keys are read from the rank that generated them (NVLink).
 // A cluster walks through  KEY_HIST -> KEY_COLLECT -> [DIST_HIST -> DIST_COLLECT]* -> final
-// DIST_HIST -> DIST_COLLECT(q only) -> DONE; all clusters share every streaming round.
+// DIST_HIST -> DIST_COLLECT(q only) -> DONE; a HIST round is skipped ("direct" COLLECT) when the
+// threshold can be predicted well enough (random-key start, settled C-steps).
 // Dataflow, no grid-wide barriers: CTAs 0 .. K-1 are the cluster LEADERS, the others are WORKERS.  Leader k publishes
 // the state of its cluster under an epoch number; every worker streams its static share of the cluster's chunks
 // whenever it sees a new epoch, flushes (histogram / moment partials / candidates) and arrives on a counter;
