@@ -44,6 +44,19 @@ def main():
         np.savez_compressed(os.path.join(HERE, name + ".npz"), x=sim.x, groups=sim.groups, init_gamma=ig,
                             params=np.array([N, J, K, D, it]), **{"fit_" + k: v for k, v in fit.items()})
         print(name)
+    # .init_clusts pieces (reference R/fit_sampleqc.R:286-316): per-sample medians, posterior and classification of
+    # all cells under a mixture fitted on a subsample; the mixture's parameters are stored (no sklearn at test time)
+    from sklearn.mixture import GaussianMixture
+    for name, (N, J, Kt, K, D, ds) in {"init_k4": (6000, 11, 4, 4, 3, 107), "init_d6_k3": (4000, 5, 3, 3, 6, 108)}.items():
+        sim = simulate_qcs(N, J, Kt, D, seed=ds)
+        med = O.sample_medians(sim.x, sim.groups, J)
+        idx = np.random.default_rng(ds).choice(N, 1500, replace=False)
+        gm = GaussianMixture(K, covariance_type="full", random_state=ds).fit(sim.x[idx] - med[sim.groups[idx]])
+        sigma = np.asfortranarray(np.transpose(gm.covariances_, (1, 2, 0)))
+        gamma, z = O.gmm_classify(sim.x, sim.groups, med, gm.weights_, gm.means_, sigma)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), x=sim.x, groups=sim.groups, params=np.array([N, J, K, D]),
+                            pro=gm.weights_, mean=gm.means_, sigma=sigma, medians=med, gamma=gamma, z=z)
+        print(name)
 
 
 if __name__ == "__main__":

@@ -6,7 +6,9 @@ import os
 import numpy as np
 import pytest
 
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+ALL = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLD = [p for p in ALL if not os.path.basename(p).startswith("init_")]          # fits
+GOLD_INIT = [p for p in ALL if os.path.basename(p).startswith("init_")]         # .init_clusts pieces
 KEYS_R = ("mu_0", "alpha_j", "beta_k", "sigma_k", "p_jk", "like_1", "like_2")
 
 
@@ -56,6 +58,31 @@ def test_cuda_reproduces_golden(path):
         np.testing.assert_array_equal(got["rng_state"], want["rng_state"])      # R's .Random.seed after the fit
 
 
+@pytest.mark.parametrize("path", GOLD_INIT, ids=[os.path.basename(p)[:-4] for p in GOLD_INIT])
+def test_oracle_reproduces_golden_init(oracle, path):
+    d = np.load(path)
+    N, J, K, D = [int(v) for v in d["params"]]
+    med = oracle.sample_medians(d["x"], d["groups"], J)
+    np.testing.assert_array_equal(med, d["medians"])
+    gamma, z = oracle.gmm_classify(d["x"], d["groups"], med, d["pro"], d["mean"], d["sigma"])
+    np.testing.assert_allclose(gamma, d["gamma"], rtol=1e-12, atol=1e-300)
+    np.testing.assert_array_equal(z, d["z"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", GOLD_INIT, ids=[os.path.basename(p)[:-4] for p in GOLD_INIT])
+def test_cuda_reproduces_golden_init(path):
+    from sampleqc_b200 import api
+    d = np.load(path)
+    N, J, K, D = [int(v) for v in d["params"]]
+    med, gamma, z = api.gmm_classify(np.asfortranarray(d["x"]), d["groups"], J, d["pro"], d["mean"], np.asfortranarray(d["sigma"]))
+    np.testing.assert_array_equal(med, d["medians"])                            # medians: bit-exact
+    np.testing.assert_allclose(gamma, d["gamma"], rtol=1e-10, atol=1e-14)
+    top2 = np.sort(d["gamma"], axis=1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-9
+    np.testing.assert_array_equal(z[clear], d["z"][clear])
+
+
 def test_fixture_set_is_complete():
-    names = {os.path.basename(p)[:-4] for p in GOLD}
-    assert {"robust_toy_k2", "robust_k4_track", "robust_d6_k3", "robust_k1", "mle_k3", "mle_d6_k2"} <= names
+    names = {os.path.basename(p)[:-4] for p in ALL}
+    assert {"robust_toy_k2", "robust_k4_track", "robust_d6_k3", "robust_k1", "mle_k3", "mle_d6_k2", "init_k4", "init_d6_k3"} <= names
