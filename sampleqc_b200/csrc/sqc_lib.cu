@@ -248,7 +248,7 @@ struct sqc_session {
   unsigned long long* xg_gather = nullptr; double* xg_vec = nullptr;
   uint32_t* mt_state = nullptr; uint32_t* mt_seq = nullptr; uint32_t* mt_table = nullptr; int* keybuf = nullptr;
   // distributed key stream (multi-GPU, R-compatible keys): this rank generates draws [rank * key_q, (rank + 1) * key_q) of every call
-  long long key_q = 0, key_mine = 0; uint32_t* mt_rows = nullptr; uint32_t* mt_jwin = nullptr; uint32_t* mt_seq2 = nullptr; const int* key_peer[XCHG_MAX_WORLD] = {};
+  long long key_q = 0, key_mine = 0; uint32_t* mt_rows = nullptr; uint32_t* mt_jwin = nullptr; uint32_t* mt_seq2 = nullptr; const int* key_peer[XCHG_MAX_WORLD] = {}; void* key_mapped[XCHG_MAX_WORLD] = {};
   double* o_buf = nullptr; int* o_z = nullptr; int* o_korder = nullptr; OutPtrs optr{};
   size_t o_doubles = 0;
   int mcd_grid = 0, n_sm = 0;
@@ -276,8 +276,11 @@ struct sqc_session {
   }
   ~sqc_session() {
     if (device >= 0) cudaSetDevice(device);
-    xchg_close(xc);
     if (st) cudaStreamSynchronize(st);
+    if (st_rng) cudaStreamSynchronize(st_rng);
+    if (st_rng2) cudaStreamSynchronize(st_rng2);
+    for (int q = 0; q < XCHG_MAX_WORLD; ++q) if (key_mapped[q]) { cudaIpcCloseMemHandle(key_mapped[q]); key_mapped[q] = nullptr; }
+    xchg_close(xc);
     for (auto& c : chunks) g_chunks.give(device, c);
     for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     if (ev_run0) cudaEventDestroy(ev_run0);
@@ -686,8 +689,6 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
 // buffers' IPC handles travel through the exchange window itself, so the C ABI is unchanged.
 struct KeyBufLocal { int* p = nullptr; size_t ints = 0; };
 KeyBufLocal& key_buf_local(int device) { static KeyBufLocal b[64]; return b[device & 63]; }
-struct HandleKey { unsigned char b[64]; bool operator<(const HandleKey& o) const { return memcmp(b, o.b, 64) < 0; } };
-std::map<HandleKey, void*>& key_peer_maps(int device) { static std::map<HandleKey, void*> m[64]; return m[device & 63]; }
 
 void key_stream_setup(sqc_session* S) {
   const int W = S->world, r = S->rank;
@@ -712,19 +713,13 @@ void key_stream_setup(sqc_session* S) {
   std::vector<unsigned char> hs((size_t)64 * W);
   CK(cudaMemcpyAsync(hs.data(), d_out, hs.size(), cudaMemcpyDeviceToHost, S->st));
   CK(cudaStreamSynchronize(S->st));
-  auto& maps = key_peer_maps(S->device);
-  for (int q = 0; q < W; ++q) {
+  for (int q = 0; q < W; ++q) {                                   // mapped for the life of the session (closed in its destructor)
     if (q == r) { S->key_peer[q] = kb.p; continue; }
-    HandleKey hk; memcpy(hk.b, hs.data() + (size_t)64 * q, 64);
-    auto it = maps.find(hk);
-    if (it == maps.end()) {
-      cudaIpcMemHandle_t ph; memcpy(&ph, hk.b, 64);
-      void* p = nullptr;
-      cudaError_t e = cudaIpcOpenMemHandle(&p, ph, cudaIpcMemLazyEnablePeerAccess);
-      if (e != cudaSuccess) fail(SQC_ERR_COMM, "cudaIpcOpenMemHandle (key buffer of rank %d) failed: %s", q, cudaGetErrorString(e));
-      it = maps.emplace(hk, p).first;
-    }
-    S->key_peer[q] = (const int*)it->second;
+    cudaIpcMemHandle_t ph; memcpy(&ph, hs.data() + (size_t)64 * q, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, ph, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) fail(SQC_ERR_COMM, "cudaIpcOpenMemHandle (key buffer of rank %d) failed: %s", q, cudaGetErrorString(e));
+    S->key_mapped[q] = p; S->key_peer[q] = (const int*)p;
   }
   // jump polynomials: row 0 = call to call (floor(N_total / 624) chunks), row 1 = start of the call to this rank's share
   static std::map<unsigned long long, std::vector<uint32_t>> rows;      // derived once per distance
