@@ -326,6 +326,7 @@ def main():
             roofline["traffic"] = json.load(open(tr)).get(top)
         except Exception:
             pass
+    resident_fit = sess.fetch()                                   # outside the timed region: for the validity checks below
     sess.close()
 
     # ---- e2e: the reference-facing call with pinned host buffers -------------------------------------
@@ -377,6 +378,20 @@ def main():
         e2e = {"value": N_job * e2e_iters * n_e2e / float(te.item()), "unit": "cell-iters/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": 1e3 * float(te.item()) / n_e2e, "steps": n_e2e, "timer": "host wall clock around the blocking C-ABI call, max over ranks"}
 
+    # ---- validity of what was timed (size-independent properties; rank 0's shard) ---------------------
+    checks = None
+    try:
+        f = resident_fit
+        checks = {"n_iter": int(f["n_iter"]), "z_in_1..K": bool(f["z"].min() >= 1 and f["z"].max() <= K),
+                  "p_jk_rows_sum_to_1": bool(np.allclose(f["p_jk"].sum(axis=1), 1.0, rtol=0, atol=1e-12)),
+                  "beta_k_col0_ascending": bool(np.all(np.diff(f["beta_k"][:, 0]) >= 0)),                # final relabel, :527-559
+                  "sigma_k_spd": bool(all(np.all(np.linalg.eigvalsh(f["sigma_k"][:, :, k]) > 0) for k in range(K))),
+                  "params_finite": bool(all(np.all(np.isfinite(f[k])) for k in ("mu_0", "alpha_j", "beta_k", "sigma_k", "p_jk")))}
+        if e2e is not None:                                       # the resident run and the host-buffer run are the same fit, bit for bit
+            checks["resident_equals_e2e_bitwise"] = bool(all(np.array_equal(f[k], fit[k]) for k in ("mu_0", "alpha_j", "beta_k", "sigma_k", "p_jk", "z")))
+    except Exception as ex:                                       # never lose the measurement over a check
+        checks = {"error": repr(ex)}
+
     if dist is not None:                                          # all ranks leave the group together
         dist.barrier()
         dist.destroy_process_group()
@@ -385,7 +400,7 @@ def main():
     out = {"metric": METRIC, "value": value, "unit": "cell-iters/s", "n_gpus": world, "steps": a.steps, "warmup": n_warm,
            "ms_per_step": dev_ms / a.steps, "higher_is_better": True, "scaling": "weak" if (weak or world == 1) else "strong", "vs_baseline": None, "dtype": "f64",
            "data": "synthetic", "config": config, "em_iterations_per_step": n_iter, "clocks": clocks, "e2e": e2e,
-           "gpu_launches": int(launches), "roofline": roofline}
+           "gpu_launches": int(launches), "roofline": roofline, "checks": checks}
     if not a.no_cpu_baseline and world == 1:                      # the CPU leg is reported at N = 1 only
         out["cpu_baseline"], _ = cpu_reference(x, groups, init_z, prm)
         out["cpu_baseline"]["note"] = "one single-threaded fit (the reference has no threads inside a fit); `--impl reference` runs one such fit per host core"
