@@ -12,10 +12,15 @@ ok = True
 CASES = [(40000, 12, 4, 4, 3, 12, 0), (200000, 31, 4, 3, 3, 10, 1), (1_000_000, 100, 4, 4, 3, 8, 0), (3_000_001, 150, 4, 4, 3, 4, 0)]
 if os.environ.get("MGPU_QUICK"):
     CASES = CASES[:2]
-for (N, J, Kt, K, D, em, rng) in CASES:
+CASES.append((60_000, 10, 4, 4, 3, 6, 0, "absent"))      # one cluster has no cell at all on the last rank in the first M-step
+for case in CASES:
+    (N, J, Kt, K, D, em, rng), tag = case[:7], (case[7] if len(case) > 7 else "")
     sim = simulate_qcs(N, J, Kt, D, seed=7)
     iz, ig = init_clusts(sim.x, sim.groups, J, K, seed=7)
     j0, j1, i0, i1 = multigpu.shard_by_sample(sim.groups, J, world)[rank]
+    if tag == "absent":
+        lo = multigpu.shard_by_sample(sim.groups, J, world)[world - 1][2]
+        iz = iz.copy(); iz[lo:][iz[lo:] == K - 1] = K - 2
     xs = np.asfortranarray(sim.x[i0:i1]); gs = (sim.groups[i0:i1] - j0).astype(np.int32)
     t0 = time.time()
     loc = multigpu.fit_robust_sharded(dist, local, rank, world, xs, iz[i0:i1], gs, D, j1 - j0, K, i1 - i0, i0, N, em, 0.5, 50, 0, rng_mode=rng)
@@ -25,7 +30,7 @@ for (N, J, Kt, K, D, em, rng) in CASES:
         from oracle import oracle as O
         ref = O.fit_sampleqc_robust_cpp(sim.x, iz, sim.groups, D, J, K, N, em, 0.5, 50, 0, rng_mode=rng)
         one = api.fit_sampleqc_robust_cpp(sim.x, iz, sim.groups, D, J, K, N, em, 0.5, 50, 0, rng_mode=rng, device=local)
-        print(f"robust N={N} world={world} rng={rng}: {t1-t0:.3f}s n_iter {full['n_iter']} / {ref['n_iter']} / {one['n_iter']}")
+        print(f"robust N={N} world={world} rng={rng} {tag}: {t1-t0:.3f}s n_iter {full['n_iter']} / {ref['n_iter']} / {one['n_iter']}")
         for key in ("mu_0", "alpha_j", "beta_k", "sigma_k", "p_jk", "like_1", "like_2"):
             fin = np.isfinite(ref[key])                  # plain densities may underflow: log 0 = -inf on both sides
             assert np.array_equal(fin, np.isfinite(full[key]))
