@@ -682,176 +682,7 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
   return up.release();
 }
 
-// ---- distributed key stream (multi-GPU, SQC_RNG_R_COMPAT) --------------------------------------------------------
-// R's stream is one sequence, so a call's N_total keys cost every rank O(N_total) when each generates them all.
-// Instead rank r generates draws [r Q, (r + 1) Q) of every call into a buffer the peers map (cudaIpc), and the M-step
-// kernel reads a cell's key from its owner over NVLink (4 B per cell in the one or two key rounds of a call).  The
-// buffers' IPC handles travel through the exchange window itself, so the C ABI is unchanged.
-struct KeyBufLocal { int* p = nullptr; size_t ints = 0; };
-KeyBufLocal& key_buf_local(int device) { static KeyBufLocal b[64]; return b[device & 63]; }
-
-void key_stream_setup(sqc_session* S) {
-  const int W = S->world, r = S->rank;
-  if (!mtpoly::self_check()) fail(SQC_ERR_COMM, "distributed key stream: jump polynomial derivation failed its self-check");
-  const long long per = (S->N_total + W - 1) / W;
-  S->key_q = ((per + MT_N - 1) / MT_N) * MT_N;
-  S->key_mine = std::max<long long>(0, std::min<long long>(S->key_q, S->N_total - (long long)r * S->key_q));
-  // own buffer (two calls in flight), kept per device for the life of the process: its IPC handle stays valid
-  KeyBufLocal& kb = key_buf_local(S->device);
-  if (kb.ints < 2 * (size_t)S->key_q) {
-    if (kb.p) { CK(cudaDeviceSynchronize()); cudaFree(kb.p); kb.p = nullptr; kb.ints = 0; }
-    CK(cudaMalloc((void**)&kb.p, 2 * (size_t)S->key_q * sizeof(int)));
-    kb.ints = 2 * (size_t)S->key_q;
-  }
-  S->keybuf = kb.p;
-  cudaIpcMemHandle_t h;
-  if (cudaIpcGetMemHandle(&h, kb.p) != cudaSuccess) fail(SQC_ERR_COMM, "cudaIpcGetMemHandle (key buffer) failed");
-  // all-gather of the 64-byte handles through the window
-  unsigned long long* d_in = S->alloc<unsigned long long>(8); unsigned long long* d_out = S->alloc<unsigned long long>(8 * XCHG_MAX_WORLD);
-  CK(cudaMemcpyAsync(d_in, &h, 64, cudaMemcpyHostToDevice, S->st));
-  k_xchg_gather_u64<<<1, 256, 0, S->st>>>(S->xc.dev, XCHG_CH_HOST + 0, d_in, d_out, 8, nullptr);
-  std::vector<unsigned char> hs((size_t)64 * W);
-  CK(cudaMemcpyAsync(hs.data(), d_out, hs.size(), cudaMemcpyDeviceToHost, S->st));
-  CK(cudaStreamSynchronize(S->st));
-  for (int q = 0; q < W; ++q) {                                   // mapped for the life of the session (closed in its destructor)
-    if (q == r) { S->key_peer[q] = kb.p; continue; }
-    cudaIpcMemHandle_t ph; memcpy(&ph, hs.data() + (size_t)64 * q, 64);
-    void* p = nullptr;
-    cudaError_t e = cudaIpcOpenMemHandle(&p, ph, cudaIpcMemLazyEnablePeerAccess);
-    if (e != cudaSuccess) fail(SQC_ERR_COMM, "cudaIpcOpenMemHandle (key buffer of rank %d) failed: %s", q, cudaGetErrorString(e));
-    S->key_mapped[q] = p; S->key_peer[q] = (const int*)p;
-  }
-  // jump polynomials: row 0 = call to call (floor(N_total / 624) chunks), row 1 = start of the call to this rank's share
-  static std::map<unsigned long long, std::vector<uint32_t>> rows;      // derived once per distance
-  auto row = [&](unsigned long long words) -> const std::vector<uint32_t>& {
-    auto it = rows.find(words);
-    if (it == rows.end()) { std::vector<uint32_t> v(MT_N); mtpoly::xpow(words - 1ull, v.data()); it = rows.emplace(words, std::move(v)).first; }
-    return it->second;
-  };
-  S->mt_rows = S->alloc<uint32_t>(2 * MT_N); S->mt_jwin = S->alloc<uint32_t>(2 * MT_N); S->mt_seq2 = S->alloc<uint32_t>(MT_SEQ_WORDS + 64);
-  if (getenv("SQC_RNG_INLINE") && atoi(getenv("SQC_RNG_INLINE"))) S->st_rng2 = S->st;
-  else CK(cudaStreamCreateWithFlags(&S->st_rng2, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; ++i) CK(cudaEventCreateWithFlags(&S->ev_chain[i], cudaEventDisableTiming));
-  CK(cudaEventCreateWithFlags(&S->ev_post_mcd, cudaEventDisableTiming));
-  CK(cudaMemcpyAsync(S->mt_rows, row((unsigned long long)(S->N_total / MT_N) * MT_N).data(), MT_N * sizeof(uint32_t), cudaMemcpyHostToDevice, S->st));
-  if (r > 0 && S->key_mine > 0)
-    CK(cudaMemcpyAsync(S->mt_rows + MT_N, row((unsigned long long)r * (unsigned long long)S->key_q).data(), MT_N * sizeof(uint32_t), cudaMemcpyHostToDevice, S->st));
-  CK(cudaStreamSynchronize(S->st));                                      // the rows live in a static map, but keep the copies simple
-  CK(cudaFuncSetAttribute(k_mt_jump_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_SMEM));
-}
-
-// n keys of R's stream: reads the state st_in (625 words), leaves the state after the n draws in st_out.
-// Waves of at most SQC_MT_JUMP_ROWS + 1 blocks; each wave = one sequential 33-chunk kernel + one
-// block-parallel kernel; tmp[2] hold the states between waves.
-void mt_generate(cudaStream_t stream, const uint32_t* st_in, uint32_t* st_out, uint32_t* tmp0, uint32_t* tmp1, uint32_t* seq,
-                 const uint32_t* table, int* out, long long n, const Control* ctl, sqc_session* S, int target_blocks = 49) {
-  long long done = 0; int w = 0;
-  const uint32_t* cur = st_in;
-  if (n <= 0) { CK(cudaMemcpyAsync(st_out, st_in, 625 * sizeof(uint32_t), cudaMemcpyDeviceToDevice, stream)); return; }
-  // block length = mult * 110 chunks; a wave serves up to 148 / mult + 1 blocks.  Longer blocks need fewer GF(2)
-  // correlations (the expensive part, which competes with the E-step for the SMs) at the price of a longer
-  // sequential tail; measured best at C3: ~49 blocks of 330 chunks (mult = 3).  Never more than 3: the generation
-  // of one call has to fit beside one EM iteration.  target_blocks >= 146 asks for the shortest blocks.
-  int mult = 1;
-  if (target_blocks < SQC_MT_JUMP_ROWS - 2) {
-    mult = (int)std::max<long long>(1, (n / MT_BLOCK_WORDS + target_blocks / 2) / target_blocks);
-    if (S) mult = std::min(mult, 3);
-    mult = std::min(mult, SQC_MT_JUMP_ROWS / 2);
-  }
-  const long long blk_words = MT_BLOCK_WORDS * mult;
-  const long long wave_words = (long long)(SQC_MT_JUMP_ROWS / mult + 1) * blk_words;
-  while (done < n) {
-    const long long m = std::min(n - done, wave_words - MT_N);     // a wave serves this many draws whatever mti is
-    const bool last = done + m >= n;
-    uint32_t* nxt = last ? st_out : ((w & 1) ? tmp1 : tmp0);
-    const int nb = (int)((MT_N + m + blk_words - 1) / blk_words);  // upper bound on the blocks touched (mti <= 624)
-    if (S) { Launch L(S, SQC_KF_RNG, stream, "seq"); k_mt_seq<<<1, 256, 0, stream>>>(cur, seq, ctl); L.done(); }
-    else k_mt_seq<<<1, 256, 0, stream>>>(cur, seq, ctl);
-    uint32_t* windows = seq + MT_SEQ_WORDS;                        // (SQC_MT_JUMP_ROWS + 1) x 624 behind the sequence
-    if (nb > 1) {
-      if (S) { Launch L(S, SQC_KF_RNG, stream, "jump"); k_mt_jump<<<nb - 1, MT_JUMP_THREADS, MT_SMEM, stream>>>(cur, seq, table, windows, m, mult, ctl); L.done(); }
-      else k_mt_jump<<<nb - 1, MT_JUMP_THREADS, MT_SMEM, stream>>>(cur, seq, table, windows, m, mult, ctl);
-    }
-    if (S) { Launch L(S, SQC_KF_RNG, stream, "gen"); k_mt_gen<<<nb, MT_GEN_THREADS, 0, stream>>>(cur, nxt, seq, windows, out + done, m, mult, ctl); L.done(); }
-    else k_mt_gen<<<nb, MT_GEN_THREADS, 0, stream>>>(cur, nxt, seq, windows, out + done, m, mult, ctl);
-    cur = nxt; done += m; ++w;
-  }
-}
-
-// Keys of update_beta_scale_k call `call` (every call consumes exactly N_total draws).
-// They do not depend on the data, so they are produced on a side stream, up to two calls ahead of the EM
-// loop; state_after[c] lives in slot c % 3 so that the state after the last EXECUTED call survives.
-void enqueue_keys(sqc_session* S, int call, cudaEvent_t after) {
-  if (S->rng_mode != SQC_RNG_R_COMPAT) return;
-  const int kb = call & 1;
-  // the buffer of call was last read by the M-step of call - 2 (key_free), and the generation is meant to run beside
-  // the M-step kernel of call - 1, which leaves room for it (`after` is recorded right before that launch)
-  CK(cudaStreamWaitEvent(S->st_rng, S->ev_key_free[kb], 0));
-  if (after) CK(cudaStreamWaitEvent(S->st_rng, after, 0));
-  uint32_t* base = S->mt_state;
-  if (S->key_q) {
-    // distributed stream: only this rank's share, from the state enqueue_chain left in slot 5 + (call & 1)
-    CK(cudaStreamWaitEvent(S->st_rng, S->ev_chain[kb], 0));
-    if (S->key_mine > 0)
-      mt_generate(S->st_rng, base + 640 * (5 + kb), base + 640 * 7, base + 640 * 3, base + 640 * 4, S->mt_seq, S->mt_table,
-                  S->keybuf + (size_t)kb * S->key_q, S->key_mine, S->dev.ctl, S, S->mt_target_blocks);
-  } else
-  mt_generate(S->st_rng, base + 640 * ((call + 2) % 3), base + 640 * (call % 3), base + 640 * 3, base + 640 * 4, S->mt_seq, S->mt_table,
-              S->keybuf + (size_t)kb * S->N_total, S->N_total, S->dev.ctl, S, S->mt_target_blocks);
-  CK(cudaEventRecord(S->ev_key_ready[kb], S->st_rng));
-}
-// distributed stream: the state in front of `call` (slot (call + 2) % 3) -> the state after it (slot call % 3) and the
-// state in front of this rank's share (slot 5 + (call & 1)), by jump polynomials.  Data-independent and tiny (one or
-// two CTAs, but ~0.2 ms of latency), so it runs on its own stream one call ahead of the generation.
-void enqueue_chain(sqc_session* S, int call, cudaEvent_t after) {
-  uint32_t* base = S->mt_state;
-  if (after) CK(cudaStreamWaitEvent(S->st_rng2, after, 0));
-  const uint32_t* in = base + 640 * ((call + 2) % 3);
-  const bool has_rank = S->rank > 0 && S->key_mine > 0;
-  { Launch L(S, SQC_KF_RNG, S->st_rng2, "chain_seq"); k_mt_seq<<<1, 256, 0, S->st_rng2>>>(in, S->mt_seq2, S->dev.ctl); L.done(); }
-  { Launch L(S, SQC_KF_RNG, S->st_rng2, "chain_jump"); k_mt_jump_rows<<<has_rank ? 2 : 1, MT_JUMP_THREADS, MT_SMEM, S->st_rng2>>>(S->mt_seq2, S->mt_rows, S->mt_jwin, S->dev.ctl); L.done(); }
-  { Launch L(S, SQC_KF_RNG, S->st_rng2, "chain_fix"); k_mt_fix<<<1, 256, 0, S->st_rng2>>>(in, S->mt_jwin, base + 640 * (call % 3), base + 640 * (5 + (call & 1)), S->N_total, has_rank ? 1 : 0, S->dev.ctl); L.done(); }
-  CK(cudaEventRecord(S->ev_chain[call & 1], S->st_rng2));
-}
-void enqueue_next_keys(sqc_session* S, int call) {
-  if (S->rng_mode != SQC_RNG_R_COMPAT || call + 1 > S->em_iters) return;
-  CK(cudaEventRecord(S->ev_pre_mcd, S->st));
-  enqueue_keys(S, call + 1, S->ev_pre_mcd);
-}
-void use_keys(sqc_session* S, int call) {
-  if (S->rng_mode == SQC_RNG_R_COMPAT) {
-    CK(cudaStreamWaitEvent(S->st, S->ev_key_ready[call & 1], 0));
-    if (S->key_q) {
-      // every rank's share of this call must be complete before any rank's M-step kernel reads it: one tiny exchange
-      // behind the wait orders them (the peers' reads end before this kernel's last exchange of the call, so the
-      // buffer may be refilled once the kernel is done - the same event that frees it locally)
-      { Launch L(S, SQC_KF_UPDATE, nullptr, "key_fence"); k_xchg_sum_f64<<<1, 32, 0, S->st>>>(S->xc.dev, XCHG_CH_HOST + 0, S->xg_vec + 8, 1, &S->dev.ctl->cont); L.done(); }
-      S->mb.keys = S->keybuf + (size_t)(call & 1) * S->key_q;
-      for (int q = 0; q < S->world; ++q) S->mb.key_peer[q] = S->key_peer[q] + (size_t)(call & 1) * S->key_q;
-      S->mb.key_q = S->key_q; S->mb.key_qinv = 1.0 / (double)S->key_q;
-    } else
-    S->mb.keys = S->keybuf + (size_t)(call & 1) * S->N_total;
-    // the keys of the NEXT call are generated while this call's M-step kernel runs (released only now: kernels that
-    // slip onto the SMs during a wait above would hold up the cooperative launch that follows)
-    if (!S->rng_after_mcd) enqueue_next_keys(S, call);
-  } else S->mb.keys = nullptr;
-  S->mb.call_mix = counter_call_mix(S->seed, 0u);
-  S->mb.stream_base = (long long)call * S->N_total;
-}
-// behind the M-step kernel: the state chain of call + 2 (tiny; a CTA of it in front of the cooperative launch would
-// delay that launch by its whole 0.15 ms)
-void after_mcd_keys(sqc_session* S, int call) {
-  if (S->rng_mode != SQC_RNG_R_COMPAT) return;
-  if (S->rng_after_mcd) enqueue_next_keys(S, call);
-  if (S->key_q && call + 2 <= S->em_iters) {
-    CK(cudaEventRecord(S->ev_post_mcd, S->st));
-    enqueue_chain(S, call + 2, S->ev_post_mcd);             // its share-state slot was last read by the keys of `call`
-  }
-}
-void release_keys(sqc_session* S, int call) {
-  if (S->rng_mode != SQC_RNG_R_COMPAT) return;
-  CK(cudaEventRecord(S->ev_key_free[call & 1], S->st));
-}
+#include "sqc_keys_host.inl"
 
 void run_robust(sqc_session* S) {
   Dev& s = S->dev;
@@ -1112,84 +943,7 @@ int sqc_outlier_maha(const sqc_maha_args* a, double* maha, uint8_t* outlier, dou
   }, err, errlen);
 }
 
-// .init_clusts on the device (R/fit_sampleqc.R:277-331): per-sample medians, then (optionally) the classification of
-// all cells under the mixture the caller fitted on its subsample
-int sqc_init_clusts(const sqc_init_args* a, double* medians, double* gamma, int32_t* z, char* err, size_t errlen) {
-  return guarded([&] {
-    if (!a || !a->x || !a->groups || !medians) fail(SQC_ERR_BAD_ARG, "null input");
-    if (a->abi_version != SQC_ABI_VERSION) fail(SQC_ERR_BAD_ARG, "ABI version mismatch");
-    const int D = a->D, J = a->J; const long long N = a->N;
-    const bool classify = a->pro != nullptr;
-    const int K = classify ? a->K : 0;
-    if (D < 1 || D > SQC_MAXD || J < 1 || N < 1 || (classify && (K < 1 || K > SQC_MAXK || !a->mean || !a->sigma))) fail(SQC_ERR_BAD_ARG, "bad dimensions");
-    if ((gamma || z) && !classify) fail(SQC_ERR_BAD_ARG, "gamma / z requested without a mixture");
-    int dev; select_device(a->device, &dev);
-    // segment bounds; cells of a sample need not be contiguous (stable counting sort by sample if they are not)
-    std::vector<long long> bounds((size_t)J + 1, 0);
-    bool sorted = true;
-    for (long long i = 0; i < N; ++i) {
-      const int g = a->groups[i];
-      if (g < 0 || g >= J) fail(SQC_ERR_BAD_ARG, "groups out of range");
-      bounds[(size_t)g + 1]++;
-      if (i && g < a->groups[i - 1]) sorted = false;
-    }
-    for (int j = 0; j < J; ++j) bounds[(size_t)j + 1] += bounds[j];
-    // mixture parameters: mean, inverse Cholesky factor, log-density constant
-    const int P = D + D * D + 1;
-    std::vector<double> par((size_t)std::max(K, 1) * P, 0.0);
-    for (int k = 0; k < K; ++k) {
-      double L[SQC_MAXD * SQC_MAXD], Li[SQC_MAXD * SQC_MAXD];
-      if (!small_chol_inv(a->sigma + (size_t)k * D * D, D, L, Li)) fail(SQC_ERR_NOT_SPD, "mixture covariance %d is not positive definite", k);
-      double c = log(a->pro[k]) - 0.5 * D * 1.8378770664093454835606594728112;
-      for (int d = 0; d < D; ++d) { par[(size_t)k * P + d] = a->mean[k + (size_t)K * d]; c -= log(L[d + D * d]); }
-      for (int e = 0; e < D * D; ++e) par[(size_t)k * P + D + e] = Li[e];
-      par[(size_t)k * P + D + D * D] = c;
-    }
-    double *dx = nullptr, *dmed = nullptr, *dpar = nullptr, *dgam = nullptr; int *dg = nullptr, *dz = nullptr, *dflag = nullptr; long long* db = nullptr;
-    auto cleanup = [&] { cudaFree(dx); cudaFree(dmed); cudaFree(dpar); cudaFree(dgam); cudaFree(dg); cudaFree(dz); cudaFree(dflag); cudaFree(db); };
-    try {
-      CK(cudaMalloc((void**)&dx, (size_t)N * D * sizeof(double))); CK(cudaMalloc((void**)&dmed, (size_t)J * D * sizeof(double)));
-      CK(cudaMalloc((void**)&db, ((size_t)J + 1) * sizeof(long long))); CK(cudaMalloc((void**)&dflag, sizeof(int)));
-      CK(cudaMemset(dflag, 0, sizeof(int)));
-      CK(cudaMemcpy(db, bounds.data(), ((size_t)J + 1) * sizeof(long long), cudaMemcpyHostToDevice));
-      std::vector<long long> pos;                               // pos[i]: where cell i sits in sample order
-      if (sorted) CK(cudaMemcpy(dx, a->x, (size_t)N * D * sizeof(double), cudaMemcpyHostToDevice));
-      else {
-        std::vector<long long> next(bounds.begin(), bounds.end() - 1);
-        pos.resize((size_t)N);
-        for (long long i = 0; i < N; ++i) pos[(size_t)i] = next[(size_t)a->groups[i]]++;
-        std::vector<double> col((size_t)N);
-        for (int d = 0; d < D; ++d) {
-          for (long long i = 0; i < N; ++i) col[(size_t)pos[(size_t)i]] = a->x[(size_t)d * N + i];
-          CK(cudaMemcpy(dx + (size_t)d * N, col.data(), (size_t)N * sizeof(double), cudaMemcpyHostToDevice));
-        }
-      }
-      k_sample_median<<<J * D, MED_THREADS>>>(dx, db, N, J, dmed, dflag);
-      CK(cudaGetLastError());
-      int flag = 0;
-      CK(cudaMemcpy(&flag, dflag, sizeof(int), cudaMemcpyDeviceToHost));
-      if (flag) fail(SQC_ERR_NAN, "NaN in x");
-      CK(cudaMemcpy(medians, dmed, (size_t)J * D * sizeof(double), cudaMemcpyDeviceToHost));
-      if (classify && (gamma || z)) {
-        CK(cudaMalloc((void**)&dg, (size_t)N * sizeof(int))); CK(cudaMalloc((void**)&dpar, par.size() * sizeof(double)));
-        if (gamma) CK(cudaMalloc((void**)&dgam, (size_t)N * K * sizeof(double)));
-        if (z) CK(cudaMalloc((void**)&dz, (size_t)N * sizeof(int)));
-        if (!sorted) CK(cudaMemcpy(dx, a->x, (size_t)N * D * sizeof(double), cudaMemcpyHostToDevice));   // classify in the caller's order
-        CK(cudaMemcpy(dg, a->groups, (size_t)N * sizeof(int), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(dpar, par.data(), par.size() * sizeof(double), cudaMemcpyHostToDevice));
-        const int grid = (int)std::min<long long>((N + 255) / 256, 148 * 16);
-        const size_t sm = (size_t)K * P * sizeof(double);
-#define SQC_CASE_CLASSIFY(DD) case DD: k_gmm_classify<DD><<<grid, 256, sm>>>(dx, dg, N, J, K, dmed, dpar, dgam, dz); break;
-        switch (D) { SQC_FOR_D(SQC_CASE_CLASSIFY) default: fail(SQC_ERR_BAD_ARG, "D = %d not compiled in", D); }
-        CK(cudaGetLastError());
-        if (gamma) CK(cudaMemcpy(gamma, dgam, (size_t)N * K * sizeof(double), cudaMemcpyDeviceToHost));
-        if (z) CK(cudaMemcpy(z, dz, (size_t)N * sizeof(int), cudaMemcpyDeviceToHost));
-      }
-      CK(cudaDeviceSynchronize());
-    } catch (...) { cleanup(); throw; }
-    cleanup();
-  }, err, errlen);
-}
+#include "sqc_init_host.inl"
 
 int sqc_xchg_export(int device, void* handle_out, char* err, size_t errlen) {
   return guarded([&] {
@@ -1216,105 +970,6 @@ const char* sqc_status_name(int st) {
     case SQC_ERR_COMM: return "SQC_ERR_COMM"; case SQC_ERR_NOMEM: return "SQC_ERR_NOMEM"; default: return "SQC_ERR_UNKNOWN";
   }
 }
-int sqc_device_qchisq(const double* p, const double* df, double* out, int32_t n, int device, char* err, size_t errlen) {
-  return guarded([&] {
-    if (!p || !df || !out || n < 0) fail(SQC_ERR_BAD_ARG, "bad arguments");
-    int d; select_device(device, &d);
-    double* buf = nullptr; CK(cudaMalloc((void**)&buf, (size_t)3 * std::max(n, 1) * sizeof(double)));
-    cudaMemcpy(buf, p, n * sizeof(double), cudaMemcpyHostToDevice); cudaMemcpy(buf + n, df, n * sizeof(double), cudaMemcpyHostToDevice);
-    k_qchisq<<<(n + 127) / 128, 128>>>(buf, buf + n, buf + 2 * (size_t)n, n);
-    cudaError_t e = cudaMemcpy(out, buf + 2 * (size_t)n, n * sizeof(double), cudaMemcpyDeviceToHost);
-    cudaFree(buf); CK(e);
-  }, err, errlen);
-}
-int sqc_device_expneg(const double* x, double* out, int32_t n, int device, char* err, size_t errlen) {
-  return guarded([&] {
-    if (!x || !out || n < 0) fail(SQC_ERR_BAD_ARG, "bad arguments");
-    int d; select_device(device, &d);
-    double* buf = nullptr; CK(cudaMalloc((void**)&buf, (size_t)2 * std::max(n, 1) * sizeof(double)));
-    cudaMemcpy(buf, x, n * sizeof(double), cudaMemcpyHostToDevice);
-    k_expneg<<<(n + 127) / 128, 128>>>(buf, buf + n, n);
-    cudaError_t e = cudaMemcpy(out, buf + n, n * sizeof(double), cudaMemcpyDeviceToHost);
-    cudaFree(buf); CK(e);
-  }, err, errlen);
-}
-int sqc_device_rkeys(uint32_t seed, int64_t skip, int32_t* keys_out, int64_t n, int device, char* err, size_t errlen) {
-  return guarded([&] {
-    if (!keys_out || n < 0 || skip < 0) fail(SQC_ERR_BAD_ARG, "bad arguments");
-    int d; select_device(device, &d);
-    uint32_t *st = nullptr, *st2 = nullptr, *st3 = nullptr, *st4 = nullptr, *seq = nullptr, *table = nullptr; int* out = nullptr;
-    auto cleanup = [&] { cudaFree(st); cudaFree(st2); cudaFree(st3); cudaFree(st4); cudaFree(seq); cudaFree(table); cudaFree(out); };
-    try {
-      CK(cudaMalloc((void**)&st, 640 * sizeof(uint32_t))); CK(cudaMalloc((void**)&st2, 640 * sizeof(uint32_t)));
-      CK(cudaMalloc((void**)&st3, 640 * sizeof(uint32_t))); CK(cudaMalloc((void**)&st4, 640 * sizeof(uint32_t)));
-      CK(cudaMalloc((void**)&seq, (MT_SEQ_WORDS + (size_t)(SQC_MT_JUMP_ROWS + 2) * MT_N) * sizeof(uint32_t))); CK(cudaMalloc((void**)&table, sizeof sqc_mt_jump_table));
-      CK(cudaMalloc((void**)&out, (size_t)std::max<int64_t>(std::max(n, skip), 1) * sizeof(int)));
-      CK(cudaMemcpy(table, sqc_mt_jump_table, sizeof sqc_mt_jump_table, cudaMemcpyHostToDevice));
-      CK(cudaFuncSetAttribute(k_mt_jump, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_SMEM));
-      k_mt_seed<<<1, 32>>>(st, seed);
-      // skipped draws are generated and discarded as a separate call, so the state hand-over is exercised
-      // target_blocks = 1000: the shortest blocks, so that small requests still exercise the jump table
-      if (skip > 0) { mt_generate(0, st, st2, st3, st4, seq, table, out, skip, nullptr, nullptr, 1000); std::swap(st, st2); }
-      mt_generate(0, st, st2, st3, st4, seq, table, out, n, nullptr, nullptr, n > 2000000 ? 20 : 1000);
-      CK(cudaGetLastError());
-      CK(cudaMemcpy(keys_out, out, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
-    } catch (...) { cleanup(); throw; }
-    cleanup();
-  }, err, errlen);
-}
-
-// test hook for the distributed key stream (what one rank of `world` does over `calls` consecutive calls of n_total draws):
-// keys_out = calls x Q ints (rank `rank`'s share of every call, Q = *q_out draws per rank), state_out = R's state after the
-// last call (identical on every rank).  Runs on one GPU: the pieces (host-derived jump polynomials, k_mt_jump_rows,
-// k_mt_fix, share generation) are the ones sqc_fit_robust uses with world > 1.
-int sqc_device_rkeys_share(uint32_t seed, int64_t n_total, int world, int rank, int calls, int32_t* keys_out, int64_t* q_out, int32_t* state_out,
-                           int device, char* err, size_t errlen) {
-  return guarded([&] {
-    if (!keys_out || !q_out || n_total < 624LL * 8 * world || world < 1 || world > XCHG_MAX_WORLD || rank < 0 || rank >= world || calls < 1) fail(SQC_ERR_BAD_ARG, "bad arguments");
-    int d; select_device(device, &d);
-    if (!mtpoly::self_check()) fail(SQC_ERR_COMM, "jump polynomial derivation failed its self-check");
-    const long long per = (n_total + world - 1) / world, Q = ((per + MT_N - 1) / MT_N) * MT_N;
-    const long long mine = std::max<long long>(0, std::min<long long>(Q, n_total - (long long)rank * Q));
-    *q_out = Q;
-    uint32_t *st = nullptr, *seq = nullptr, *seq2 = nullptr, *table = nullptr, *rows = nullptr, *jwin = nullptr; int* out = nullptr;
-    auto cleanup = [&] { cudaFree(st); cudaFree(seq); cudaFree(seq2); cudaFree(table); cudaFree(rows); cudaFree(jwin); cudaFree(out); };
-    try {
-      CK(cudaMalloc((void**)&st, 640 * 8 * sizeof(uint32_t)));
-      CK(cudaMalloc((void**)&seq, (MT_SEQ_WORDS + (size_t)(SQC_MT_JUMP_ROWS + 2) * MT_N) * sizeof(uint32_t))); CK(cudaMalloc((void**)&seq2, (MT_SEQ_WORDS + 64) * sizeof(uint32_t)));
-      CK(cudaMalloc((void**)&table, sizeof sqc_mt_jump_table)); CK(cudaMalloc((void**)&rows, 2 * MT_N * sizeof(uint32_t))); CK(cudaMalloc((void**)&jwin, 2 * MT_N * sizeof(uint32_t)));
-      CK(cudaMalloc((void**)&out, (size_t)std::max<long long>(mine, 1) * sizeof(int)));
-      CK(cudaMemcpy(table, sqc_mt_jump_table, sizeof sqc_mt_jump_table, cudaMemcpyHostToDevice));
-      std::vector<uint32_t> r0(MT_N), r1(MT_N);
-      mtpoly::xpow((unsigned long long)(n_total / MT_N) * MT_N - 1ull, r0.data());
-      CK(cudaMemcpy(rows, r0.data(), MT_N * sizeof(uint32_t), cudaMemcpyHostToDevice));
-      const bool has_rank = rank > 0 && mine > 0;
-      if (has_rank) { mtpoly::xpow((unsigned long long)rank * (unsigned long long)Q - 1ull, r1.data()); CK(cudaMemcpy(rows + MT_N, r1.data(), MT_N * sizeof(uint32_t), cudaMemcpyHostToDevice)); }
-      CK(cudaFuncSetAttribute(k_mt_jump, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_SMEM));
-      CK(cudaFuncSetAttribute(k_mt_jump_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MT_SMEM));
-      k_mt_seed<<<1, 32>>>(st + 640 * 2, seed);
-      for (int c = 0; c < calls; ++c) {
-        const uint32_t* in = st + 640 * ((c + 2) % 3);
-        k_mt_seq<<<1, 256>>>(in, seq2, nullptr);
-        k_mt_jump_rows<<<has_rank ? 2 : 1, MT_JUMP_THREADS, MT_SMEM>>>(seq2, rows, jwin, nullptr);
-        k_mt_fix<<<1, 256>>>(in, jwin, st + 640 * (c % 3), st + 640 * 5, n_total, has_rank ? 1 : 0, nullptr);
-        if (mine > 0) {
-          mt_generate(0, st + 640 * 5, st + 640 * 7, st + 640 * 3, st + 640 * 4, seq, table, out, mine, nullptr, nullptr, mine > 2000000 ? 20 : 1000);
-          CK(cudaMemcpy(keys_out + (size_t)c * Q, out, (size_t)mine * sizeof(int), cudaMemcpyDeviceToHost));
-        }
-      }
-      CK(cudaGetLastError());
-      if (state_out) CK(cudaMemcpy(state_out, st + 640 * ((calls - 1) % 3), 625 * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    } catch (...) { cleanup(); throw; }
-    cleanup();
-  }, err, errlen);
-}
-
-// host-only test hook: the jump polynomial x^e mod phi_MT19937 the distributed key stream derives at session creation
-// (624 words, bit i of word w = coefficient of x^(32 w + i)); needs no GPU
-int sqc_mt_jump_poly(uint64_t e, uint32_t* out624) {
-  if (!out624) return SQC_ERR_BAD_ARG;
-  mtpoly::xpow((unsigned long long)e, out624);
-  return mtpoly::self_check() ? SQC_OK : SQC_ERR_COMM;
-}
+#include "sqc_hooks_host.inl"
 
 }  // extern "C"
