@@ -347,7 +347,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
       ++my_epochs;
       const bool tr = mb.trace && b == mb.trace_leader && tid == 0 && my_epochs < 500;
       long long* trow = mb.trace + 16 * my_epochs;
-      if (tr) { trow[0] = gtimer(); trow[4] = sh_clu.phase; trow[5] = 0; for (int e = 6; e < 16; ++e) trow[e] = 0; }
+      if (tr) { trow[0] = gtimer(); trow[4] = sh_clu.phase; trow[5] = 0; for (int e = 6; e < 16; ++e) trow[e] = 0; trow[13] = sh_clu.direct; trow[14] = sh_clu.iters; }
       if (tid == 0) {
         const int ph = sh_clu.phase; const long long n = sh_clu.n_loc;
         const bool keyr = (ph == PH_KEY_HIST || ph == PH_KEY_COLLECT);
