@@ -53,6 +53,31 @@ __device__ __forceinline__ int ld_stream_s32(const int* p) {
   return v;
 }
 
+// ---------------------------------------------------------------------------------------------
+// bulk asynchronous copies global -> shared (TMA engine, cp.async.bulk; SASS UBLKCP) completed on an mbarrier:
+// the tile movers of the E-step / partition passes.  One thread arms the barrier with the byte count and issues
+// the copies; every thread of the CTA waits on the barrier's phase parity before it reads the stage.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {   // 16-byte aligned, bytes % 16 == 0
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+
 // exp(x) for x <= 0 (the density exponents -q/2):  x = (32 n + j) ln2/32 + r,  exp(x) = 2^n * 2^(j/32) * exp(r).
 // k = 32 n + j by the 1.5 * 2^52 rounding trick, two-step Cody-Waite reduction (|r| <= ln2/64), degree-6 Taylor
 // polynomial, one table look-up (32 doubles, L1-resident), scaling by exponent arithmetic.  <= 2 ulp from the

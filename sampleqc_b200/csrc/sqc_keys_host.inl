@@ -156,6 +156,7 @@ void use_keys(sqc_session* S, int call) {
   } else S->mb.keys = nullptr;
   S->mb.call_mix = counter_call_mix(S->seed, 0u);
   S->mb.stream_base = (long long)call * S->N_total;
+  S->mb.call = call;
 }
 // behind the M-step kernel: the state chain of call + 2 (tiny; a CTA of it in front of the cooperative launch would
 // delay that launch by its whole 0.15 ms)

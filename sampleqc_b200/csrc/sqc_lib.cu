@@ -24,6 +24,7 @@
 
 #include "../../include/sampleqc_cuda.h"
 #include "sqc_mcd.cuh"
+#include "sqc_stream.cuh"
 #include "sqc_mt.cuh"
 #include "sqc_mle.cuh"
 #include "sqc_xchg.cuh"
@@ -251,7 +252,8 @@ struct sqc_session {
   long long key_q = 0, key_mine = 0; uint32_t* mt_rows = nullptr; uint32_t* mt_jwin = nullptr; uint32_t* mt_seq2 = nullptr; const int* key_peer[XCHG_MAX_WORLD] = {}; void* key_mapped[XCHG_MAX_WORLD] = {};
   double* o_buf = nullptr; int* o_z = nullptr; int* o_korder = nullptr; OutPtrs optr{};
   size_t o_doubles = 0;
-  int mcd_grid = 0, n_sm = 0;
+  int mcd_grid = 0, n_sm = 0, grid_estep = 0, grid_part = 0;
+  bool stream_kernels = true;            // persistent TMA-fed E-step / partition kernels (SQC_STREAM=0: one CTA per tile, round-1 kernels)
   bool sorted = true; std::vector<long long> perm;      // perm[i] = original index of the cell stored at i
   bool profile = false;
   struct Ev { cudaEvent_t a, b; int fam; const char* tag = nullptr; };
@@ -319,8 +321,30 @@ struct Launch {
   void done() { if (ev) CK(cudaEventRecord(ev->b, stream())); CK(cudaGetLastError()); }
 };
 
+// grid of the persistent E-step / partition kernels: every SM holds as many CTAs as fit, each owns a contiguous tile range
+template <int D> int stream_grid(sqc_session* S, bool part) {
+  const Dev& s = S->dev;
+  int per = 0;
+  if (part) {
+    CK(cudaFuncSetAttribute(k_partition_stream<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)partition_stream_smem<D>(s.K)));
+    CK(cudaFuncSetAttribute(k_partition_stream<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)partition_stream_smem<D>(s.K)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_partition_stream<D, 1>, EST_THREADS, partition_stream_smem<D>(s.K)));
+  } else {
+    CK(cudaFuncSetAttribute(k_estep_stream<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)estep_stream_smem<D>(s.K)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_estep_stream<D>, EST_THREADS, estep_stream_smem<D>(s.K)));
+  }
+  if (per < 1) fail(SQC_ERR_CUDA, "streaming kernel for D = %d does not fit on an SM", D);
+  return std::max(1, std::min(s.T, S->n_sm * per));
+}
 template <int D> void launch_estep(sqc_session* S, int mode) {
   const Dev& s = S->dev;
+  if (mode == 0 && S->stream_kernels) {
+    if (!S->grid_estep) S->grid_estep = stream_grid<D>(S, false);
+    Launch L(S, SQC_KF_ESTEP);
+    k_estep_stream<D><<<S->grid_estep, EST_THREADS, estep_stream_smem<D>(s.K), S->st>>>(s);
+    L.done();
+    return;
+  }
   const size_t sm = (size_t)(s.K * ParK<D>::SZ + (EST_THREADS / 32) * s.K * (D + 1)) * sizeof(double);
   Launch L(S, mode == 0 ? SQC_KF_ESTEP : SQC_KF_INIT);
   if (mode == 0) k_estep<D, 0><<<s.T, EST_THREADS, sm, S->st>>>(s);
@@ -329,6 +353,14 @@ template <int D> void launch_estep(sqc_session* S, int mode) {
 }
 template <int D> void launch_partition(sqc_session* S, int like) {
   const Dev& s = S->dev;
+  if (S->stream_kernels) {
+    if (!S->grid_part) S->grid_part = stream_grid<D>(S, true);
+    Launch L(S, SQC_KF_PARTITION);
+    if (like) k_partition_stream<D, 1><<<S->grid_part, EST_THREADS, partition_stream_smem<D>(s.K), S->st>>>(s);
+    else k_partition_stream<D, 0><<<S->grid_part, EST_THREADS, partition_stream_smem<D>(s.K), S->st>>>(s);
+    L.done();
+    return;
+  }
   const size_t sm = (size_t)(s.K * ParK<D>::SZ) * sizeof(double) + (size_t)TileCfg<D>::CPT * (EST_THREADS / 32) * s.K * sizeof(int);
   Launch L(S, SQC_KF_PARTITION);
   if (like) k_partition<D, 1><<<s.T, EST_THREADS, sm, S->st>>>(s);
@@ -525,7 +557,8 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
   pt.mark("setup");
   // ---- upload x first (asynchronous from pinned memory), scan the sample layout on the host meanwhile ----
   Dev& s = S->dev;
-  s.x = S->alloc<double>((size_t)N * D, false);
+  S->stream_kernels = getenv("SQC_STREAM") && atoi(getenv("SQC_STREAM")) != 0;   // experimental (measured slower, profiles/r2e): off by default
+  s.x = S->alloc<double>((size_t)N * D + 2, false);          // + 2: the bulk copies of the last column round up to 16 bytes
   CK(cudaMemcpyAsync(s.x, a->x, (size_t)N * D * sizeof(double), cudaMemcpyHostToDevice, S->st));
   // cells of a sample must be contiguous; permute once if they are not
   std::vector<long long> n_j(J, 0);
@@ -647,6 +680,7 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
     mb.cand_rec = S->alloc<unsigned long long>(nreg * MCD_CAPW * (2 + D), false);
     mb.cand_cnt = S->alloc<unsigned int>(nreg);
     mb.fhist = S->alloc<unsigned int>((size_t)K * (MCD_NF + 4));
+    mb.pred = S->alloc<McdPred>(K);
     mb.xc = S->xc.dev;
     mb.epoch = S->alloc<unsigned int>(2 * SQC_MAXK + 4); mb.arrive = mb.epoch + SQC_MAXK; mb.status = (int*)(mb.epoch + 2 * SQC_MAXK);
     s.mcd_sync = mb.epoch;
@@ -695,6 +729,7 @@ void run_robust(sqc_session* S) {
   CK(cudaMemsetAsync(s.sigma, 0, (size_t)S->K * S->D * S->D * sizeof(double), S->st));
   CK(cudaMemsetAsync(s.like1, 0, (size_t)(std::max(S->em_iters, 0) + 1) * sizeof(double), S->st));
   CK(cudaMemsetAsync(s.like2, 0, (size_t)(std::max(S->em_iters, 0) + 1) * sizeof(double), S->st));
+  CK(cudaMemsetAsync(S->mb.pred, 0xFF, (size_t)S->K * sizeof(McdPred), S->st));          // no threshold history: call[] = -1
   if (S->mt_state) {                                                                    // set_seed_cpp, :475
     CK(cudaEventRecord(S->ev_key_free[0], S->st)); CK(cudaEventRecord(S->ev_key_free[1], S->st));   // after k_ctl_reset
     if (S->key_q) {

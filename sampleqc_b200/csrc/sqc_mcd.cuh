@@ -48,7 +48,16 @@ constexpr int MCD_WARPS = MCD_THREADS / 32;
 #define SQC_MCD_DIRECT_KEYCAP 12000.0   // same for the random-key start round (the leader walks them in ~20 us)
 #endif
 #ifndef SQC_MCD_DIRECT_CAP
-#define SQC_MCD_DIRECT_CAP 3000.0 // expected candidates a direct round may catch
+#define SQC_MCD_DIRECT_CAP 12000.0 // expected candidates a direct round may catch
+#endif
+#ifndef SQC_MCD_NOISE0
+#define SQC_MCD_NOISE0 3.0        // first C-step: half-width of the predicted band in units of 1/sqrt(n) (call-to-call std of the threshold ~1.4/sqrt(n))
+#endif
+#ifndef SQC_MCD_PREDICT
+#define SQC_MCD_PREDICT 1         // 0: no band prediction from the previous update_beta_scale_k calls (debug / A-B)
+#endif
+#ifndef SQC_MCD_KEY_SIGMAS
+#define SQC_MCD_KEY_SIGMAS 3.2    // half-width of the direct key band in standard deviations of the h-th key (a miss costs one regular round)
 #endif
 constexpr int MCD_NB = 4096;                         // histogram bins per window
 constexpr int MCD_NF = 1024;                         // fine bins inside the candidate bin (leader post; a 4 KB exchange on multi-GPU)
@@ -59,6 +68,19 @@ constexpr int MCD_TCACHE = 64;                       // tie candidates whose res
 constexpr int MCD_TINY = 512;                        // tie candidates (inside one fine bin) over all ranks
 constexpr size_t MCD_SMEM = (size_t)(MCD_NB + 8) * 4 + (size_t)MCD_TINY * 20 + 256;
 template <int D> struct McdCfg { static constexpr int CPT = (D <= 4) ? 8 : 4; static constexpr int CHUNK = MCD_THREADS * CPT; };
+
+constexpr int MCD_HMAX = 64;                         // C-steps per launch whose thresholds are remembered; slot MCD_HMAX = the final q-pass
+
+// Thresholds a cluster reached in the previous update_beta_scale_k calls (one per EM iteration), by C-step index.  The
+// random start draws a fresh half of the cluster every call, but the half is large: the h-th distance of C-step i moves
+// by ~1/sqrt(n) (i = 0) or far less (i > 0) from one call to the next once the labels settle (measured with
+// oracle/np_restatement.py traces).  The leader predicts a narrow band around last call's value and goes straight to a
+// COLLECT round; a miss falls back to the regular HIST round, so the selection stays exact.  Ring of 3 slots (call % 3).
+struct McdPred {
+  int call[3], nsteps[3];
+  unsigned long long thr[3][MCD_HMAX + 1];             // distance bits; [MCD_HMAX] = the final quantile q (:98-100)
+  double dens[3][MCD_HMAX + 1];                        // candidates per unit of relative width around that threshold
+};
 
 enum { PH_KEY_HIST = 0, PH_KEY_COLLECT = 1, PH_DIST_HIST = 2, PH_DIST_COLLECT = 3, PH_DONE = 4 };
 
@@ -72,6 +94,7 @@ struct McdClu {
   int shift, phase, is_final, iters, n_hist_rounds, direct;   // direct: COLLECT round entered without a HIST round (predicted band)
   int key_shift, pad2;                 // shift of the +-8 sigma key window while a direct key round is tried
   double last_rel, dens;               // relative change of the threshold over the last C-step; candidates per unit of relative width
+  double band_c, band_w;               // centre and relative half-width of the predicted band of a direct distance round
   double det_old, det_new, q_chisq;
   double cshift[SQC_MAXD];             // moment shift
   double loc[SQC_MAXD];
@@ -100,6 +123,8 @@ struct McdBufs {
   double key_qinv;
   unsigned long long call_mix;         // counter-mode key mix for this call
   long long stream_base;               // call * N_total: index of this call's first draw
+  McdPred* pred;                       // K: threshold history of the previous calls (band prediction)
+  int call, pad_call;                  // index of this update_beta_scale_k call (0 = initial labelling)
   unsigned int* epoch;                 // K: state version of every cluster (0 at launch; the leader publishes 1, 2, ...)
   unsigned int* arrive;                // K: worker arrivals (0 at launch)
   int* status;                         // in-kernel error word (0 at launch): identical on every rank, derived from exchanged data only
@@ -255,16 +280,20 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
   __shared__ double sh_red[32 * NM];
   __shared__ double sh_out[NM];
   __shared__ double sh_tr[MCD_TCACHE * D];      // residuals of the first tie candidates (leader)
+  __shared__ unsigned short sh_tord[MCD_TINY];  // tie members in (key, rank, position) order
   __shared__ long long sh_cstart[SQC_MAXK + 1];
   __shared__ long long sh_scan[33];
   __shared__ int sh_flag[6];
   __shared__ int sh_ph[SQC_MAXK];
   __shared__ long long sh_n[SQC_MAXK];
   __shared__ unsigned long long sh_u64[4];
+  __shared__ unsigned long long sh_pT1[MCD_HMAX + 1], sh_pT2[MCD_HMAX + 1];   // leader: thresholds of the previous two calls by C-step index (0 = none)
+  __shared__ double sh_pD1[MCD_HMAX + 1];
   __shared__ McdClu sh_clu;                    // worker: snapshot of the state of the cluster being streamed
   __shared__ int sh_ep[SQC_MAXK], sh_eloc[SQC_MAXK], sh_done[SQC_MAXK], sh_off[SQC_MAXK];
 
   if (!s.ctl->cont) return;                    // uniform across the grid (and across ranks): nobody reaches a barrier
+  const long long t_entry = mb.trace ? gtimer() : 0;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, G = gridDim.x, b = blockIdx.x, K = s.K;
   const int world = (MULTI && mb.xc.world > 1) ? mb.xc.world : 1, myrank = world > 1 ? mb.xc.rank : 0;
   // the candidate caps bound the per-rank work of a leader post and the load of the per-warp candidate regions: with the
@@ -300,10 +329,10 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         c.wlo = (unsigned long long)lo; c.whi = (unsigned long long)hi;
         c.shift = window_shift(c.wlo, c.whi);
         c.phase = PH_KEY_HIST;
-        // the key threshold is predictable: go straight to a COLLECT round over the band p 2^31 +- 4 sigma when that
-        // band holds few enough keys (expected 8 sigma_rank = 8 sqrt(n p (1 - p))); a miss falls back to KEY_HIST
-        const double exp_cand = 8.0 * sqrt((double)n * p * (1.0 - p));
-        const double blo = p * two31 - 4.0 * sig - 1.0, bhi = p * two31 + 4.0 * sig + 1.0;
+        // the key threshold is predictable: go straight to a COLLECT round over the band p 2^31 +- SQC_MCD_KEY_SIGMAS sigma
+        // when that band holds few enough keys (expected 2 s sqrt(n p (1 - p))); a miss falls back to KEY_HIST
+        const double exp_cand = 2.0 * SQC_MCD_KEY_SIGMAS * sqrt((double)n * p * (1.0 - p));
+        const double blo = p * two31 - SQC_MCD_KEY_SIGMAS * sig - 1.0, bhi = p * two31 + SQC_MCD_KEY_SIGMAS * sig + 1.0;
         if (SQC_MCD_DIRECT && n > 65536 && exp_cand <= SQC_MCD_DIRECT_KEYCAP * cap_scale && blo > 0.0 && bhi < two31) {
           c.blo = (unsigned long long)blo; c.bhi = (unsigned long long)bhi;
           int fs = 0;
@@ -316,6 +345,20 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
       W->cnt_below[k] = 0ull; W->cnt_nan[k] = 0ull;
     }
     for (int i = tid; i < MCD_NB; i += MCD_THREADS) mb.hist[k * MCD_NB + i] = 0u;
+    // threshold history of the previous two calls (band prediction); this call writes slot call % 3
+    {
+      McdPred& P = mb.pred[k];
+      const int s1 = (mb.call + 2) % 3, s2 = (mb.call + 1) % 3;
+      const bool v1 = SQC_MCD_PREDICT && mb.call >= 1 && P.call[s1] == mb.call - 1, v2 = v1 && mb.call >= 2 && P.call[s2] == mb.call - 2;
+      const int n1 = v1 ? min(P.nsteps[s1], MCD_HMAX) : 0, n2 = v2 ? min(P.nsteps[s2], MCD_HMAX) : 0;
+      for (int i = tid; i <= MCD_HMAX; i += MCD_THREADS) {
+        const bool in1 = v1 && (i < n1 || i == MCD_HMAX), in2 = v2 && (i < n2 || i == MCD_HMAX);
+        sh_pT1[i] = in1 ? P.thr[s1][i] : 0ull; sh_pD1[i] = in1 ? P.dens[s1][i] : 0.0;
+        sh_pT2[i] = in2 ? P.thr[s2][i] : 0ull;
+      }
+      __syncthreads();
+      if (tid == 0) { P.call[mb.call % 3] = mb.call; P.nsteps[mb.call % 3] = 0; P.thr[mb.call % 3][MCD_HMAX] = 0ull; }
+    }
   }
 
   if (b < K) {
@@ -333,6 +376,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
     };
     int ep = 1;
     publish(1);
+    if (mb.trace && b == mb.trace_leader && tid == 0) { mb.trace[1] = t_entry; mb.trace[2] = gtimer(); }
     if (tid == 0) {
       // qchisq(h / n, D) of the consistency factor (:101-102) is first needed after the start rounds: evaluate it
       // while the workers stream the first one
@@ -440,8 +484,19 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
           }
           part_pre[q] = a2;
         }
+        // candidate counts of this thread's regions: same L2 round trip as the partials and the fine histogram
+        unsigned int cn[MCD_RPT];
+#pragma unroll
+        for (int i = 0; i < MCD_RPT; ++i) { const int rg = tid * MCD_RPT + i; cn[i] = (rg < regions) ? ccnt[rg] : 0u; }
         // 1. fine histogram of the candidates: built by the workers with atomics on mb.fhist
-        for (int i = tid; i < MCD_NF + 4; i += MCD_THREADS) { sh_hist[i] = mb.fhist[k * (MCD_NF + 4) + i]; mb.fhist[k * (MCD_NF + 4) + i] = 0u; }
+        {
+          constexpr int FPT = (MCD_NF + 4 + MCD_THREADS - 1) / MCD_THREADS;
+          unsigned int fv[FPT];
+#pragma unroll
+          for (int i = 0; i < FPT; ++i) { const int e = tid + i * MCD_THREADS; fv[i] = (e < MCD_NF + 4) ? mb.fhist[k * (MCD_NF + 4) + e] : 0u; }
+#pragma unroll
+          for (int i = 0; i < FPT; ++i) { const int e = tid + i * MCD_THREADS; if (e < MCD_NF + 4) { sh_hist[e] = fv[i]; mb.fhist[k * (MCD_NF + 4) + e] = 0u; } }
+        }
         if (tid == 0) { sh_flag[4] = 0; sh_flag[5] = 0; }
         if (direct && wid == 0) {                                    // cells strictly under the band: moment 0 of the partials (exact: counts < 2^53)
           const double cb = warp_sum(part_pre[0]);
@@ -486,39 +541,50 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
           // memory, then thread t takes candidates t, t + threads, ... (one record load each, all independent)
           unsigned int* sh_pref = sh_hist + MCD_NF + 8;            // regions + 1 words behind the fine histogram
           long long mine_c = 0;
-          unsigned int cn[MCD_RPT];
 #pragma unroll
-          for (int i = 0; i < MCD_RPT; ++i) { const int rg = tid * MCD_RPT + i; cn[i] = (rg < regions) ? min(ccnt[rg], (unsigned)MCD_CAPW) : 0u; mine_c += cn[i]; }
+          for (int i = 0; i < MCD_RPT; ++i) { cn[i] = min(cn[i], (unsigned)MCD_CAPW); mine_c += cn[i]; }
           long long ncand_loc;
           long long off_c = block_excl_scan<MCD_THREADS>(mine_c, sh_scan, &ncand_loc);
 #pragma unroll
           for (int i = 0; i < MCD_RPT; ++i) { const int rg = tid * MCD_RPT + i; if (rg < regions) sh_pref[rg] = (unsigned int)off_c; off_c += cn[i]; }
           if (tid == 0) sh_pref[regions] = (unsigned int)ncand_loc;
           __syncthreads();
-          for (int f = tid; f < (int)ncand_loc; f += MCD_THREADS) {
-            int lo = 0, hi = regions;                               // the region with sh_pref[rg] <= f < sh_pref[rg + 1]
-            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sh_pref[mid] <= (unsigned)f) lo = mid; else hi = mid; }
-            const int rg = lo; const unsigned int sl = (unsigned)f - sh_pref[rg];   // (empty regions share a prefix with their successor: the largest index wins, which is the owner)
-            const unsigned long long* rec = mb.cand_rec + (((long long)k * regions + rg) * MCD_CAPW + sl) * (2 + D);
-            unsigned long long wv[2 + D];
+          // MCD_PB candidates per thread and trip: the record loads of a batch are all in flight together (the pass is
+          // bound by L2 round trips, ~1.5 us each while the workers stream)
+          constexpr int MCD_PB = (D <= 4) ? 4 : 2;
+          for (int f0 = tid; f0 < (int)ncand_loc; f0 += MCD_THREADS * MCD_PB) {
+            unsigned long long wv[MCD_PB][2 + D]; int rgs[MCD_PB]; unsigned int sls[MCD_PB]; bool live[MCD_PB];
 #pragma unroll
-            for (int e = 0; e < 2 + D; ++e) wv[e] = rec[e];
-            const unsigned long long bits = wv[0];
-            const int fb = (int)((bits - blo) >> fshift);
-            if (fb < fbin) {
-              if (need_mom) {
-                double r[D];
+            for (int q = 0; q < MCD_PB; ++q) {
+              const int f = f0 + q * MCD_THREADS;
+              live[q] = f < (int)ncand_loc;
+              int lo = 0, hi = regions;                             // the region with sh_pref[rg] <= f < sh_pref[rg + 1]
+              while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sh_pref[mid] <= (unsigned)f) lo = mid; else hi = mid; }
+              rgs[q] = lo; sls[q] = live[q] ? (unsigned)f - sh_pref[lo] : 0u;   // (empty regions share a prefix with their successor: the largest index wins, which is the owner)
+              const unsigned long long* rec = mb.cand_rec + (((long long)k * regions + rgs[q]) * MCD_CAPW + sls[q]) * (2 + D);
 #pragma unroll
-                for (int d = 0; d < D; ++d) r[d] = __longlong_as_double((long long)wv[2 + d]);
-                Mom<D>::add(tot, r, cs, true);
-              }
-            } else if (fb == fbin) {
-              const int t = atomicAdd(&sh_flag[4], 1);
-              if (t < MCD_TINY) {
-                sh_tkey[t] = bits; sh_tpos[t] = (unsigned int)wv[1]; sh_tref[t] = (unsigned int)(rg * MCD_CAPW + sl); sh_trank[t] = (unsigned)myrank;
-                if (t < MCD_TCACHE) {
+              for (int e = 0; e < 2 + D; ++e) wv[q][e] = live[q] ? __ldcg(rec + e) : 0ull;
+            }
 #pragma unroll
-                  for (int d = 0; d < D; ++d) sh_tr[t * D + d] = __longlong_as_double((long long)wv[2 + d]);
+            for (int q = 0; q < MCD_PB; ++q) {
+              if (!live[q]) continue;
+              const unsigned long long bits = wv[q][0];
+              const int fb = (int)((bits - blo) >> fshift);
+              if (fb < fbin) {
+                if (need_mom) {
+                  double r[D];
+#pragma unroll
+                  for (int d = 0; d < D; ++d) r[d] = __longlong_as_double((long long)wv[q][2 + d]);
+                  Mom<D>::add(tot, r, cs, true);
+                }
+              } else if (fb == fbin) {
+                const int t = atomicAdd(&sh_flag[4], 1);
+                if (t < MCD_TINY) {
+                  sh_tkey[t] = bits; sh_tpos[t] = (unsigned int)wv[q][1]; sh_tref[t] = (unsigned int)(rgs[q] * MCD_CAPW + sls[q]); sh_trank[t] = (unsigned)myrank;
+                  if (t < MCD_TCACHE) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) sh_tr[t * D + d] = __longlong_as_double((long long)wv[q][2 + d]);
+                  }
                 }
               }
             }
@@ -595,8 +661,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
               before += (kj < ki) || (kj == ki && (rj < ri || (rj == ri && pj < pi)));
             }
             if (before == (int)take2 - 1) sh_u64[2] = ki;           // the h-th smallest key itself
-            // remember membership in the top bit of the reference
-            if (before < (int)take2) sh_tref[i] |= 0x80000000u; else sh_tref[i] &= 0x7fffffffu;
+            if (before < (int)take2) sh_tord[before] = (unsigned short)i;   // members by rank ((key, rank, position) is unique)
           }
           __syncthreads();
           thr = sh_u64[2];
@@ -610,18 +675,10 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
 #pragma unroll
               for (int m = 0; m < NM; ++m) ttot[m] = 0.0;
             }
-            unsigned long long lastk = 0ull; unsigned lastp = 0u, lastr = 0u; bool first = true;
-            for (;;) {
-              int best = -1;
-              for (int i = 0; i < ntie; ++i) {
-                if (!(sh_tref[i] & 0x80000000u)) continue;
-                const bool after = first || sh_tkey[i] > lastk || (sh_tkey[i] == lastk && (sh_trank[i] > lastr || (sh_trank[i] == lastr && sh_tpos[i] > lastp)));
-                if (!after) continue;
-                if (best < 0 || sh_tkey[i] < sh_tkey[best] ||
-                    (sh_tkey[i] == sh_tkey[best] && (sh_trank[i] < sh_trank[best] || (sh_trank[i] == sh_trank[best] && sh_tpos[i] < sh_tpos[best])))) best = i;
-              }
-              if (best < 0) break;
-              const unsigned ref = sh_tref[best] & 0x7fffffffu;
+            const int nmem = (int)min((long long)ntie, take2);
+            for (int m2 = 0; m2 < nmem; ++m2) {
+              const int best = (int)sh_tord[m2];
+              const unsigned ref = sh_tref[best];
               double r[D];
               if (!MULTI || sh_trank[best] == (unsigned)myrank) {
                 const long long cb = (long long)k * regions * MCD_CAPW + (long long)ref;
@@ -634,7 +691,6 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
                 }
               }
               if constexpr (MULTI) Mom<D>::add(ttot, r, cs, true); else Mom<D>::add(tot, r, cs, true);
-              lastk = sh_tkey[best]; lastp = sh_tpos[best]; lastr = sh_trank[best]; first = false;
             }
           }
         }
@@ -673,7 +729,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
             // the predicted band missed the h-th distance (or caught too many cells): take the regular HIST round
             cl.direct = 0; cl.last_rel = 1.0;
             cl.phase = PH_DIST_HIST; cl.n_hist_rounds = 0;
-            const double t = __longlong_as_double((long long)cl.t_prev);
+            const double t = cl.band_c;
             set_dist_window(cl, t * 0.25, t * 8.0);
           } else if (!ok) {
             // too many candidates in one place (region overflow or a crowded fine bin): refine with another HIST round
@@ -704,11 +760,19 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
                 cl.dens = relw > 0.0 ? (double)ncand_all / relw : 1e300;
               }
               cl.t_prev = thr;
+              if (cl.iters - 1 < MCD_HMAX) { McdPred& P = mb.pred[k]; P.thr[mb.call % 3][cl.iters - 1] = thr; P.dens[mb.call % 3][cl.iters - 1] = cl.dens; }
               if (tr) trow[12] = (long long)thr;
               atomicAdd((unsigned long long*)&s.ctl->mcd_csteps, 1ull);
             } else {
               // consistency rescale (:98-103): q = h-th smallest distance under the final estimates
               const double q = __longlong_as_double((long long)thr);
+              {
+                McdPred& P = mb.pred[k];
+                const double relw = (double)(cl.bhi - cl.blo) * 2.220446049250313e-16;
+                P.thr[mb.call % 3][MCD_HMAX] = thr; P.dens[mb.call % 3][MCD_HMAX] = relw > 0.0 ? (double)ncand_all / relw : 1e300;
+                P.nsteps[mb.call % 3] = cl.iters;
+              }
+              if (tr) trow[12] = (long long)thr;
               const double f = q / cl.q_chisq;
               for (int e = 0; e < D * D; ++e) { cl.scale[e] = cl.scale[e] * f; s.sigma[k * D * D + e] = cl.scale[e]; }
               for (int d = 0; d < D; ++d) s.beta[k * D + d] = cl.loc[d];
@@ -725,12 +789,30 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
             else {
               cl.is_final = go_final ? 1 : 0;
               cl.phase = PH_DIST_HIST; cl.n_hist_rounds = 0; cl.direct = 0;
-              // once the threshold has settled (it moves less from one C-step to the next), skip the HIST round: predict a
-              // band around the last threshold that should hold the next one and few enough cells; the COLLECT round
-              // counts the cells under the band itself.  A miss costs one regular round.
-              const double wband = 2.0 * cl.last_rel + 5e-4;
-              if (cl.t_prev && cl.last_rel < 0.02 && cl.dens * 2.0 * wband <= SQC_MCD_DIRECT_CAP * cap_scale && SQC_MCD_DIRECT) {
-                const double t = __longlong_as_double((long long)cl.t_prev);
+              // Skip the HIST round when the threshold can be predicted: a band that should hold the next threshold and
+              // few enough cells; the COLLECT round counts the cells under the band itself.  A miss costs one regular
+              // round.  Two predictors, the narrower band wins:
+              //  (a) inside this call, once the threshold has settled: around the last threshold, +- twice its last move;
+              //  (b) from the previous calls (EM iterations): the threshold the same C-step index reached last time,
+              //      +- 2.5 x its move between the last two calls + the sampling noise of the random start
+              //      (~1/sqrt(n) relative for the first C-step, far less afterwards).
+              double wband = 1e300, tband = 0.0;
+              if (cl.t_prev && cl.last_rel < 0.02) {
+                const double w = 2.0 * cl.last_rel + 5e-4;
+                if (cl.dens * 2.0 * w <= SQC_MCD_DIRECT_CAP * cap_scale) { wband = w; tband = __longlong_as_double((long long)cl.t_prev); }
+              }
+              {
+                const int hi = go_final ? MCD_HMAX : (cl.iters < MCD_HMAX ? cl.iters : -1);
+                if (hi >= 0 && sh_pT1[hi]) {
+                  const double c1 = __longlong_as_double((long long)sh_pT1[hi]);
+                  const double noise = ((hi == 0) ? SQC_MCD_NOISE0 : 1.5) / sqrt((double)cl.n);
+                  const double w = sh_pT2[hi] ? 2.5 * fabs(c1 - __longlong_as_double((long long)sh_pT2[hi])) / c1 + noise : 6.0 * noise;
+                  if (sh_pD1[hi] * 2.0 * w <= SQC_MCD_DIRECT_CAP * cap_scale && w < wband && w < 0.2) { wband = w; tband = c1; }
+                }
+              }
+              if (wband < 1e300 && SQC_MCD_DIRECT) {
+                const double t = tband;
+                cl.band_c = t; cl.band_w = wband;
                 cl.blo = dist_bits(t * (1.0 - wband)); cl.bhi = dist_bits(t * (1.0 + wband));
                 int fs = 0;
                 while (fs < 62 && ((cl.bhi - cl.blo) >> fs) >= (unsigned long long)MCD_NF) ++fs;

@@ -30,7 +30,7 @@ for leader in range(K):
     s.close()
     R = int(buf[0]); t = buf.reshape(-1, 16)
     base = t[1][0]
-    print(f"leader {leader}: rounds {R}  span {(t[R][3] - t[1][0]) / 1e3:.1f} us")
+    print(f"leader {leader}: rounds {R}  span {(t[R][3] - t[1][0]) / 1e3:.1f} us   kernel entry -> first publish {(t[0][2] - t[0][1]) / 1e3:.1f} us, entry -> end of last post {(t[R][3] - t[0][1]) / 1e3:.1f} us")
     print("  ep  start_us  wait_us  post_us  ph  dir  ncand   T")
     for r in range(1, R + 1):
         t0, t1, t2, t3, ph, ch = t[r][:6]

@@ -1,0 +1,97 @@
+"""GPU parity on BASELINE.json's own configurations (C1..C5), through the C ABI against the CPU
+oracle on the same seeded inputs:
+
+  C1  simulate_qcs defaults (1e5 cells, 2000 cells / sample), fitted with K = 2 robust, both key modes, to convergence
+  C2  1 M cells x 100 samples, D = 3, K = 4 robust — "the parity fixture"  — in full, em_iters = 50
+  C4  shape: D = 6 AND K = 6 together (>= 200 k cells)
+  C5  shape: K = 5, robust and MLE (>= 500 k cells)
+
+Bars (north_star): same number of EM iterations, labels bit-identical, parameters and likelihoods within 1e-8 relative,
+outlier flags identical apart from cells within 1e-9 of the cut, R's RNG state after the fit identical."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-8
+
+
+def _compare(ref, got, N, keys=("mu_0", "alpha_j", "beta_k", "sigma_k", "p_jk")):
+    assert got["n_iter"] == ref["n_iter"]
+    for key in keys:
+        scale = np.max(np.abs(ref[key]))
+        np.testing.assert_allclose(got[key], ref[key], rtol=RTOL, atol=RTOL * scale, err_msg=key)
+    n = ref["n_iter"]
+    fin = np.isfinite(ref["like_1"][:n].ravel())
+    np.testing.assert_array_equal(fin, np.isfinite(got["like_1"][:n].ravel()))
+    np.testing.assert_allclose(got["like_1"][:n].ravel()[fin], ref["like_1"][:n].ravel()[fin], rtol=RTOL, err_msg="like_1")
+    np.testing.assert_allclose(got["like_2"][:n].ravel()[fin], ref["like_2"][:n].ravel()[fin], rtol=RTOL, err_msg="like_2")
+    np.testing.assert_array_equal(got["z"], ref["z"])
+
+
+@pytest.mark.parametrize("rng_mode", [0, 1])
+def test_c1_full_size(oracle, rng_mode):
+    """BASELINE configs[0]: the reference's own CPU-runnable case at its real size"""
+    from sampleqc_b200 import api
+    from sampleqc_b200.simulate import make_config
+    sim, iz, _, p = make_config("C1")
+    N, J, K, D = p["N"], p["J"], p["K"], p["D"]
+    assert (N, K, D) == (100_000, 2, 3)
+    ref = oracle.fit_sampleqc_robust_cpp(sim.x, iz, sim.groups, D, J, K, N, 50, 0.5, 50, 0, rng_mode=rng_mode)
+    got = api.fit_sampleqc_robust_cpp(sim.x, iz, sim.groups, D, J, K, N, 50, 0.5, 50, 0, rng_mode=rng_mode)
+    _compare(ref, got, N)
+    assert got["rng_draws"] == ref["rng_draws"] == (1 + ref["n_iter"]) * N
+    if rng_mode == 0:
+        np.testing.assert_array_equal(got["rng_state"], ref["rng_state"])
+
+
+def test_c2_full(oracle):
+    """BASELINE configs[1] in full: 1 M cells x 100 samples, K = 4, em_iters = 50 (what fit_sampleqc sends), then the
+    outlier flags of the fitted model"""
+    from sampleqc_b200 import api
+    from sampleqc_b200.simulate import make_config
+    sim, iz, _, p = make_config("C2")
+    N, J, K, D = p["N"], p["J"], p["K"], p["D"]
+    assert (N, J, K, D) == (1_000_000, 100, 4, 3)
+    ref = oracle.fit_sampleqc_robust_cpp(sim.x, iz, sim.groups, D, J, K, N, 50, 0.5, 50, 0)
+    got = api.fit_sampleqc_robust_cpp(sim.x, iz, sim.groups, D, J, K, N, 50, 0.5, 50, 0)
+    _compare(ref, got, N)
+    np.testing.assert_array_equal(got["rng_state"], ref["rng_state"])
+    assert got["mcd_iters_hit"] == ref["mcd_iters_hit"]
+    fit = api.recentre(got)
+    m_ref, o_ref, c_ref = oracle.outlier_maha(sim.x, sim.groups, fit["mu_0"], fit["alpha_j"], fit["beta_k"], fit["sigma_k"], 0.01)
+    m, o, c = api.calc_outliers(sim.x, sim.groups, fit["mu_0"], fit["alpha_j"], fit["beta_k"], fit["sigma_k"], 0.01)
+    near = np.abs(m_ref.min(axis=1) - c_ref) < 1e-9
+    np.testing.assert_array_equal(o[~near], o_ref[~near])
+    assert 0 < o.sum() < N
+
+
+def test_c4_shape_d6_k6(oracle):
+    """BASELINE configs[3] shape: D = 6 and K = 6 together (the larger covariance / Cholesky path)"""
+    from sampleqc_b200 import api
+    from sampleqc_b200.simulate import make_config
+    sim, iz, _, p = make_config("C4", scale=0.05)              # 250 k cells x 25 samples
+    N, J, K, D = p["N"], p["J"], p["K"], p["D"]
+    assert N >= 200_000 and (K, D) == (6, 6)
+    ref = oracle.fit_sampleqc_robust_cpp(sim.x, iz, sim.groups, D, J, K, N, 10, 0.5, 50, 0)
+    got = api.fit_sampleqc_robust_cpp(sim.x, iz, sim.groups, D, J, K, N, 10, 0.5, 50, 0)
+    _compare(ref, got, N)
+    np.testing.assert_array_equal(got["rng_state"], ref["rng_state"])
+
+
+def test_c5_shape_k5_robust_and_mle(oracle):
+    """BASELINE configs[4] shape: K = 5, both variants"""
+    from sampleqc_b200 import api
+    from sampleqc_b200.simulate import make_config
+    sim, iz, ig, p = make_config("C5", scale=0.012)            # 600 k cells x 60 samples
+    N, J, K, D = p["N"], p["J"], p["K"], p["D"]
+    assert N >= 500_000 and K == 5
+    ref = oracle.fit_sampleqc_robust_cpp(sim.x, iz, sim.groups, D, J, K, N, 8, 0.5, 50, 0)
+    got = api.fit_sampleqc_robust_cpp(sim.x, iz, sim.groups, D, J, K, N, 8, 0.5, 50, 0)
+    _compare(ref, got, N)
+    ref = oracle.fit_sampleqc_mle_cpp(sim.x, ig, sim.groups, D, J, K, N, 5, 0)
+    got = api.fit_sampleqc_mle_cpp(sim.x, ig, sim.groups, D, J, K, N, 5, 0)
+    for key in ("mu_0", "alpha_j", "beta_k", "sigma_k", "p_k", "p_jk", "gamma_i", "like_1", "like_2"):
+        scale = np.max(np.abs(ref[key]))
+        np.testing.assert_allclose(got[key], ref[key], rtol=1e-8, atol=1e-8 * scale, err_msg=key)
+    np.testing.assert_array_equal(got["z"], ref["z"])
