@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SQC_ABI_VERSION 1
+#define SQC_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SQC_API __attribute__((visibility("default")))
@@ -96,7 +96,15 @@ typedef struct sqc_fit_args {
   int64_t  cell_offset;     /* index of this shard's first cell in the full data set         */
   int64_t  N_total;         /* cells over all shards (== N when world <= 1)                  */
   const void* peer_handles; /* world x SQC_IPC_HANDLE_BYTES: sqc_xchg_export() of every rank */
+  /* multi-GPU from ONE call (what the Rcpp stubs use: fit_sampleqc() makes a single call per sample group,
+   * R/fit_sampleqc.R:229-238).  Only read when world <= 1.  0 or 1: one GPU (`device`); n > 1: the library shards the
+   * cells by sample over GPUs 0 .. n-1 of this process (one host thread per GPU, peer access instead of IPC handles);
+   * SQC_ALL_GPUS: every visible GPU (at most 8).  Fewer GPUs are used when there are fewer samples than GPUs; a data
+   * set whose samples are interleaved cell by cell is fitted on one GPU.  Results are those of the one-GPU fit
+   * (sharded fit == oracle, tests/test_gpu_multi.py).                                                       */
+  int32_t  n_gpus;
 } sqc_fit_args;
+#define SQC_ALL_GPUS (-1)
 
 /* ---- fit outputs (all caller-allocated; NULL pointers are skipped) --------------------- */
 typedef struct sqc_fit_out {
@@ -237,6 +245,16 @@ SQC_API int sqc_device_rkeys(uint32_t seed, int64_t skip, int32_t* keys_out, int
  * keys_out holds calls x Q ints, state_out (625 words, may be NULL) R's state after the last call.                     */
 SQC_API int sqc_device_rkeys_share(uint32_t seed, int64_t n_total, int world, int rank, int calls, int32_t* keys_out,
                            int64_t* q_out, int32_t* state_out, int device, char* err, size_t errlen);
+
+/* host-only (no GPU needed): the sample-aligned shards a fit with n_gpus > 1 is cut into.  shard_cells: n_gpus + 1 cell
+ * boundaries; sample_rank (J, may be NULL): shard that owns every sample code, -1 for a sample without cells.  Returns
+ * the number of shards (<= n_gpus; fewer when there are fewer samples), 0 when cells of a sample are interleaved (the
+ * fit then runs on one GPU), < 0 on bad arguments                                                                    */
+SQC_API int sqc_plan_shards(const int32_t* groups, int64_t N, int32_t J, int32_t n_gpus, int64_t* shard_cells, int32_t* sample_rank);
+
+/* measured fp64 FMA issue rate of the device in FMA instructions per second (x 2 = FLOP/s): the co-limit of the E-step /
+ * partition passes next to HBM bandwidth, reported by bench.py beside the HBM roofline          */
+SQC_API int sqc_fp64_peak(int device, double* dfma_per_s, char* err, size_t errlen);
 
 /* host-only (no GPU needed): x^e mod phi_MT19937 over GF(2), the jump polynomial that moves the Mersenne-Twister state
  * e words ahead (624 words, bit i of word w = coefficient of x^(32 w + i)); SQC_ERR_COMM if the self-check against the

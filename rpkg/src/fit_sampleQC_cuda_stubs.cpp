@@ -23,18 +23,22 @@ using namespace Rcpp;
 
 namespace {
 
-// R's RNG state after the reference would have consumed (1 + n_iter) * N unif_rand draws: written back into
-// .Random.seed so that code running after the fit sees the stream where the reference leaves it
-// (the reference calls set.seed(seed) through Rcpp::Function, helpers.cpp:10-14, and Rcpp::RNGScope
-// brackets the export, RcppExports.cpp:38).
+// R's RNG state after the reference would have consumed (1 + n_iter) * N unif_rand draws, so that code running
+// after the fit sees the stream where the reference leaves it (the reference calls set.seed(seed) through
+// Rcpp::Function, helpers.cpp:10-14, and Rcpp::RNGScope brackets the export, RcppExports.cpp:38).
+// The export runs inside that RNGScope: its destructor calls PutRNGstate(), which OVERWRITES .Random.seed with R's
+// internal C state.  Writing the variable alone would therefore be lost; after the assignment GetRNGstate() is
+// called so that the internal state is re-read from .Random.seed — PutRNGstate() at scope exit then writes back
+// exactly what was set here.
 void restore_r_rng(unsigned int seed, const sqc_fit_out& out) {
   Environment base = Environment::namespace_env("base");
   Function set_seed = base["set.seed"];
   set_seed(seed);                                   // selects Mersenne-Twister exactly as the reference does
   Environment global = Environment::global_env();
-  IntegerVector rs = global[".Random.seed"];        // [0] = RNG kind code, [1] = mti, [2..625] = mt
+  IntegerVector rs = clone(as<IntegerVector>(global[".Random.seed"]));   // [0] = RNG kind code, [1] = mti, [2..625] = mt
   for (int i = 0; i < 625; ++i) rs[1 + i] = out.rng_state[i];
   global[".Random.seed"] = rs;
+  GetRNGstate();                                    // internal state <- .Random.seed (R_ext/Random.h)
 }
 
 void check_status(int status, const char* err) {

@@ -9,7 +9,7 @@ import ctypes as C
 
 import numpy as np
 
-SQC_ABI_VERSION = 1
+SQC_ABI_VERSION = 2
 SQC_IPC_HANDLE_BYTES = 64
 SQC_N_KERNEL_FAMILIES = 8
 
@@ -58,6 +58,7 @@ class SqcFitArgs(C.Structure):
         ("cell_offset", C.c_int64),
         ("N_total", C.c_int64),
         ("peer_handles", C.c_void_p),
+        ("n_gpus", C.c_int32),
     ]
 
 
@@ -208,7 +209,7 @@ class FitBuffers:
 
 def make_fit_args(x, groups, D, J, K, N, em_iters, *, init_z=None, init_gamma=None, mcd_alpha=0.5,
                   mcd_iters=50, seed=0, track=False, rng_mode=SQC_RNG_R_COMPAT, device=-1,
-                  rank=0, world=1, cell_offset=0, N_total=None, peer_handles=None):
+                  rank=0, world=1, cell_offset=0, N_total=None, peer_handles=None, n_gpus=1):
     """Build a sqc_fit_args plus the list of numpy arrays that must stay alive during the call."""
     keep = []
     xa = f64_colmajor(x)
@@ -233,6 +234,7 @@ def make_fit_args(x, groups, D, J, K, N, em_iters, *, init_z=None, init_gamma=No
     a.track, a.rng_mode, a.device = int(bool(track)), int(rng_mode), int(device)
     a.rank, a.world, a.cell_offset = int(rank), int(world), int(cell_offset)
     a.N_total = int(N if N_total is None else N_total)
+    a.n_gpus = int(n_gpus)
     if peer_handles is not None:
         ph = np.ascontiguousarray(np.frombuffer(bytes(peer_handles), dtype=np.uint8))
         keep.append(ph)

@@ -9,7 +9,7 @@ import os
 from . import _abi as A
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsampleqc_cuda.so")
+LIB_PATH = os.environ.get("SQC_LIB") or os.path.join(_HERE, "libsampleqc_cuda.so")          # SQC_LIB: a development variant of the same library
 _LIB = None
 
 # every symbol include/sampleqc_cuda.h declares
@@ -17,7 +17,7 @@ EXPORTS = (
     "sqc_fit_robust", "sqc_fit_mle", "sqc_outlier_maha", "sqc_init_clusts",
     "sqc_session_create", "sqc_session_run", "sqc_session_fetch", "sqc_session_stats", "sqc_session_profile",
     "sqc_session_destroy", "sqc_xchg_export", "sqc_xchg_release",
-    "sqc_trim", "sqc_abi_version", "sqc_device_count", "sqc_status_name", "sqc_device_qchisq", "sqc_device_rkeys", "sqc_device_rkeys_share", "sqc_device_expneg", "sqc_mt_jump_poly",
+    "sqc_trim", "sqc_abi_version", "sqc_device_count", "sqc_status_name", "sqc_device_qchisq", "sqc_device_rkeys", "sqc_device_rkeys_share", "sqc_device_expneg", "sqc_mt_jump_poly", "sqc_fp64_peak", "sqc_plan_shards",
 )
 
 
@@ -71,6 +71,10 @@ def lib():
     L.sqc_device_rkeys.restype = C.c_int
     L.sqc_device_rkeys_share.argtypes = [C.c_uint32, C.c_int64, C.c_int, C.c_int, C.c_int, A.c_int32_p, C.POINTER(C.c_int64), A.c_int32_p, C.c_int, C.c_char_p, C.c_size_t]
     L.sqc_device_rkeys_share.restype = C.c_int
+    L.sqc_fp64_peak.argtypes = [C.c_int, A.c_double_p, C.c_char_p, C.c_size_t]
+    L.sqc_fp64_peak.restype = C.c_int
+    L.sqc_plan_shards.argtypes = [A.c_int32_p, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), A.c_int32_p]
+    L.sqc_plan_shards.restype = C.c_int
     L.sqc_mt_jump_poly.argtypes = [C.c_uint64, C.c_void_p]
     L.sqc_mt_jump_poly.restype = C.c_int
     if L.sqc_abi_version() != A.SQC_ABI_VERSION:

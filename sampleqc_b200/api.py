@@ -22,20 +22,21 @@ from ._lib import check, lib
 
 
 def fit_sampleqc_robust_cpp(x, init_z, groups, D, J, K, N, em_iters, mcd_alpha, mcd_iters, seed, track=False,
-                            rng_mode=SQC_RNG_R_COMPAT, device=-1, alloc=None, out=None):
+                            rng_mode=SQC_RNG_R_COMPAT, device=-1, alloc=None, out=None, n_gpus=1):
     """reference src/fit_sampleQC_robust_cpp.cpp:451-577; returns the Rcpp list as a dict (:562-575).
-    `out`: a FitBuffers of matching shape to be reused across calls (e.g. pinned host memory)."""
+    `out`: a FitBuffers of matching shape to be reused across calls (e.g. pinned host memory).
+    `n_gpus` > 1 (or -1 = all visible): the library shards this one call over the GPUs of the process."""
     args, keep = A.make_fit_args(x, groups, D, J, K, N, em_iters, init_z=init_z, mcd_alpha=mcd_alpha,
-                                 mcd_iters=mcd_iters, seed=seed, track=track, rng_mode=rng_mode, device=device)
+                                 mcd_iters=mcd_iters, seed=seed, track=track, rng_mode=rng_mode, device=device, n_gpus=n_gpus)
     bufs = out if out is not None else A.FitBuffers(D, J, K, N, em_iters, SQC_VARIANT_ROBUST, track, alloc=alloc)
     err = C.create_string_buffer(512)
     check(lib().sqc_fit_robust(C.byref(args), C.byref(bufs.out), err, 512), err)
     return bufs.as_list()
 
 
-def fit_sampleqc_mle_cpp(x, init_gamma_i, groups, D, J, K, N, n_iter, seed, device=-1, alloc=None):
+def fit_sampleqc_mle_cpp(x, init_gamma_i, groups, D, J, K, N, n_iter, seed, device=-1, alloc=None, n_gpus=1):
     """reference src/fit_sampleQC_mle_cpp.cpp:279-357; returns the Rcpp list as a dict (:341-356)."""
-    args, keep = A.make_fit_args(x, groups, D, J, K, N, n_iter, init_gamma=init_gamma_i, seed=seed, device=device)
+    args, keep = A.make_fit_args(x, groups, D, J, K, N, n_iter, init_gamma=init_gamma_i, seed=seed, device=device, n_gpus=n_gpus)
     bufs = A.FitBuffers(D, J, K, N, n_iter, SQC_VARIANT_MLE, alloc=alloc)
     err = C.create_string_buffer(512)
     check(lib().sqc_fit_mle(C.byref(args), C.byref(bufs.out), err, 512), err)
@@ -225,3 +226,11 @@ def device_expneg(x, device=-1):
     err = C.create_string_buffer(512)
     check(lib().sqc_device_expneg(A.ptr_d(x), A.ptr_d(out), x.size, device, err, 512), err)
     return out
+
+
+def fp64_peak(device=-1) -> float:
+    """measured fp64 FMA instructions per second of the device (x 2 = FLOP/s)"""
+    v = C.c_double(0)
+    err = C.create_string_buffer(512)
+    check(lib().sqc_fp64_peak(int(device), C.byref(v), err, 512), err)
+    return v.value

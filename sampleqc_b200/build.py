@@ -7,7 +7,7 @@ import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "sqc_lib.cu")
-OUT = os.path.join(_HERE, "libsampleqc_cuda.so")
+OUT = os.environ.get("SQC_BUILD_OUT") or os.path.join(_HERE, "libsampleqc_cuda.so")      # SQC_BUILD_OUT: development variants
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-pthread"]
 

@@ -100,3 +100,46 @@ int sqc_mt_jump_poly(uint64_t e, uint32_t* out624) {
   mtpoly::xpow((unsigned long long)e, out624);
   return mtpoly::self_check() ? SQC_OK : SQC_ERR_COMM;
 }
+
+// measured fp64 FMA throughput of the device (the co-limit of the E-step / partition passes):
+// every thread runs 8 independent DFMA chains; returns FMA instructions per second over the whole GPU (x 2 = FLOP/s)
+int sqc_fp64_peak(int device, double* dfma_per_s, char* err, size_t errlen) {
+  return guarded([&] {
+    if (!dfma_per_s) fail(SQC_ERR_BAD_ARG, "null output");
+    int d; select_device(device, &d);
+    int n_sm = 0; CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, d));
+    double* out = nullptr; CK(cudaMalloc((void**)&out, sizeof(double)));
+    cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    const int iters = 8192, grid = n_sm * 2, threads = 1024;
+    k_fp64_peak<<<grid, threads>>>(out, 64, 1.0000001);            // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+      CK(cudaEventRecord(a)); k_fp64_peak<<<grid, threads>>>(out, iters, 1.0000001); CK(cudaEventRecord(b)); CK(cudaEventSynchronize(b));
+      float ms = 0; CK(cudaEventElapsedTime(&ms, a, b)); best = std::min(best, ms);
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
+    *dfma_per_s = (double)grid * threads * 8.0 * iters / (best * 1e-3);
+  }, err, errlen);
+}
+
+// host-only test hook: the shards sqc_fit_robust / sqc_fit_mle cut for n_gpus GPUs (sqc_inproc_host.inl).  shard_cells
+// receives n_gpus + 1 cell boundaries, sample_rank[j] the shard that owns sample code j (-1: a sample without cells goes
+// to the last shard).  Returns the number of shards (<= n_gpus), 0 when the samples are interleaved (one GPU is used),
+// < 0 on bad arguments.  Needs no GPU.
+int sqc_plan_shards(const int32_t* groups, int64_t N, int32_t J, int32_t n_gpus, int64_t* shard_cells, int32_t* sample_rank) {
+  if (!groups || N < 1 || J < 1 || n_gpus < 1 || n_gpus > XCHG_MAX_WORLD || !shard_cells) return SQC_ERR_BAD_ARG;
+  sqc_fit_args a = {}; a.N = N; a.J = J; a.groups = groups;
+  std::vector<InprocShard> sh;
+  try { if (!make_shards(&a, n_gpus, sh)) return 0; } catch (const SqcFail& e) { return e.code > 0 ? -e.code : e.code; }
+  if (sample_rank) for (int j = 0; j < J; ++j) sample_rank[j] = -1;
+  for (size_t q = 0; q < sh.size(); ++q) {
+    shard_cells[q] = sh[q].i0; shard_cells[q + 1] = sh[q].i1;
+    if (sample_rank) for (int c : sh[q].codes) if (sample_rank[c] < 0 && sh[q].i1 > sh[q].i0) {
+      // codes of empty samples are appended to the last shard: keep them at -1
+      bool has = false;
+      for (long long i = sh[q].i0; i < sh[q].i1 && !has; ++i) has = groups[i] == c;
+      if (has) sample_rank[c] = (int)q;
+    }
+  }
+  return (int)sh.size();
+}

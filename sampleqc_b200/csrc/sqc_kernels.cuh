@@ -59,6 +59,7 @@ struct Dev {
   // parameters
   double* mu0; double* alpha; double* beta; double* sigma; double* linv; double* ainv; double* logP; double* Pk;
   double* p_jk; double* logp_jk;
+  double* dens_cons; double* dens_tab; int* dens_slow;     // density constants of the passes (k_after_mstep): K x DensK::SZ | J x K x 33 | J
   // tile partials / reduced statistics
   double* t_ll1; double* t_ll2; int* t_nk; double* t_sk; int* s_base; int* t_rel; unsigned int* done_ctr; unsigned int* mcd_sync; double* t_col;
   int* n_jk; double* s_jk;
@@ -101,31 +102,6 @@ template <int NT> __device__ __forceinline__ long long block_excl_scan(long long
   return sh[w] + inc - v;
 }
 
-// ---------------------------------------------------------------------------------------------
-// per-(tile, component) density constants staged in shared memory
-//   mean = alpha_j + beta_k (the reference forms mu_ik first: robust_cpp.cpp:363,423), inverse Cholesky
-//   rows, log p_jk, log-normaliser, p_jk, normaliser  (RcppDist::dmvnorm)
-// ---------------------------------------------------------------------------------------------
-template <int D> struct ParK { static constexpr int SZ = D + SQC_TRI(D) + 4; };
-
-template <int D> __device__ __forceinline__ void stage_params(const Dev& s, int j, double* sh /* K * SZ */) {
-  constexpr int SZ = ParK<D>::SZ;
-  for (int idx = threadIdx.x; idx < s.K * SZ; idx += blockDim.x) {
-    const int k = idx / SZ, e = idx % SZ;
-    double v;
-    if (e < D) v = s.alpha[j * D + e] + s.beta[k * D + e];
-    else if (e < D + SQC_TRI(D)) {
-      int t = e - D, r = 0;
-      while ((r + 1) * (r + 2) / 2 <= t) ++r;
-      int c = t - r * (r + 1) / 2;
-      v = s.linv[k * D * D + r + D * c];
-    } else if (e == D + SQC_TRI(D)) v = s.logp_jk[j * s.K + k];
-    else if (e == D + SQC_TRI(D) + 1) v = s.logP[k];
-    else if (e == D + SQC_TRI(D) + 2) v = s.p_jk[j * s.K + k];
-    else v = s.Pk[k];
-    sh[idx] = v;
-  }
-}
 // squared Mahalanobis norm |Linv v|^2 with Linv packed lower-triangular row-major
 template <int D> __device__ __forceinline__ double maha_tri(const double (&v)[D], const double* lt) {
   double q = 0.0;
@@ -140,24 +116,281 @@ template <int D> __device__ __forceinline__ double maha_tri(const double (&v)[D]
 }
 
 // ---------------------------------------------------------------------------------------------
-// E-step pass.  One CTA per sample-aligned tile.
-//   MODE 0: like_2 + new labels + z_delta + statistics of the NEW labels   (:506, :509, :519)
-//   MODE 1: statistics of the current labels only (initial labelling)
-// Statistics per tile: n_k (int) and sum_k x (D doubles) -> reduced per sample by k_post_stats.
+// per-cell mixture densities (RcppDist::dmvnorm at robust_cpp.cpp:364, :424), K components at
+// ~22 fp64 instructions per (cell, component) at D = 3.
+//
+//   * alpha_j is subtracted from the cell ONCE (xp = x - alpha_j); per component the whitened residual is the affine
+//     form  y = L_k^-1 xp - c_k  with  c_k = L_k^-1 beta_k  (the reference forms mu_ik = alpha_j + beta_k first; the
+//     two differ by rounding only), so the per-component constants L_k^-1, c_k do not depend on the sample;
+//   * exp(-q/2) by table + short polynomial with the reduction done on q itself:  k = round(-q 16/ln2),
+//     r' = q + k ln2/16 (|r'| <= ln2/32),  exp(-q/2) = 2^(k/32) exp(-r'/2);  exp(-r'/2) by its degree-4 Taylor
+//     polynomial (relative error <= 1.3e-12, far inside the 1e-8 bar on the likelihoods — the labels do not use it);
+//     2^(j/32), j = k mod 32, comes from a shared-memory table that already carries the component's weight
+//     p_jk (2 pi)^(-D/2) det^(-1/2), and 2^(k div 32) is added to the exponent field: 8 fp64 instructions per term
+//     including the accumulation (the general exp_neg below: 15);
+//   * cells whose likelihood is not safely inside the normal range (every exponent below ~ -530: cells tens of
+//     standard deviations from every component; NaN / Inf input) are recomputed by dens_slow with exp_neg, which
+//     follows the reference's arithmetic down to the subnormals.
 // ---------------------------------------------------------------------------------------------
-template <int D, int MODE>
-__global__ void __launch_bounds__(EST_THREADS, (D <= 4) ? SQC_EST_MINB : 2) k_estep(Dev s) {        // D > 4: 2 CTAs / 128 registers (no spills), measured on C4
-  constexpr int CPT = TileCfg<D>::CPT, SZ = ParK<D>::SZ, NW = EST_THREADS / 32;
+template <int D> struct DensK { static constexpr int SZ = SQC_TRI(D) + D; };         // L^-1 packed lower (row-major), c = L^-1 beta
+constexpr int DENS_TAB = 33;                      // per (sample, component): 32 weighted table entries w 2^(i/32) + the log weight
+constexpr int DENS_KMIN = -900 * 32;              // fast path: exp(-q/2) >= 2^-900; the weights lie in (1e-20, 1e20), so the exponent arithmetic cannot wrap
+constexpr double DENS_SAFE = 1e-230;              // a likelihood under this is recomputed on the slow path (clamped terms are < 1e-249)
+
+// shared-memory footprint of the constants of K components (doubles): per-component constants + weight tables + alpha_j
+template <int D> __host__ __device__ constexpr int dens_doubles(int K) { return K * DensK<D>::SZ + K * DENS_TAB + D + 2; }
+
+// Copy the constants of sample j's tile into shared memory (they are derived once per M-step by k_after_mstep: no
+// arithmetic and no dependent loads in the prologue of the ~10^4 tile CTAs).  Needs a barrier after.
+template <int D> __device__ __forceinline__ void stage_dens(const Dev& s, int j, double* cons, double* tab, double* aj, bool with_like) {
+  const int K = s.K;
+  if (with_like) {
+    for (int idx = threadIdx.x; idx < K * DensK<D>::SZ; idx += blockDim.x) cons[idx] = s.dens_cons[idx];
+    const double* tj = s.dens_tab + (size_t)j * K * DENS_TAB;
+    for (int idx = threadIdx.x; idx < K * DENS_TAB; idx += blockDim.x) tab[idx] = tj[idx];
+  }
+  if (threadIdx.x < D) aj[threadIdx.x] = s.alpha[j * D + threadIdx.x];
+}
+// the derivation (one warp per sample; Pk, logP: the component normalisers in shared memory)
+template <int D> __device__ __forceinline__ void derive_dens_sample(const Dev& s, int j, int lane, const double* Pk, const double* logP) {
+  const int K = s.K;
+  double* tj = s.dens_tab + (size_t)j * K * DENS_TAB;
+  bool bad = false;
+  for (int k = 0; k < K; ++k) {
+    const double w = s.p_jk[j * K + k] * Pk[k];              // p_jk * normaliser (:424)
+    bad = bad || !(w > 1e-20 && w < 1e20);
+    tj[k * DENS_TAB + lane] = w * c_exp_tab[lane];
+    if (lane == 0) tj[k * DENS_TAB + 32] = s.logp_jk[j * K + k] + logP[k];   // log(p_jk) + log-normaliser (:364)
+  }
+  if (lane == 0) s.dens_slow[j] = bad ? 1 : 0;               // weights outside the range the fast path's exponent arithmetic is safe for
+}
+template <int D> __device__ __forceinline__ void derive_dens_component(const Dev& s, int k, const double* Li /* D x D column-major */) {
+  constexpr int TRI = SQC_TRI(D), SZ = DensK<D>::SZ;
+  double* ck = s.dens_cons + k * SZ;
+  for (int r = 0; r < D; ++r) {
+    double c = 0.0;
+    for (int cc = 0; cc <= r; ++cc) { const double l = Li[r + D * cc]; ck[r * (r + 1) / 2 + cc] = l; c = fma(l, s.beta[k * D + cc], c); }
+    ck[TRI + r] = c;
+  }
+}
+
+// the reference's arithmetic for one cell (mean formed first, general exp with gradual underflow): the slow path.
+// Takes plain pointers: a reference to the by-value kernel parameter block would force a copy of it into local memory.
+template <int D> __device__ __noinline__ double dens_slow(const double* xcell, long long N, const double* aj, const double* beta, const double* linv,
+                                                          const double* pj, const double* Pk, int K) {
+  double x[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) x[d] = xcell[(long long)d * N];
+  double like = 0.0;
+  for (int k = 0; k < K; ++k) {
+    double v[D], lt[SQC_TRI(D)];
+#pragma unroll
+    for (int d = 0; d < D; ++d) v[d] = x[d] - (aj[d] + beta[k * D + d]);
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+      for (int c = 0; c <= r; ++c) lt[r * (r + 1) / 2 + c] = linv[k * D * D + r + D * c];
+    const double q = maha_tri<D>(v, lt);
+    like += pj[k] * (Pk[k] * exp_neg(-0.5 * q));
+  }
+  return like;
+}
+
+// squared whitened norm of xp under component constants pk = {L^-1 packed, c}
+template <int D> __device__ __forceinline__ double maha_affine(const double (&xp)[D], const double* pk) {
+  double q = 0.0;
+#pragma unroll
+  for (int r = 0; r < D; ++r) {
+    double y = -pk[SQC_TRI(D) + r];
+#pragma unroll
+    for (int c = 0; c <= r; ++c) y = fma(pk[r * (r + 1) / 2 + c], xp[c], y);
+    q = fma(y, y, q);
+  }
+  return q;
+}
+// like += w 2^(j/32) (table entry) * 2^n * exp(-r'/2).  The exponent k is clamped to [DENS_KMIN, 0] as an integer: a
+// cell that far out (or with q beyond the range the rounding trick is exact for) contributes ~2^-900 w times a bounded
+// polynomial — nothing beside a regular term, and under DENS_SAFE when every component is that far away, which sends
+// the cell to dens_slow; NaN / Inf distances give a NaN term and take the same route.
+__device__ __forceinline__ double dens_term(double q, const double* tabk, double like) {
+  const double magic = 6755399441055744.0;
+  const double t = fma(q, -23.083120654223414192, magic);             // -16 / ln 2
+  const double kf = t - magic;
+  const double rp = fma(kf, 4.33216987849965803e-02, q);              // ln2 / 16:  r' = q + k ln2/16
+  double p = fma(rp, 1.0 / 384.0, -1.0 / 48.0);
+  p = fma(p, rp, 0.125);
+  p = fma(p, rp, -0.5);
+  p = fma(p, rp, 1.0);
+  const int k = min(max(__double2loint(t), DENS_KMIN), 0);
+  const double w = tabk[k & 31];
+  const double sc = __hiloint2double(__double2hiint(w) + ((k >> 5) << 20), __double2loint(w));
+  return fma(sc, p, like);
+}
+
+// ---------------------------------------------------------------------------------------------
+// E-step pass.  One CTA per sample-aligned tile.
+//   like_2 (:506) + new labels (calc_expected_z :344-396, :509) + z_delta (:519) + the CHANGE of the per-(tile,
+//   component) statistics n_k, sum_k x that update_alpha_j :116-157 / update_p_jk :322-341 are computed from:
+//   a cell that moves from component a to b subtracts its x from (tile, a) and adds it to (tile, b), applied in
+//   (cell slot, lane) order per warp and the warps in warp order — bit-reproducible.  Warps without a changed
+//   label (the common case after the first iterations) skip that part.  The initial statistics come from
+//   k_tile_stats (one full pass per fit).
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(EST_THREADS, (D <= 4) ? SQC_EST_MINB : 2) k_estep(Dev s) {
+  constexpr int CPT = TileCfg<D>::CPT, SZ = DensK<D>::SZ, NW = EST_THREADS / 32;
   extern __shared__ double sh_dyn[];
-  double* sh_par = sh_dyn;                                   // K * SZ
-  double* sh_red = sh_par + s.K * SZ;                        // NW * K * (D + 1)
+  const int K = s.K, KD = K * (D + 1);
+  double* cons = sh_dyn;                                     // K * SZ
+  double* tab = cons + K * SZ;                               // K * DENS_TAB
+  double* aj = tab + K * DENS_TAB;                           // D (+ pad)
+  double* dw = aj + D + 2;                                   // NW * K * (D + 1) statistic deltas (zeroed lazily)
   __shared__ double sh_w[NW];
   __shared__ int sh_i[NW * 2];
+  __shared__ int sh_flag[2];                                 // [1] some warp changed labels
   if (!s.ctl->cont) return;
   const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int j = s.tile_sample[t], start = s.tile_start[t], len = s.tile_len[t];
-  if (MODE == 0) stage_params<D>(s, j, sh_par);
-  double xv[CPT][D]; int zo[CPT]; bool valid[CPT];
+  // the cell loads go out first; the constants are copied while they are in flight
+  double xp[CPT][D]; int zo[CPT]; bool valid[CPT];
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) {
+    const int i = c * EST_THREADS + tid;
+    valid[c] = i < len;
+    const long long gi = (long long)start + (valid[c] ? i : 0);
+#pragma unroll
+    for (int d = 0; d < D; ++d) xp[c][d] = ld_stream(s.x + (long long)d * s.N + gi);
+    zo[c] = (int)ld_stream_u8(s.z + gi);
+  }
+  const bool slow_tile = s.dens_slow[j] != 0;
+  if (tid < 2) sh_flag[tid] = 0;
+  stage_dens<D>(s, j, cons, tab, aj, true);
+  __syncthreads();
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const double a = aj[d];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) xp[c][d] -= a;
+  }
+  double best[CPT], like[CPT]; int zn[CPT];
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) { best[c] = -CUDART_INF; like[c] = 0.0; zn[c] = 0; }
+  for (int k = 0; k < K; ++k) {
+    const double* pk = cons + k * SZ;
+    const double* tk = tab + k * DENS_TAB;
+    const double lc = tk[32];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const double q = maha_affine<D>(xp[c], pk);
+      const double l = fma(-0.5, q, lc);                     // log(p_jk) + dmvnorm(log = TRUE), :364
+      if (l > best[c]) { best[c] = l; zn[c] = k; }           // strict >, first max, :375-378
+      like[c] = dens_term(q, tk, like[c]);                   // p_jk * dmvnorm(log = FALSE), :424
+    }
+  }
+  int nzero = 0, delta = 0;
+  bool anyc = false, suspect = slow_tile;
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) {
+    suspect = suspect || (valid[c] && !(like[c] >= DENS_SAFE));
+    if (valid[c] && !(best[c] > -CUDART_INF)) nzero += K;    // like_max stays -inf through all K tests, :380-382
+    const bool chg = valid[c] && zn[c] != zo[c];
+    if (chg) { s.z[(long long)start + c * EST_THREADS + tid] = (uint8_t)zn[c]; ++delta; }
+    anyc = anyc || chg;
+  }
+  if (suspect) {                                             // rare: one test per thread on the fast path
+#pragma unroll
+    for (int c = 0; c < CPT; ++c)
+      if (valid[c] && (slow_tile || !(like[c] >= DENS_SAFE)))
+        like[c] = dens_slow<D>(s.x + (long long)start + c * EST_THREADS + tid, s.N, s.alpha + j * D, s.beta, s.linv, s.p_jk + j * K, s.Pk, K);
+  }
+  double ll = sum_log<CPT>(like, valid);                     // :428
+  // labels that moved: statistics of the old component lose the cell, those of the new one gain it
+  if (__any_sync(0xffffffffu, anyc)) {
+    double* mydw = dw + (size_t)w * KD;
+    bool chg[CPT]; int nchg = 0;
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) { chg[c] = valid[c] && zn[c] != zo[c]; nchg += __popc(__ballot_sync(0xffffffffu, chg[c])); }
+    if (nchg <= 6) {
+      // a few cells: applied one by one in (cell slot, lane) order
+      for (int e = lane; e < KD; e += 32) mydw[e] = 0.0;
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        unsigned mk = __ballot_sync(0xffffffffu, chg[c]);
+        while (mk) {
+          const int l = __ffs(mk) - 1; mk &= mk - 1;
+          if (lane == l) {
+            double* a = mydw + zo[c] * (D + 1); double* b = mydw + zn[c] * (D + 1);
+            a[0] -= 1.0; b[0] += 1.0;
+            const long long gi = (long long)start + c * EST_THREADS + tid;
+#pragma unroll
+            for (int d = 0; d < D; ++d) { const double xv = s.x[(long long)d * s.N + gi]; a[1 + d] -= xv; b[1 + d] += xv; }
+          }
+          __syncwarp();
+        }
+      }
+    } else {
+      // many cells (the first iterations): per component a signed masked sum over the warp, fixed shuffle tree
+      double xv[CPT][D];
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        const long long gi = (long long)start + c * EST_THREADS + tid;
+#pragma unroll
+        for (int d = 0; d < D; ++d) xv[c][d] = chg[c] ? s.x[(long long)d * s.N + gi] : 0.0;
+      }
+      constexpr int NP = (D + 1 <= 2) ? 2 : (D + 1 <= 4) ? 4 : (D + 1 <= 8) ? 8 : 16;
+      for (int k = 0; k < K; ++k) {
+        double sv[NP];
+#pragma unroll
+        for (int e = 0; e < NP; ++e) sv[e] = 0.0;
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) {
+          const double sg = chg[c] ? ((zn[c] == k ? 1.0 : 0.0) - (zo[c] == k ? 1.0 : 0.0)) : 0.0;
+          sv[0] += sg;
+#pragma unroll
+          for (int d = 0; d < D; ++d) sv[1 + d] = fma(sg, xv[c][d], sv[1 + d]);
+        }
+        warp_sum_vec<NP>(sv, lane);
+        constexpr int STR = 32 / NP;
+        if ((lane & (STR - 1)) == 0 && lane / STR < D + 1) mydw[k * (D + 1) + lane / STR] = sv[0];
+      }
+    }
+    if (lane == 0) { sh_flag[1] = 1; sh_i[NW + w] = 1; }
+  } else if (lane == 0) sh_i[NW + w] = 0;
+  ll = warp_sum(ll); delta = warp_sum_i(delta); nzero = warp_sum_i(nzero);
+  if (lane == 0) { sh_w[w] = ll; sh_i[w] = delta; }
+  if (nzero && lane == 0) atomicAdd(&s.ctl->n_zero, nzero);
+  __syncthreads();
+  if (sh_flag[1]) {
+    for (int idx = tid; idx < KD; idx += EST_THREADS) {
+      double acc = 0.0;
+#pragma unroll
+      for (int ww = 0; ww < NW; ++ww) if (sh_i[NW + ww]) acc += dw[(size_t)ww * KD + idx];
+      const int k = idx / (D + 1), e = idx % (D + 1);
+      if (e == 0) s.t_nk[t * K + k] += (int)acc;
+      else s.t_sk[((long long)t * K + k) * D + (e - 1)] += acc;
+    }
+  }
+  if (tid == 0) {
+    double a = 0.0; int dl = 0;
+#pragma unroll
+    for (int ww = 0; ww < NW; ++ww) { a += sh_w[ww]; dl += sh_i[ww]; }
+    s.t_ll2[t] = a;
+    if (dl) atomicAdd(&s.ctl->z_delta, dl);
+  }
+}
+
+// statistics of the CURRENT labels, one full pass (initial labelling): per tile and component the count and the sum
+// of x, reduced over the tile in fixed order
+template <int D>
+__global__ void __launch_bounds__(EST_THREADS) k_tile_stats(Dev s) {
+  constexpr int CPT = TileCfg<D>::CPT, NW = EST_THREADS / 32;
+  extern __shared__ double sh_dyn[];
+  double* sh_red = sh_dyn;                                   // NW * K * (D + 1)
+  if (!s.ctl->cont) return;
+  const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int start = s.tile_start[t], len = s.tile_len[t];
+  double xv[CPT][D]; int zn[CPT]; bool valid[CPT];
 #pragma unroll
   for (int c = 0; c < CPT; ++c) {
     const int i = c * EST_THREADS + tid;
@@ -165,46 +398,8 @@ __global__ void __launch_bounds__(EST_THREADS, (D <= 4) ? SQC_EST_MINB : 2) k_es
     const long long gi = (long long)start + (valid[c] ? i : 0);
 #pragma unroll
     for (int d = 0; d < D; ++d) xv[c][d] = ld_stream(s.x + (long long)d * s.N + gi);
-    zo[c] = (int)ld_stream_u8(s.z + gi);
+    zn[c] = (int)ld_stream_u8(s.z + gi);
   }
-  int zn[CPT];
-  double ll = 0.0; int delta = 0, nzero = 0;
-  if (MODE == 0) {
-    __syncthreads();
-    double best[CPT], like[CPT];
-#pragma unroll
-    for (int c = 0; c < CPT; ++c) { best[c] = -CUDART_INF; like[c] = 0.0; zn[c] = 0; }
-    for (int k = 0; k < s.K; ++k) {
-      const double* pk = sh_par + k * SZ;
-      double m[D], lt[SQC_TRI(D)];
-#pragma unroll
-      for (int d = 0; d < D; ++d) m[d] = pk[d];
-#pragma unroll
-      for (int e = 0; e < SQC_TRI(D); ++e) lt[e] = pk[D + e];
-      const double logp = pk[D + SQC_TRI(D)], logP = pk[D + SQC_TRI(D) + 1], p = pk[D + SQC_TRI(D) + 2], P = pk[D + SQC_TRI(D) + 3];
-#pragma unroll
-      for (int c = 0; c < CPT; ++c) {
-        double v[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) v[d] = xv[c][d] - m[d];
-        const double q = maha_tri<D>(v, lt);
-        const double l = logp + (logP - 0.5 * q);            // log(p_jk) + dmvnorm(log=TRUE), :364
-        if (l > best[c]) { best[c] = l; zn[c] = k; }         // strict >, first max, :375-378
-        if (valid[c] && best[c] == -CUDART_INF) ++nzero;     // :380-382
-        like[c] += p * (P * exp_neg(-0.5 * q));              // p_jk * dmvnorm(log=FALSE), :424
-      }
-    }
-    ll = sum_log<CPT>(like, valid);                          // :428
-#pragma unroll
-    for (int c = 0; c < CPT; ++c) if (valid[c]) {
-      delta += (zn[c] != zo[c]);
-      s.z[(long long)start + c * EST_THREADS + tid] = (uint8_t)zn[c];
-    }
-  } else {
-#pragma unroll
-    for (int c = 0; c < CPT; ++c) zn[c] = zo[c];
-  }
-  // statistics of the labels zn: per component count and sum of x, reduced over the tile
   constexpr int NP = (D + 1 <= 2) ? 2 : (D + 1 <= 4) ? 4 : (D + 1 <= 8) ? 8 : 16;
   for (int k = 0; k < s.K; ++k) {
     double sv[NP];
@@ -221,8 +416,6 @@ __global__ void __launch_bounds__(EST_THREADS, (D <= 4) ? SQC_EST_MINB : 2) k_es
     constexpr int STR = 32 / NP;
     if ((lane & (STR - 1)) == 0 && lane / STR < D + 1) sh_red[(w * s.K + k) * (D + 1) + lane / STR] = sv[0];
   }
-  ll = warp_sum(ll); delta = warp_sum_i(delta); nzero = warp_sum_i(nzero);
-  if (lane == 0) { sh_w[w] = ll; sh_i[w] = delta; sh_i[NW + w] = nzero; }
   __syncthreads();
   for (int idx = tid; idx < s.K * (D + 1); idx += EST_THREADS) {
     const int k = idx / (D + 1), e = idx % (D + 1);
@@ -231,14 +424,6 @@ __global__ void __launch_bounds__(EST_THREADS, (D <= 4) ? SQC_EST_MINB : 2) k_es
     for (int ww = 0; ww < NW; ++ww) acc += sh_red[(ww * s.K + k) * (D + 1) + e];
     if (e == 0) s.t_nk[t * s.K + k] = (int)acc;
     else s.t_sk[((long long)t * s.K + k) * D + (e - 1)] = acc;
-  }
-  if (MODE == 0 && tid == 0) {
-    double a = 0.0; int dl = 0, nz = 0;
-#pragma unroll
-    for (int ww = 0; ww < NW; ++ww) { a += sh_w[ww]; dl += sh_i[ww]; nz += sh_i[NW + ww]; }
-    s.t_ll2[t] = a;
-    if (dl) atomicAdd(&s.ctl->z_delta, dl);
-    if (nz) atomicAdd(&s.ctl->n_zero, nz);
   }
 }
 
@@ -250,71 +435,77 @@ __global__ void __launch_bounds__(EST_THREADS, (D <= 4) ? SQC_EST_MINB : 2) k_es
 // ---------------------------------------------------------------------------------------------
 template <int D, int LIKE>
 __global__ void __launch_bounds__(EST_THREADS, (D <= 4) ? SQC_PART_MINB : 3) k_partition(Dev s) {   // D > 4: 3 CTAs / 80 registers, measured on C4
-  constexpr int CPT = TileCfg<D>::CPT, SZ = ParK<D>::SZ, NW = EST_THREADS / 32;
+  constexpr int CPT = TileCfg<D>::CPT, SZ = DensK<D>::SZ, NW = EST_THREADS / 32;
   extern __shared__ double sh_dyn[];
-  double* sh_par = sh_dyn;                                   // K * SZ
-  int* sh_cnt = (int*)(sh_par + s.K * SZ);                   // CPT * NW * K exclusive prefixes
+  const int K = s.K;
+  double* cons = sh_dyn;                                     // K * SZ
+  double* tab = cons + K * SZ;                               // K * DENS_TAB
+  double* aj = tab + K * DENS_TAB;                           // D (+ pad)
+  int* sh_cnt = (int*)(aj + D + 2);                          // CPT * NW * K exclusive prefixes
   __shared__ double sh_w[NW];
   if (!s.ctl->cont) return;
   const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (t == 0 && tid < 2 * SQC_MAXK + 1) s.mcd_sync[tid] = 0u;      // epochs, arrivals and status word of the k_mcd launch that follows
   const int j = s.tile_sample[t], start = s.tile_start[t], len = s.tile_len[t];
-  if (LIKE) stage_params<D>(s, j, sh_par);
-  double xv[CPT][D]; int zo[CPT]; bool valid[CPT];
+  double xp[CPT][D]; int zo[CPT]; bool valid[CPT];
 #pragma unroll
   for (int c = 0; c < CPT; ++c) {
     const int i = c * EST_THREADS + tid;
     valid[c] = i < len;
     const long long gi = (long long)start + (valid[c] ? i : 0);
 #pragma unroll
-    for (int d = 0; d < D; ++d) xv[c][d] = ld_stream(s.x + (long long)d * s.N + gi);
+    for (int d = 0; d < D; ++d) xp[c][d] = ld_stream(s.x + (long long)d * s.N + gi);
     zo[c] = valid[c] ? (int)ld_stream_u8(s.z + gi) : -1;
   }
+  stage_dens<D>(s, j, cons, tab, aj, LIKE != 0);
   // per (iteration c, warp, component) counts -> exclusive prefix in tile order (c, warp, lane)
   int myrank[CPT];
-  for (int k = 0; k < s.K; ++k) {
+  for (int k = 0; k < K; ++k) {
 #pragma unroll
     for (int c = 0; c < CPT; ++c) {
       const unsigned b = __ballot_sync(0xffffffffu, zo[c] == k);
       if (zo[c] == k) myrank[c] = __popc(b & ((1u << lane) - 1u));
-      if (lane == 0) sh_cnt[(c * NW + w) * s.K + k] = __popc(b);
+      if (lane == 0) sh_cnt[(c * NW + w) * K + k] = __popc(b);
     }
   }
   __syncthreads();
-  if (tid < s.K) {                                           // tiny serial scan per component
+  if (tid < K) {                                             // tiny serial scan per component
     // base of this tile inside the cluster segment: cells of the earlier samples (s_base) + of the earlier tiles of this sample (t_rel)
-    int run = s.s_base[j * s.K + tid] + s.t_rel[t * s.K + tid];
-    for (int e = 0; e < CPT * NW; ++e) { int v = sh_cnt[e * s.K + tid]; sh_cnt[e * s.K + tid] = run; run += v; }
+    int run = s.s_base[j * K + tid] + s.t_rel[t * K + tid];
+    for (int e = 0; e < CPT * NW; ++e) { int v = sh_cnt[e * K + tid]; sh_cnt[e * K + tid] = run; run += v; }
+  }
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const double a = aj[d];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) xp[c][d] -= a;             // :274
   }
   __syncthreads();
-  double aj[D];
-#pragma unroll
-  for (int d = 0; d < D; ++d) aj[d] = s.alpha[j * D + d];
 #pragma unroll
   for (int c = 0; c < CPT; ++c) if (valid[c]) {
-    const long long pos = s.clu_off[zo[c]] + sh_cnt[(c * NW + w) * s.K + zo[c]] + myrank[c];
+    const long long pos = s.clu_off[zo[c]] + sh_cnt[(c * NW + w) * K + zo[c]] + myrank[c];
 #pragma unroll
-    for (int d = 0; d < D; ++d) s.rs[(long long)d * s.rs_stride + pos] = xv[c][d] - aj[d];   // :274
+    for (int d = 0; d < D; ++d) s.rs[(long long)d * s.rs_stride + pos] = xp[c][d];
   }
   if (LIKE) {
     double like[CPT];
 #pragma unroll
     for (int c = 0; c < CPT; ++c) like[c] = 0.0;
-    for (int k = 0; k < s.K; ++k) {
-      const double* pk = sh_par + k * SZ;
-      double m[D], lt[SQC_TRI(D)];
+    for (int k = 0; k < K; ++k) {
+      const double* pk = cons + k * SZ;
+      const double* tk = tab + k * DENS_TAB;
 #pragma unroll
-      for (int d = 0; d < D; ++d) m[d] = pk[d];
+      for (int c = 0; c < CPT; ++c) like[c] = dens_term(maha_affine<D>(xp[c], pk), tk, like[c]);
+    }
+    const bool slow_tile = s.dens_slow[j] != 0;
+    bool suspect = slow_tile;
 #pragma unroll
-      for (int e = 0; e < SQC_TRI(D); ++e) lt[e] = pk[D + e];
-      const double p = pk[D + SQC_TRI(D) + 2], P = pk[D + SQC_TRI(D) + 3];
+    for (int c = 0; c < CPT; ++c) suspect = suspect || (valid[c] && !(like[c] >= DENS_SAFE));
+    if (suspect) {
 #pragma unroll
-      for (int c = 0; c < CPT; ++c) {
-        double v[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) v[d] = xv[c][d] - m[d];
-        like[c] += p * (P * exp_neg(-0.5 * maha_tri<D>(v, lt)));
-      }
+      for (int c = 0; c < CPT; ++c)
+        if (valid[c] && (slow_tile || !(like[c] >= DENS_SAFE)))
+          like[c] = dens_slow<D>(s.x + (long long)start + c * EST_THREADS + tid, s.N, s.alpha + j * D, s.beta, s.linv, s.p_jk + j * K, s.Pk, K);
     }
     double ll = sum_log<CPT>(like, valid);
     ll = warp_sum(ll);

@@ -23,22 +23,29 @@ void key_stream_setup(sqc_session* S) {
     kb.ints = 2 * (size_t)S->key_q;
   }
   S->keybuf = kb.p;
-  cudaIpcMemHandle_t h;
-  if (cudaIpcGetMemHandle(&h, kb.p) != cudaSuccess) fail(SQC_ERR_COMM, "cudaIpcGetMemHandle (key buffer) failed");
-  // all-gather of the 64-byte handles through the window
-  unsigned long long* d_in = S->alloc<unsigned long long>(8); unsigned long long* d_out = S->alloc<unsigned long long>(8 * XCHG_MAX_WORLD);
-  CK(cudaMemcpyAsync(d_in, &h, 64, cudaMemcpyHostToDevice, S->st));
-  k_xchg_gather_u64<<<1, 256, 0, S->st>>>(S->xc.dev, XCHG_CH_HOST + 0, d_in, d_out, 8, nullptr);
-  std::vector<unsigned char> hs((size_t)64 * W);
-  CK(cudaMemcpyAsync(hs.data(), d_out, hs.size(), cudaMemcpyDeviceToHost, S->st));
-  CK(cudaStreamSynchronize(S->st));
-  for (int q = 0; q < W; ++q) {                                   // mapped for the life of the session (closed in its destructor)
-    if (q == r) { S->key_peer[q] = kb.p; continue; }
-    cudaIpcMemHandle_t ph; memcpy(&ph, hs.data() + (size_t)64 * q, 64);
-    void* p = nullptr;
-    cudaError_t e = cudaIpcOpenMemHandle(&p, ph, cudaIpcMemLazyEnablePeerAccess);
-    if (e != cudaSuccess) fail(SQC_ERR_COMM, "cudaIpcOpenMemHandle (key buffer of rank %d) failed: %s", q, cudaGetErrorString(e));
-    S->key_mapped[q] = p; S->key_peer[q] = (const int*)p;
+  if (S->grp) {
+    // in-process ranks: every key buffer is an ordinary device pointer once all of them exist
+    CK(cudaDeviceSynchronize());
+    if (!S->grp->sync(true)) fail(SQC_ERR_COMM, "another GPU of the fit failed while the key buffers were set up");
+    for (int q = 0; q < W; ++q) S->key_peer[q] = key_buf_local(S->grp->device[q]).p;
+  } else {
+    cudaIpcMemHandle_t h;
+    if (cudaIpcGetMemHandle(&h, kb.p) != cudaSuccess) fail(SQC_ERR_COMM, "cudaIpcGetMemHandle (key buffer) failed");
+    // all-gather of the 64-byte handles through the window
+    unsigned long long* d_in = S->alloc<unsigned long long>(8); unsigned long long* d_out = S->alloc<unsigned long long>(8 * XCHG_MAX_WORLD);
+    CK(cudaMemcpyAsync(d_in, &h, 64, cudaMemcpyHostToDevice, S->st));
+    k_xchg_gather_u64<<<1, 256, 0, S->st>>>(S->xc.dev, XCHG_CH_HOST + 0, d_in, d_out, 8, nullptr);
+    std::vector<unsigned char> hs((size_t)64 * W);
+    CK(cudaMemcpyAsync(hs.data(), d_out, hs.size(), cudaMemcpyDeviceToHost, S->st));
+    CK(cudaStreamSynchronize(S->st));
+    for (int q = 0; q < W; ++q) {                                   // mapped for the life of the session (closed in its destructor)
+      if (q == r) { S->key_peer[q] = kb.p; continue; }
+      cudaIpcMemHandle_t ph; memcpy(&ph, hs.data() + (size_t)64 * q, 64);
+      void* p = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&p, ph, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) fail(SQC_ERR_COMM, "cudaIpcOpenMemHandle (key buffer of rank %d) failed: %s", q, cudaGetErrorString(e));
+      S->key_mapped[q] = p; S->key_peer[q] = (const int*)p;
+    }
   }
   // jump polynomials: row 0 = call to call (floor(N_total / 624) chunks), row 1 = start of the call to this rank's share
   static std::map<unsigned long long, std::vector<uint32_t>> rows;      // derived once per distance

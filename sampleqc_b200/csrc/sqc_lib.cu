@@ -6,6 +6,7 @@
 // nothing returns to the host until convergence) and copies the results back.  There is no CPU
 // fallback: without a CUDA device every compute entry point returns SQC_ERR_CUDA.
 #include <algorithm>
+#include <condition_variable>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -24,12 +25,14 @@
 
 #include "../../include/sampleqc_cuda.h"
 #include "sqc_mcd.cuh"
-#include "sqc_stream.cuh"
 #include "sqc_mt.cuh"
 #include "sqc_mle.cuh"
 #include "sqc_xchg.cuh"
 #include "sqc_init.cuh"
 
+#ifndef SQC_MCD_RESERVE_SMS
+#define SQC_MCD_RESERVE_SMS 50   // SMs k_mcd leaves to the key-stream kernels (R-compatible keys only), see session_create
+#endif
 #ifndef SQC_FOR_D
 #define SQC_FOR_D(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
 #endif
@@ -85,34 +88,47 @@ __global__ void k_ctl_start_loop(Dev s) {
 // what RcppDist::dmvnorm recomputes on every call, SURVEY Appendix A4, hoisted); the other blocks update
 // p_jk = (1 + n_jk) / (K + n_j) (update_p_jk :322-341) when with_p is set
 template <int D>
-__device__ void derive_component(Dev& s, int k) {
+__device__ void derive_component(Dev& s, int k, bool store, double* shPk, double* shlogP) {
   double S[D * D], Ai[D * D];
 #pragma unroll
   for (int e = 0; e < D * D; ++e) S[e] = s.sigma[k * D * D + e];
   const bool ok1 = inv_small<D>(S, Ai);
   double L[SQC_MAXD * SQC_MAXD], Li[SQC_MAXD * SQC_MAXD];
   const bool ok2 = small_chol_inv(S, D, L, Li);
+  const double det = small_det(S, D);
+  shlogP[k] = -1.0 * (D / 2.0) * 1.837877066409345483560659472811 - 0.5 * log(det);
+  shPk[k] = 1.0 / sqrt(pow(6.283185307179586476925286766559, (double)D) * det);
+  if (!store) return;
   if (!ok1) { atomicCAS(&s.ctl->status, 0, SQC_D_SINGULAR); return; }
   if (!ok2) { atomicCAS(&s.ctl->status, 0, SQC_D_NOT_SPD); return; }
-  const double det = small_det(S, D);
 #pragma unroll
   for (int e = 0; e < D * D; ++e) { s.linv[k * D * D + e] = Li[e]; s.ainv[k * D * D + e] = Ai[e]; }
-  s.logP[k] = -1.0 * (D / 2.0) * 1.837877066409345483560659472811 - 0.5 * log(det);
-  s.Pk[k] = 1.0 / sqrt(pow(6.283185307179586476925286766559, (double)D) * det);
+  s.logP[k] = shlogP[k]; s.Pk[k] = shPk[k];
+  derive_dens_component<D>(s, k, Li);
 }
+// after an M-step.  Every block derives the component normalisers for itself (K tiny factorisations; block 0 also
+// stores the per-component constants: inverse Cholesky factor, inverse, normalisers — what RcppDist::dmvnorm
+// recomputes on every call, SURVEY Appendix A4, hoisted); then one warp per sample: p_jk = (1 + n_jk) / (K + n_j)
+// (update_p_jk :322-341) when with_p is set, and the sample's weighted exp tables / log weights for the two passes.
 template <int D>
-__global__ void k_after_mstep(Dev s, int with_p) {
+__global__ void __launch_bounds__(256) k_after_mstep(Dev s, int with_p) {
+  __shared__ double shPk[SQC_MAXK], shlogP[SQC_MAXK];
   if (!s.ctl->cont) return;
-  if (blockIdx.x == 0) { if ((int)threadIdx.x < s.K) derive_component<D>(s, threadIdx.x); return; }
-  if (!with_p) return;
-  const int j = (blockIdx.x - 1) * blockDim.x + threadIdx.x;
+  const int K = s.K, lane = threadIdx.x & 31;
+  if ((int)threadIdx.x < K) derive_component<D>(s, threadIdx.x, blockIdx.x == 0, shPk, shlogP);
+  __syncthreads();
+  const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (j >= s.J) return;
-  long long nj = s.K;
-  for (int k = 0; k < s.K; ++k) nj += s.n_jk[j * s.K + k];
-  for (int k = 0; k < s.K; ++k) {
-    const double p = (1.0 + (double)s.n_jk[j * s.K + k]) / (double)nj;
-    s.p_jk[j * s.K + k] = p; s.logp_jk[j * s.K + k] = log(p);
+  if (with_p) {
+    long long nj = K;
+    for (int k = 0; k < K; ++k) nj += s.n_jk[j * K + k];
+    if (lane < K) {
+      const double p = (1.0 + (double)s.n_jk[j * K + lane]) / (double)nj;
+      s.p_jk[j * K + lane] = p; s.logp_jk[j * K + lane] = log(p);
+    }
+    __syncwarp();
   }
+  derive_dens_sample<D>(s, j, lane, shPk, shlogP);
 }
 // final relabel by ascending beta_k[,0] (robust_cpp.cpp:527-531, reorder_z :434-445) and packing of
 // every output into the column-major shapes of the Rcpp list
@@ -149,6 +165,15 @@ __global__ void k_widen_labels(const int* in, uint8_t* out, long long n, int K, 
 __global__ void k_expneg(const double* x, double* out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = exp_neg(x[i]);
+}
+__global__ void __launch_bounds__(1024) k_fp64_peak(double* out, int iters, double m) {
+  double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, 1e-9); a1 = fma(a1, m, 1e-9); a2 = fma(a2, m, 1e-9); a3 = fma(a3, m, 1e-9);
+    a4 = fma(a4, m, 1e-9); a5 = fma(a5, m, 1e-9); a6 = fma(a6, m, 1e-9); a7 = fma(a7, m, 1e-9);
+  }
+  const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (r == 12345.678) *out = r;
 }
 __global__ void k_qchisq(const double* p, const double* df, double* out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -229,6 +254,26 @@ ChunkCache g_chunks;
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
+// one sharded fit inside ONE process (sqc_fit_args.n_gpus > 1): a host thread and a device per rank.  The ranks meet at
+// a few host-side sync points while their sessions are built (windows allocated and cleared, key buffers allocated);
+// a rank that fails says so there, and every rank gives up before an exchange kernel could wait for it.
+// ---------------------------------------------------------------------------------------------
+struct InprocGroup {
+  int world = 1; int device[XCHG_MAX_WORLD] = {};
+  std::mutex mu; std::condition_variable cv; int arrived = 0; unsigned long long gen = 0; bool failed = false;
+  bool sync(bool ok) {                                  // true iff no rank has failed so far
+    std::unique_lock<std::mutex> lk(mu);
+    if (!ok) failed = true;
+    if (failed) { cv.notify_all(); return false; }
+    const unsigned long long g = gen;
+    if (++arrived == world) { arrived = 0; ++gen; cv.notify_all(); }
+    else cv.wait(lk, [&] { return gen != g || failed; });
+    return !failed;
+  }
+  void abort() { std::lock_guard<std::mutex> lk(mu); failed = true; cv.notify_all(); }
+};
+
+// ---------------------------------------------------------------------------------------------
 // session
 // ---------------------------------------------------------------------------------------------
 struct sqc_session {
@@ -243,6 +288,7 @@ struct sqc_session {
   McdBufs mb{};
   MleBufs ml{};
   Xchg xc{};
+  InprocGroup* grp = nullptr;            // non-null: the ranks are threads of this process
   uint8_t* z0 = nullptr; double* alpha0 = nullptr; double* gamma0 = nullptr;
   int mt_target_blocks = 49;
   bool rng_after_mcd = false;          // generate the next call's keys behind (not beside) the M-step kernel
@@ -252,9 +298,10 @@ struct sqc_session {
   long long key_q = 0, key_mine = 0; uint32_t* mt_rows = nullptr; uint32_t* mt_jwin = nullptr; uint32_t* mt_seq2 = nullptr; const int* key_peer[XCHG_MAX_WORLD] = {}; void* key_mapped[XCHG_MAX_WORLD] = {};
   double* o_buf = nullptr; int* o_z = nullptr; int* o_korder = nullptr; OutPtrs optr{};
   size_t o_doubles = 0;
-  int mcd_grid = 0, n_sm = 0, grid_estep = 0, grid_part = 0;
-  bool stream_kernels = true;            // persistent TMA-fed E-step / partition kernels (SQC_STREAM=0: one CTA per tile, round-1 kernels)
-  bool sorted = true; std::vector<long long> perm;      // perm[i] = original index of the cell stored at i
+  int mcd_grid = 0, n_sm = 0;
+  long long ld = 0;                      // leading dimension of the caller's x / init_gamma
+  bool sorted = true; std::vector<long long> perm;      // perm[i] = original index of the cell stored at i (cells of a sample were interleaved)
+  std::vector<int> smap;                                // non-empty: internal sample r is the caller's sample smap[r] (contiguous runs in non-ascending code order)
   bool profile = false;
   struct Ev { cudaEvent_t a, b; int fam; const char* tag = nullptr; };
   std::vector<Ev> evs; size_t ev_used = 0;
@@ -321,47 +368,23 @@ struct Launch {
   void done() { if (ev) CK(cudaEventRecord(ev->b, stream())); CK(cudaGetLastError()); }
 };
 
-// grid of the persistent E-step / partition kernels: every SM holds as many CTAs as fit, each owns a contiguous tile range
-template <int D> int stream_grid(sqc_session* S, bool part) {
-  const Dev& s = S->dev;
-  int per = 0;
-  if (part) {
-    CK(cudaFuncSetAttribute(k_partition_stream<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)partition_stream_smem<D>(s.K)));
-    CK(cudaFuncSetAttribute(k_partition_stream<D, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)partition_stream_smem<D>(s.K)));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_partition_stream<D, 1>, EST_THREADS, partition_stream_smem<D>(s.K)));
-  } else {
-    CK(cudaFuncSetAttribute(k_estep_stream<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)estep_stream_smem<D>(s.K)));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_estep_stream<D>, EST_THREADS, estep_stream_smem<D>(s.K)));
-  }
-  if (per < 1) fail(SQC_ERR_CUDA, "streaming kernel for D = %d does not fit on an SM", D);
-  return std::max(1, std::min(s.T, S->n_sm * per));
-}
 template <int D> void launch_estep(sqc_session* S, int mode) {
   const Dev& s = S->dev;
-  if (mode == 0 && S->stream_kernels) {
-    if (!S->grid_estep) S->grid_estep = stream_grid<D>(S, false);
+  if (mode == 0) {
+    const size_t sm = (size_t)(dens_doubles<D>(s.K) + (EST_THREADS / 32) * s.K * (D + 1)) * sizeof(double);
     Launch L(S, SQC_KF_ESTEP);
-    k_estep_stream<D><<<S->grid_estep, EST_THREADS, estep_stream_smem<D>(s.K), S->st>>>(s);
+    k_estep<D><<<s.T, EST_THREADS, sm, S->st>>>(s);
     L.done();
-    return;
+  } else {                                                   // statistics of the initial labelling (one full pass per fit)
+    const size_t sm = (size_t)((EST_THREADS / 32) * s.K * (D + 1)) * sizeof(double);
+    Launch L(S, SQC_KF_INIT);
+    k_tile_stats<D><<<s.T, EST_THREADS, sm, S->st>>>(s);
+    L.done();
   }
-  const size_t sm = (size_t)(s.K * ParK<D>::SZ + (EST_THREADS / 32) * s.K * (D + 1)) * sizeof(double);
-  Launch L(S, mode == 0 ? SQC_KF_ESTEP : SQC_KF_INIT);
-  if (mode == 0) k_estep<D, 0><<<s.T, EST_THREADS, sm, S->st>>>(s);
-  else k_estep<D, 1><<<s.T, EST_THREADS, sm, S->st>>>(s);
-  L.done();
 }
 template <int D> void launch_partition(sqc_session* S, int like) {
   const Dev& s = S->dev;
-  if (S->stream_kernels) {
-    if (!S->grid_part) S->grid_part = stream_grid<D>(S, true);
-    Launch L(S, SQC_KF_PARTITION);
-    if (like) k_partition_stream<D, 1><<<S->grid_part, EST_THREADS, partition_stream_smem<D>(s.K), S->st>>>(s);
-    else k_partition_stream<D, 0><<<S->grid_part, EST_THREADS, partition_stream_smem<D>(s.K), S->st>>>(s);
-    L.done();
-    return;
-  }
-  const size_t sm = (size_t)(s.K * ParK<D>::SZ) * sizeof(double) + (size_t)TileCfg<D>::CPT * (EST_THREADS / 32) * s.K * sizeof(int);
+  const size_t sm = (size_t)dens_doubles<D>(s.K) * sizeof(double) + (size_t)TileCfg<D>::CPT * (EST_THREADS / 32) * s.K * sizeof(int);
   Launch L(S, SQC_KF_PARTITION);
   if (like) k_partition<D, 1><<<s.T, EST_THREADS, sm, S->st>>>(s);
   else k_partition<D, 0><<<s.T, EST_THREADS, sm, S->st>>>(s);
@@ -479,7 +502,7 @@ void do_update_alpha(sqc_session* S) {
   switch (S->D) { SQC_FOR_D(SQC_CASE_ALPHA) default: fail(SQC_ERR_BAD_ARG, "D = %d not compiled in", S->D); }
   L.done();
 }
-#define SQC_CASE_AFTER(DD) case DD: k_after_mstep<DD><<<1 + (with_p ? (S->J + 127) / 128 : 0), 128, 0, S->st>>>(S->dev, with_p); break;
+#define SQC_CASE_AFTER(DD) case DD: k_after_mstep<DD><<<(S->J + 7) / 8, 256, 0, S->st>>>(S->dev, with_p); break;
 void do_after_mstep(sqc_session* S, int with_p) {
   Launch L(S, SQC_KF_UPDATE);
   switch (S->D) { SQC_FOR_D(SQC_CASE_AFTER) default: fail(SQC_ERR_BAD_ARG, "D = %d not compiled in", S->D); }
@@ -527,15 +550,16 @@ struct PhaseTimer {
   void mark(const char* w) { if (!on || n >= 16) return; const double t = now_ms(); what[n] = w; dt[n++] = t - t0; t0 = t; }
   void dump(const char* head) { if (!on) return; fprintf(stderr, "[sqc timing] %s:", head); for (int i = 0; i < n; ++i) fprintf(stderr, " %s %.2f", what[i], dt[i]); fprintf(stderr, "\n"); }
 };
-sqc_session* session_create(const sqc_fit_args* a, int variant) {
+sqc_session* session_create(const sqc_fit_args* a, int variant, InprocGroup* grp = nullptr, long long ld = 0) {
   PhaseTimer pt;
   check_args(a, variant);
+  if (ld <= 0) ld = a->N;                               // leading dimension of the host matrices x / init_gamma (in-process shards are row ranges)
   std::unique_ptr<sqc_session> up(new sqc_session());
   sqc_session* S = up.get();
   select_device(a->device, &S->device);
   CK(cudaStreamCreateWithFlags(&S->st, cudaStreamNonBlocking));
   CK(cudaDeviceGetAttribute(&S->n_sm, cudaDevAttrMultiProcessorCount, S->device));
-  S->D = a->D; S->J = a->J; S->K = a->K; S->N = a->N; S->variant = variant;
+  S->D = a->D; S->J = a->J; S->K = a->K; S->N = a->N; S->variant = variant; S->grp = grp; S->ld = ld;
   S->world = a->world > 1 ? a->world : 1; S->rank = S->world > 1 ? a->rank : 0;
   S->N_total = S->world > 1 ? a->N_total : a->N;
   S->em_iters = a->em_iters; S->mcd_iters = a->mcd_iters; S->mcd_alpha = a->mcd_alpha; S->seed = a->seed;
@@ -557,16 +581,24 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
   pt.mark("setup");
   // ---- upload x first (asynchronous from pinned memory), scan the sample layout on the host meanwhile ----
   Dev& s = S->dev;
-  S->stream_kernels = getenv("SQC_STREAM") && atoi(getenv("SQC_STREAM")) != 0;   // experimental (measured slower, profiles/r2e): off by default
-  s.x = S->alloc<double>((size_t)N * D + 2, false);          // + 2: the bulk copies of the last column round up to 16 bytes
-  CK(cudaMemcpyAsync(s.x, a->x, (size_t)N * D * sizeof(double), cudaMemcpyHostToDevice, S->st));
-  // cells of a sample must be contiguous; permute once if they are not
+  s.x = S->alloc<double>((size_t)N * D, false);
+  CK(cudaMemcpy2DAsync(s.x, (size_t)N * sizeof(double), a->x, (size_t)ld * sizeof(double), (size_t)N * sizeof(double), D, cudaMemcpyHostToDevice, S->st));
+  // Cells of a sample must be contiguous in HBM (tiles never cross a sample boundary).  Three cases:
+  //   groups non-decreasing                     -> as is;
+  //   every sample one contiguous run, any order -> as is, samples relabelled by order of appearance (rows of alpha_j /
+  //      p_jk are put back in code order on fetch).  This is what fit_sampleqc() sends: x is an rbind over samples, but
+  //      groups = as.integer(factor(sample_ids)) numbers them alphabetically (R/fit_sampleqc.R:205-216).  Cell order is
+  //      untouched, so the randperm keys pair with the same cells as in the reference (restrict_to_x_k keeps cell order);
+  //   cells of a sample interleaved             -> stable counting sort by sample, once.  The fit is valid, but the
+  //      R-compatible key stream is then consumed in the sorted cell order, not the caller's.
   std::vector<long long> n_j(J, 0);
-  bool sorted = true;
+  bool sorted = true, contiguous = true;
+  std::vector<int> run_code;                          // sample codes in order of appearance (while contiguous)
   {
     const int nth = (N >= (1 << 20)) ? 4 : 1;           // a few host threads: the scan hides behind the upload of x
     std::vector<std::vector<long long>> cnt(nth, std::vector<long long>(J, 0));
-    std::vector<long long> bad(nth, -1); std::vector<char> srt(nth, 1);
+    std::vector<std::vector<int>> runs(nth);
+    std::vector<long long> bad(nth, -1); std::vector<char> srt(nth, 1), ovf(nth, 0);
     auto scan = [&](int t) {
       const long long i0 = N * t / nth, i1 = N * (t + 1) / nth;
       long long* c = cnt[t].data();
@@ -575,7 +607,10 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
         const int g = a->groups[i];
         if ((unsigned)g >= (unsigned)J) { bad[t] = i; return; }
         c[g]++;
-        if (g < prev) srt[t] = 0;
+        if (g != prev) {
+          if (g < prev) srt[t] = 0;
+          if ((long long)runs[t].size() <= J) runs[t].push_back(g); else ovf[t] = 1;
+        }
         prev = g;
       }
     };
@@ -586,17 +621,36 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
     for (int t = 0; t < nth; ++t) {
       if (bad[t] >= 0) { cudaStreamSynchronize(S->st); fail(SQC_ERR_BAD_ARG, "groups out of range at cell %lld", bad[t]); }
       if (!srt[t]) sorted = false;
+      if (ovf[t]) contiguous = false;
       for (int j = 0; j < J; ++j) n_j[j] += cnt[t][j];
+      for (int g : runs[t]) if ((long long)run_code.size() <= J) run_code.push_back(g); else contiguous = false;
+    }
+    if (!sorted && contiguous) {                        // one run per sample?
+      std::vector<char> seen(J, 0);
+      for (int g : run_code) { if (seen[g]) { contiguous = false; break; } seen[g] = 1; }
     }
   }
   pt.mark("x_enqueue+scan");
-  S->sorted = sorted;
-  if (!sorted) {                                    // stable counting sort by sample
+  S->sorted = sorted || contiguous;                     // cells stay where they are
+  S->smap.clear();
+  if (!sorted && contiguous) {                          // relabel the samples by appearance; empty samples go last
+    std::vector<char> seen(J, 0);
+    for (int g : run_code) { S->smap.push_back(g); seen[g] = 1; }
+    for (int j = 0; j < J; ++j) if (!seen[j]) S->smap.push_back(j);
+    std::vector<long long> n_int(J);
+    for (int r = 0; r < J; ++r) n_int[r] = n_j[S->smap[r]];
+    n_j.swap(n_int);
+  } else if (!sorted) {                                 // stable counting sort by sample
+    if (S->rng_mode == SQC_RNG_R_COMPAT && variant == SQC_VARIANT_ROBUST) {
+      static bool warned = false;
+      if (!warned) { warned = true; fprintf(stderr, "sampleqc_cuda: cells of a sample are not contiguous; they are sorted by sample once, and the R-compatible random-start keys follow that sorted cell order\n"); }
+    }
     std::vector<long long> start(J + 1, 0);
     for (int j = 0; j < J; ++j) start[j + 1] = start[j] + n_j[j];
     S->perm.resize(N);
     for (long long i = 0; i < N; ++i) S->perm[start[a->groups[i]]++] = i;
   }
+  sorted = S->sorted;
   const int TILE = tile_cells(D);
   S->tile = TILE;
   std::vector<int> t_start, t_len, t_sample, s_tb(J + 1, 0), s_n(J);
@@ -623,6 +677,7 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
   s.sigma = S->alloc<double>((size_t)K * D * D); s.linv = S->alloc<double>((size_t)K * D * D); s.ainv = S->alloc<double>((size_t)K * D * D);
   s.logP = S->alloc<double>(K); s.Pk = S->alloc<double>(K);
   s.p_jk = S->alloc<double>((size_t)J * K); s.logp_jk = S->alloc<double>((size_t)J * K);
+  s.dens_cons = S->alloc<double>((size_t)K * (SQC_TRI(SQC_MAXD) + SQC_MAXD)); s.dens_tab = S->alloc<double>((size_t)J * K * DENS_TAB); s.dens_slow = S->alloc<int>(J);
   s.t_ll1 = S->alloc<double>(T); s.t_ll2 = S->alloc<double>(T);
   s.t_nk = S->alloc<int>((size_t)T * K); s.t_sk = S->alloc<double>((size_t)T * K * D); s.s_base = S->alloc<int>((size_t)J * K); s.t_rel = S->alloc<int>((size_t)T * K); s.done_ctr = S->alloc<unsigned int>(4);
   s.t_col = S->alloc<double>((size_t)T * D);
@@ -646,13 +701,27 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
     CK(cudaStreamSynchronize(S->st));
     std::vector<double> col(N);
     for (int d = 0; d < D; ++d) {
-      for (long long i = 0; i < N; ++i) col[i] = a->x[(size_t)d * N + S->perm[i]];
+      for (long long i = 0; i < N; ++i) col[i] = a->x[(size_t)d * ld + S->perm[i]];
       CK(cudaMemcpyAsync(s.x + (size_t)d * N, col.data(), (size_t)N * sizeof(double), cudaMemcpyHostToDevice, S->st));
       CK(cudaStreamSynchronize(S->st));
     }
   }
   if (S->world > 1) {
-    try { xchg_open(S->xc, S->device, S->rank, S->world, a->peer_handles); }
+    try {
+      if (grp) {
+        // in-process ranks: clear the own window, enable peer access, meet, then take the peers' windows as plain pointers
+        xchg_ensure(S->device, true);
+        for (int r = 0; r < S->world; ++r) if (grp->device[r] != S->device) {
+          cudaError_t e = cudaDeviceEnablePeerAccess(grp->device[r], 0);
+          if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+          else if (e != cudaSuccess) throw std::runtime_error(std::string("cudaDeviceEnablePeerAccess failed: ") + cudaGetErrorString(e));
+        }
+        CK(cudaStreamSynchronize(S->st));               // x is on the device: a failure so far is local
+        if (!grp->sync(true)) fail(SQC_ERR_COMM, "another GPU of the fit failed while the sessions were built");
+        xchg_open_inproc(S->xc, S->device, S->rank, S->world, grp->device);
+      } else xchg_open(S->xc, S->device, S->rank, S->world, a->peer_handles);
+    }
+    catch (const SqcFail&) { throw; }
     catch (const std::exception& e) { fail(SQC_ERR_COMM, "%s", e.what()); }
     S->xg_gather = S->alloc<unsigned long long>((size_t)XCHG_MAX_WORLD * SQC_MAXK); S->xg_vec = S->alloc<double>(16);
   }
@@ -672,6 +741,15 @@ sqc_session* session_create(const sqc_fit_args* a, int variant) {
     s.rs_stride = ((N + 32ll * (K + 1)) + 31) & ~31ll;
     s.rs = S->alloc<double>((size_t)s.rs_stride * D);
     S->mcd_grid = do_mcd_grid(D, S->n_sm);
+    if (S->rng_mode == SQC_RNG_R_COMPAT) {
+      // R-compatible keys: the M-step kernel leaves some SMs to the key-stream kernels of the NEXT call, which run beside
+      // it on the side stream (a CTA of k_mcd owns a whole SM, so they cannot share one; without free SMs the generation
+      // falls onto the E-step / partition passes and onto the critical path: +50 % per iteration at C3).  k_mcd is
+      // HBM / latency bound, not SM bound.
+      int reserve = getenv("SQC_MCD_RESERVE") ? atoi(getenv("SQC_MCD_RESERVE")) : SQC_MCD_RESERVE_SMS;
+      reserve = std::max(0, std::min(reserve, S->mcd_grid - 2 * K - 8));
+      S->mcd_grid -= reserve;
+    }
     McdBufs& mb = S->mb;
     mb.work = S->alloc<McdWork>(1);
     mb.hist = S->alloc<unsigned int>((size_t)K * MCD_NB);
@@ -871,11 +949,22 @@ void session_fetch(sqc_session* S, sqc_fit_out* o) {
   CK(cudaStreamSynchronize(S->st));
   const double* p = h.data();
   if (o->mu_0) memcpy(o->mu_0, p, sizeof(double) * D); p += D;
-  if (o->alpha_j) memcpy(o->alpha_j, p, sizeof(double) * J * D); p += (size_t)J * D;
+  auto rows_out = [&](double* dst, const double* src, int ncol) {    // J x ncol column-major; internal sample order -> the caller's codes
+    if (S->smap.empty()) { memcpy(dst, src, sizeof(double) * J * ncol); return; }
+    for (int c = 0; c < ncol; ++c) for (int r = 0; r < J; ++r) dst[S->smap[r] + (size_t)J * c] = src[r + (size_t)J * c];
+  };
+  if (o->alpha_j) rows_out(o->alpha_j, p, D); p += (size_t)J * D;
   if (o->beta_k) memcpy(o->beta_k, p, sizeof(double) * K * D); p += (size_t)K * D;
   if (o->sigma_k) memcpy(o->sigma_k, p, sizeof(double) * K * D * D); p += (size_t)K * D * D;
-  if (o->p_jk) memcpy(o->p_jk, p, sizeof(double) * J * K);
+  if (o->p_jk) rows_out(o->p_jk, p, K);
   if (S->track) reorder_track(S, o, korder);
+  if (S->track && !S->smap.empty()) {
+    std::vector<double> tmp;
+    for (int it = 0; it < em; ++it) {
+      if (o->track_alpha_j) { double* b = o->track_alpha_j + (size_t)it * J * D; tmp.assign(b, b + (size_t)J * D); rows_out(b, tmp.data(), D); }
+      if (o->track_p_jk) { double* b = o->track_p_jk + (size_t)it * J * K; tmp.assign(b, b + (size_t)J * K); rows_out(b, tmp.data(), K); }
+    }
+  }
   o->n_iter = S->h_ctl.iter; o->mcd_iters_hit = S->h_ctl.mcd_hit; o->n_zero_like = S->h_ctl.n_zero;
   o->rng_draws = (long long)(1 + S->h_ctl.iter) * S->N_total;
 }
@@ -904,14 +993,24 @@ int one_shot(const sqc_fit_args* a, sqc_fit_out* o, int variant, char* err, size
   return st;
 }
 
+#include "sqc_inproc_host.inl"
+
 }  // namespace
 
 #include "sqc_mle_host.inl"
 
 extern "C" {
 
-int sqc_fit_robust(const sqc_fit_args* a, sqc_fit_out* o, char* err, size_t errlen) { return one_shot(a, o, SQC_VARIANT_ROBUST, err, errlen); }
-int sqc_fit_mle(const sqc_fit_args* a, sqc_fit_out* o, char* err, size_t errlen) { return one_shot(a, o, SQC_VARIANT_MLE, err, errlen); }
+// n_gpus > 1 (or SQC_ALL_GPUS): the library shards the call over the GPUs of this process (sqc_inproc_host.inl)
+static int fit_entry(const sqc_fit_args* a, sqc_fit_out* o, int variant, char* err, size_t errlen) {
+  if (a && a->abi_version == SQC_ABI_VERSION) {
+    const int n = resolve_n_gpus(a);
+    if (n > 1) { const int st = fit_inproc(a, o, variant, n, err, errlen); if (st != -1000) return st; }
+  }
+  return one_shot(a, o, variant, err, errlen);
+}
+int sqc_fit_robust(const sqc_fit_args* a, sqc_fit_out* o, char* err, size_t errlen) { return fit_entry(a, o, SQC_VARIANT_ROBUST, err, errlen); }
+int sqc_fit_mle(const sqc_fit_args* a, sqc_fit_out* o, char* err, size_t errlen) { return fit_entry(a, o, SQC_VARIANT_MLE, err, errlen); }
 
 int sqc_session_create(const sqc_fit_args* a, int variant, sqc_session** out, char* err, size_t errlen) {
   if (out) *out = nullptr;

@@ -30,6 +30,14 @@
 // scale, det, Cholesky, loop test :84) and publishes the next epoch.  Clusters advance independently, so one
 // cluster's post-processing overlaps the streaming of the others and a slowly converging cluster does not
 // hold grid barriers for everybody.
+// Two worker classes.  A small cluster that needs many C-steps is the critical chain of a launch (10 rounds against 4-5
+// of the big ones at C3), and with one pool its renewed epoch has to wait until every worker has finished the share of
+// a big cluster it is in the middle of (non-preemptive, ~17 us of a ~33 us round).  So while big AND small clusters are
+// active, a fixed share of the workers (SQC_MCD_SMALL_WORKERS) serves only the small clusters (n_k <= N /
+// SQC_MCD_SMALL_DIV) and the others only the big ones; when one class has finished, its workers join the other.  Who
+// serves an epoch is decided by the leader and published in the epoch word ({number, done, all}), so the arrival count
+// it waits for and the set of per-CTA partials / candidate regions it reads are known exactly; the chunk dealing, hence
+// every reduction order, is a function of that set only: results stay bit-reproducible.
 #pragma once
 #include "sqc_kernels.cuh"
 #include "sqc_xchg.cuh"
@@ -58,6 +66,12 @@ constexpr int MCD_WARPS = MCD_THREADS / 32;
 #endif
 #ifndef SQC_MCD_KEY_SIGMAS
 #define SQC_MCD_KEY_SIGMAS 3.2    // half-width of the direct key band in standard deviations of the h-th key (a miss costs one regular round)
+#endif
+#ifndef SQC_MCD_SMALL_DIV
+#define SQC_MCD_SMALL_DIV 8       // a cluster with n_k <= N / SQC_MCD_SMALL_DIV is "small" (two worker classes, see k_mcd)
+#endif
+#ifndef SQC_MCD_SMALL_WORKERS
+#define SQC_MCD_SMALL_WORKERS 0.22 // share of the worker CTAs reserved for the small clusters while big ones are active (0: one class)
 #endif
 constexpr int MCD_NB = 4096;                         // histogram bins per window
 constexpr int MCD_NF = 1024;                         // fine bins inside the candidate bin (leader post; a 4 KB exchange on multi-GPU)
@@ -92,7 +106,7 @@ struct McdClu {
   unsigned long long blo, bhi;         // candidate bin (sortable bits)
   unsigned long long t_prev;           // last resolved threshold (distance bits), 0 = none
   int shift, phase, is_final, iters, n_hist_rounds, direct;   // direct: COLLECT round entered without a HIST round (predicted band)
-  int key_shift, pad2;                 // shift of the +-8 sigma key window while a direct key round is tried
+  int key_shift, serve_all;            // shift of the +-8 sigma key window while a direct key round is tried; serve_all: every worker serves this epoch (else: the cluster's class only)
   double last_rel, dens;               // relative change of the threshold over the last C-step; candidates per unit of relative width
   double band_c, band_w;               // centre and relative half-width of the predicted band of a direct distance round
   double det_old, det_new, q_chisq;
@@ -290,7 +304,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
   __shared__ unsigned long long sh_pT1[MCD_HMAX + 1], sh_pT2[MCD_HMAX + 1];   // leader: thresholds of the previous two calls by C-step index (0 = none)
   __shared__ double sh_pD1[MCD_HMAX + 1];
   __shared__ McdClu sh_clu;                    // worker: snapshot of the state of the cluster being streamed
-  __shared__ int sh_ep[SQC_MAXK], sh_eloc[SQC_MAXK], sh_done[SQC_MAXK], sh_off[SQC_MAXK];
+  __shared__ int sh_ep[SQC_MAXK], sh_eloc[SQC_MAXK], sh_done[SQC_MAXK], sh_off[SQC_MAXK], sh_offc[SQC_MAXK], sh_small[SQC_MAXK];
 
   if (!s.ctl->cont) return;                    // uniform across the grid (and across ranks): nobody reaches a barrier
   const long long t_entry = mb.trace ? gtimer() : 0;
@@ -303,6 +317,15 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
   const int regions = G * MCD_WARPS, region = b * MCD_WARPS + wid;
   const int NWK = G - K;                       // worker CTAs; CTAs 0 .. K-1 are the cluster leaders
   McdWork* W = mb.work;
+  // worker classes (identical on every CTA: derived from the global cluster sizes)
+  if (tid < K) sh_small[tid] = (s.clu_n_glob[tid] * (long long)SQC_MCD_SMALL_DIV <= s.N_total) ? 1 : 0;
+  __syncthreads();
+  int n_small = 0;
+  for (int k2 = 0; k2 < K; ++k2) n_small += sh_small[k2];
+  int NS = (int)((double)NWK * SQC_MCD_SMALL_WORKERS + 0.5);
+  if (NS < 4) NS = 4;
+  const bool split = n_small > 0 && n_small < K && NS < NWK && SQC_MCD_SMALL_WORKERS > 0.0;   // both classes present
+  if (!split) NS = 0;
 
   // ---- setup: one leader CTA per cluster ----------------------------------------------------
   if (b < K) {
@@ -366,13 +389,23 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
     const int k = b;
     __syncthreads();
     // publish = copy the state to global memory, fence, release the epoch (the workers snapshot it from there)
+    // epoch word = {number, done, all}: bit 0 = every worker serves this epoch (else the cluster's class only), bit 1 = done
+    const int my_small = sh_small[k];
     auto publish = [&](int epoch_no) {
+      if (tid == 0) {
+        int all = 1;
+        if (split) {                                               // the other class joins once all of ITS clusters are done
+          for (int k2 = 0; k2 < K; ++k2) if (sh_small[k2] != my_small && !(ld_acquire_u32(&mb.epoch[k2]) & 2u)) all = 0;
+        }
+        sh_clu.serve_all = all;
+      }
+      __syncthreads();
       const unsigned long long* src = (const unsigned long long*)&sh_clu;
       unsigned long long* dst = (unsigned long long*)&W->clu[k];
       for (int i = tid; i < (int)(sizeof(McdClu) / 8); i += MCD_THREADS) dst[i] = src[i];
       __threadfence();
       __syncthreads();
-      if (tid == 0) st_release_u32(&mb.epoch[k], (unsigned)epoch_no);
+      if (tid == 0) st_release_u32(&mb.epoch[k], ((unsigned)epoch_no << 2) | (sh_clu.phase == PH_DONE ? 2u : 0u) | (sh_clu.serve_all ? 1u : 0u));
     };
     int ep = 1;
     publish(1);
@@ -384,6 +417,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
       if (c.phase != PH_DONE) c.q_chisq = dev_qchisq((double)c.h / (double)c.n, D);
     }
     long long my_epochs = 0, my_cells = 0, my_bytes = 0;
+    unsigned int want_arrivals = 0;                               // (thread 0) cumulative
     for (;;) {
       if (tid == 0) sh_flag[2] = (sh_clu.phase != PH_DONE) ? 1 : 0;
       __syncthreads();
@@ -396,8 +430,8 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         const int ph = sh_clu.phase; const long long n = sh_clu.n_loc;
         const bool keyr = (ph == PH_KEY_HIST || ph == PH_KEY_COLLECT);
         my_cells += n; my_bytes += n * ((ph == PH_KEY_HIST ? 0 : 8 * D) + ((keyr && mb.keys) ? 4 : 0));
-        // every worker arrives once per epoch, whether or not it holds cells of this cluster
-        const unsigned int want_arrivals = (unsigned)NWK * (unsigned)ep;
+        // every worker of the serving set arrives once per epoch, whether or not it holds cells of this cluster
+        want_arrivals += (unsigned)(sh_clu.serve_all ? NWK : (my_small ? NS : NWK - NS));
         unsigned long long spins = 0;
         while (ld_acquire_u32(&mb.arrive[k]) < want_arrivals) { if (++spins > (1ull << 24)) { atomicCAS(&(*mb.status), 0, SQC_D_SELECT); break; } }   // watchdog (seconds)
         __threadfence();
@@ -469,6 +503,8 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         const unsigned long long blo = cl.blo;
         const int fshift = cl.shift > 10 ? cl.shift - 10 : 0;        // MCD_NF = 1024 fine bins inside the candidate bin
         const unsigned int* ccnt = mb.cand_cnt + (long long)k * regions;
+        // CTAs that served this epoch: only their partials / candidate regions are current
+        const int cta_lo = K + (cl.serve_all ? 0 : (my_small ? 0 : NS)), cta_hi = K + (cl.serve_all ? NWK : (my_small ? NS : NWK));
         // per-CTA moment partials: issue the loads first, use them at the end (warp (m mod warps) owns moment m)
         double part_pre[(NM + MCD_WARPS - 1) / MCD_WARPS];
 #pragma unroll
@@ -478,7 +514,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
           if (m < NM && have_part) {
             double pv[8];                                            // all loads in flight together (grids up to 256 CTAs)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { const int bb = lane + 32 * i; pv[i] = (bb < G) ? mb.part[((long long)bb * K + k) * NM + m] : 0.0; }
+            for (int i = 0; i < 8; ++i) { const int bb = lane + 32 * i; pv[i] = (bb >= cta_lo && bb < cta_hi) ? mb.part[((long long)bb * K + k) * NM + m] : 0.0; }
 #pragma unroll
             for (int i = 0; i < 8; ++i) a2 += pv[i];
           }
@@ -487,7 +523,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         // candidate counts of this thread's regions: same L2 round trip as the partials and the fine histogram
         unsigned int cn[MCD_RPT];
 #pragma unroll
-        for (int i = 0; i < MCD_RPT; ++i) { const int rg = tid * MCD_RPT + i; cn[i] = (rg < regions) ? ccnt[rg] : 0u; }
+        for (int i = 0; i < MCD_RPT; ++i) { const int rg = tid * MCD_RPT + i; cn[i] = (rg >= cta_lo * MCD_WARPS && rg < cta_hi * MCD_WARPS) ? ccnt[rg] : 0u; }
         // 1. fine histogram of the candidates: built by the workers with atomics on mb.fhist
         {
           constexpr int FPT = (MCD_NF + 4 + MCD_THREADS - 1) / MCD_THREADS;
@@ -847,10 +883,16 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
   } else {
     // =========================== worker: streams its share of every cluster whenever that cluster's state is renewed ===========================
     const int w = b - K;
+    const int wk_small = (split && w < NS) ? 1 : 0;                // this worker's class
     if (tid < K) { sh_eloc[tid] = 0; sh_done[tid] = 0; }
     if (tid == 0) {                                               // static chunk assignment: round robin over the concatenated chunk lists
-      long long run = 0;
-      for (int k = 0; k < K; ++k) { sh_off[k] = (int)(run % NWK); run += (s.clu_n[k] + CHUNK - 1) / CHUNK; }
+      long long run = 0, run_c[2] = {0, 0};
+      for (int k = 0; k < K; ++k) {
+        const long long nc = (s.clu_n[k] + CHUNK - 1) / CHUNK;
+        const int c = sh_small[k], Mc = c ? NS : NWK - NS;
+        sh_off[k] = (int)(run % NWK); run += nc;                    // every worker serves
+        sh_offc[k] = Mc > 0 ? (int)(run_c[c] % Mc) : 0; run_c[c] += nc;   // the cluster's class only
+      }
     }
     __syncthreads();
     unsigned long long idle = 0;
@@ -858,12 +900,16 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
       if (tid < K) sh_ep[tid] = (int)ld_acquire_u32(&mb.epoch[tid]);
       __syncthreads();
       // serve ONE renewed cluster per poll, the smallest first: a small cluster that needs many C-steps then cycles at
-      // its own (short) period instead of waiting for a sweep over the big ones
+      // its own (short) period instead of waiting for a sweep over the big ones.  Epochs meant for the other class and
+      // finished clusters are only noted.
       if (tid == 0) {
         int sel = -1, nd = 0;
         for (int k = 0; k < K; ++k) {
           if (sh_done[k]) { ++nd; continue; }
-          if (sh_ep[k] != sh_eloc[k] && (sel < 0 || s.clu_n[k] < s.clu_n[sel])) sel = k;
+          if (sh_ep[k] == sh_eloc[k]) continue;
+          if (sh_ep[k] & 2) { sh_done[k] = 1; sh_eloc[k] = sh_ep[k]; ++nd; continue; }
+          if (!(sh_ep[k] & 1) && sh_small[k] != wk_small) { sh_eloc[k] = sh_ep[k]; continue; }
+          if (sel < 0 || s.clu_n[k] < s.clu_n[sel]) sel = k;
         }
         sh_flag[0] = sel; sh_flag[1] = nd;
       }
@@ -879,15 +925,11 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
           for (int i = tid; i < (int)(sizeof(McdClu) / 8); i += MCD_THREADS) dst[i] = __ldcg(src + i);
         }
         __syncthreads();
-        if (sh_clu.phase == PH_DONE) {
-          __syncthreads();
-          if (tid == 0) { sh_done[k] = 1; sh_eloc[k] = ep; }
-          __syncthreads();
-          ++n_done;
-          continue;
-        }
+        // my place in the set of workers that serve this epoch
+        const int M = (ep & 1) ? NWK : (wk_small ? NS : NWK - NS), me = (ep & 1) ? w : (wk_small ? w : w - NS);
+        const int off_k = (ep & 1) ? sh_off[k] : sh_offc[k];
         const long long nch = (sh_clu.n_loc + CHUNK - 1) / CHUNK;
-        const long long c_first = ((long long)w - sh_off[k] + NWK) % NWK;
+        const long long c_first = ((long long)me - off_k + M) % M;
       const McdClu& cl = sh_clu;
       const int phase = cl.phase;
       const bool hist_round = (phase == PH_KEY_HIST || phase == PH_DIST_HIST);
@@ -911,7 +953,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
       unsigned int below = 0, nnan = 0, wcount = 0;
       const long long cbase = ((long long)k * regions + region) * MCD_CAPW;
 
-      for (long long ch = c_first; ch < nch; ch += NWK) {
+      for (long long ch = c_first; ch < nch; ch += M) {
         const long long e0 = ch * CHUNK;
         double r[CPT][D]; unsigned long long bits[CPT]; bool valid[CPT];
         long long epos[CPT];

@@ -11,11 +11,11 @@ __global__ void k_mle_pack_pk(Dev s, MleBufs m, OutPtrs o, double* out_pk) {
 void mle_alloc(sqc_session& S, const sqc_fit_args* a, MleBufs& m) {
   const int D = S.D, J = S.J, K = S.K; const long long N = S.N; const int T = S.dev.T;
   double* g0 = S.alloc<double>((size_t)N * K, false);
-  if (S.sorted) CK(cudaMemcpyAsync(g0, a->init_gamma, (size_t)N * K * sizeof(double), cudaMemcpyHostToDevice, S.st));
+  if (S.sorted) CK(cudaMemcpy2DAsync(g0, (size_t)N * sizeof(double), a->init_gamma, (size_t)S.ld * sizeof(double), (size_t)N * sizeof(double), K, cudaMemcpyHostToDevice, S.st));
   else {
     std::vector<double> col(N);
     for (int k = 0; k < K; ++k) {
-      for (long long i = 0; i < N; ++i) col[i] = a->init_gamma[(size_t)k * N + S.perm[i]];
+      for (long long i = 0; i < N; ++i) col[i] = a->init_gamma[(size_t)k * S.ld + S.perm[i]];
       CK(cudaMemcpyAsync(g0 + (size_t)k * N, col.data(), (size_t)N * sizeof(double), cudaMemcpyHostToDevice, S.st));
       CK(cudaStreamSynchronize(S.st));
     }
@@ -108,10 +108,14 @@ void mle_fetch(sqc_session* S, sqc_fit_out* o) {
   }
   const double* p = h.data();
   if (o->mu_0) memcpy(o->mu_0, p, sizeof(double) * D); p += D;
-  if (o->alpha_j) memcpy(o->alpha_j, p, sizeof(double) * J * D); p += (size_t)J * D;
+  auto rows_out = [&](double* dst, const double* src, int ncol) {    // internal sample order -> the caller's codes (session_create)
+    if (S->smap.empty()) { memcpy(dst, src, sizeof(double) * J * ncol); return; }
+    for (int c = 0; c < ncol; ++c) for (int r = 0; r < J; ++r) dst[S->smap[r] + (size_t)J * c] = src[r + (size_t)J * c];
+  };
+  if (o->alpha_j) rows_out(o->alpha_j, p, D); p += (size_t)J * D;
   if (o->beta_k) memcpy(o->beta_k, p, sizeof(double) * K * D); p += (size_t)K * D;
   if (o->sigma_k) memcpy(o->sigma_k, p, sizeof(double) * K * D * D); p += (size_t)K * D * D;
-  if (o->p_jk) memcpy(o->p_jk, p, sizeof(double) * J * K);
+  if (o->p_jk) rows_out(o->p_jk, p, K);
   memset(o->rng_state, 0, sizeof o->rng_state);
   o->n_iter = n_iter; o->mcd_iters_hit = 0; o->n_zero_like = 0; o->rng_draws = 0;
 }

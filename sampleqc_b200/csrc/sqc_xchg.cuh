@@ -147,16 +147,27 @@ struct Xchg {
 struct XchgLocal { unsigned char* window = nullptr; unsigned long long* next_seq = nullptr; };
 inline XchgLocal& xchg_local(int device) { static XchgLocal w[64]; return w[device & 63]; }
 
-// allocate (once per device and process) this rank's window and export its IPC handle
-inline void xchg_export(int device, void* handle_out) {
+// allocate (once per device and process) this rank's window; reset = clear the window and the sequence counters.
+// Every multi-GPU session starts from a cleared window and sequence number 0 on every rank (a rank that failed or was
+// restarted therefore cannot leave the counters of the ranks out of step, and stale lines of earlier fits cannot
+// match): each rank clears its own window before the ranks meet (in-process: a host barrier; one process per GPU:
+// the all-gather of the handles that follows sqc_xchg_export).
+inline void xchg_ensure(int device, bool reset) {
   XchgLocal& L = xchg_local(device);
   if (!L.window) {
     if (cudaMalloc((void**)&L.window, XCHG_WINDOW_BYTES) != cudaSuccess) throw std::runtime_error("exchange window allocation failed");
-    cudaMemset(L.window, 0, XCHG_WINDOW_BYTES);
-    cudaMalloc((void**)&L.next_seq, XCHG_CHANNELS * sizeof(unsigned long long));
-    cudaMemset(L.next_seq, 0, XCHG_CHANNELS * sizeof(unsigned long long));
-    cudaDeviceSynchronize();
+    if (cudaMalloc((void**)&L.next_seq, XCHG_CHANNELS * sizeof(unsigned long long)) != cudaSuccess) throw std::runtime_error("exchange counter allocation failed");
+    reset = true;
   }
+  if (reset) {
+    cudaMemset(L.window, 0, XCHG_WINDOW_BYTES);
+    cudaMemset(L.next_seq, 0, XCHG_CHANNELS * sizeof(unsigned long long));
+    if (cudaDeviceSynchronize() != cudaSuccess) throw std::runtime_error("exchange window reset failed");
+  }
+}
+inline void xchg_export(int device, void* handle_out) {
+  xchg_ensure(device, true);
+  XchgLocal& L = xchg_local(device);
   cudaIpcMemHandle_t h;
   if (cudaIpcGetMemHandle(&h, L.window) != cudaSuccess) throw std::runtime_error("cudaIpcGetMemHandle failed");
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
@@ -174,6 +185,7 @@ inline void xchg_open(Xchg& X, int device, int rank, int world, const void* hand
   if (!L.window) throw std::runtime_error("sqc_xchg_export must be called before a multi-GPU session is created");
   X.world = world; X.rank = rank;
   X.dev.world = world; X.dev.rank = rank; X.dev.next_seq = L.next_seq;
+  X.open = true;                                       // from here on xchg_close releases what has been mapped (also after a failure half way)
   for (int r = 0; r < world; ++r) {
     if (r == rank) { X.dev.peer[r] = L.window; continue; }
     cudaIpcMemHandle_t h; memcpy(&h, (const char*)handles + (size_t)r * 64, sizeof h);
@@ -182,7 +194,18 @@ inline void xchg_open(Xchg& X, int device, int rank, int world, const void* hand
     if (e != cudaSuccess) throw std::runtime_error(std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(e));
     X.mapped[r] = p; X.dev.peer[r] = (unsigned char*)p;
   }
-  X.open = true;
+}
+// one process, one host thread per GPU: the peers' windows are ordinary device pointers (peer access enabled by the caller)
+inline void xchg_open_inproc(Xchg& X, int device, int rank, int world, const int* devices) {
+  if (world > XCHG_MAX_WORLD) throw std::runtime_error("world size above XCHG_MAX_WORLD");
+  X.world = world; X.rank = rank;
+  X.dev.world = world; X.dev.rank = rank; X.dev.next_seq = xchg_local(device).next_seq;
+  for (int r = 0; r < world; ++r) {
+    XchgLocal& L = xchg_local(devices[r]);
+    if (!L.window) throw std::runtime_error("exchange window of a peer is missing");
+    X.dev.peer[r] = L.window;
+  }
+  X.open = true;                                       // nothing mapped: xchg_close has nothing to release
 }
 inline void xchg_close(Xchg& X) {
   if (!X.open) return;

@@ -25,7 +25,13 @@ def shard_by_sample(groups: np.ndarray, J: int, world: int):
         c = int(np.searchsorted(bounds, N * r / world))
         cuts.append(min(max(c, cuts[-1]), J))
     cuts.append(J)
-    return [(cuts[r], cuts[r + 1], int(bounds[cuts[r]]), int(bounds[cuts[r + 1]])) for r in range(world)]
+    shards = [(cuts[r], cuts[r + 1], int(bounds[cuts[r]]), int(bounds[cuts[r + 1]])) for r in range(world)]
+    # every rank computes the same shards from the same inputs, so all of them fail here together: a rank without
+    # samples or cells would fail alone inside the library while its peers wait for its first exchange
+    for r, (j0, j1, i0, i1) in enumerate(shards):
+        if j1 <= j0 or i1 <= i0:
+            raise ValueError(f"rank {r} of {world} would get no cells ({J} samples, {N} cells): use fewer GPUs")
+    return shards
 
 
 def gather_handles(dist, handle: bytes, world: int, device=None) -> bytes:

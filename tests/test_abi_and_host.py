@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     lib = L.lib()
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.sqc_abi_version() == 1
+    assert lib.sqc_abi_version() == 2
     assert lib.sqc_status_name(2) == b"SQC_ERR_EMPTY_CLUSTER"
 
 
@@ -83,6 +83,8 @@ def test_shard_by_sample_balanced_and_contiguous():
         assert max(i1 - i0 for (_, _, i0, i1) in sh) <= groups.size / world + n_j.max()
     with pytest.raises(ValueError):
         shard_by_sample(groups[::-1], 37, 2)
+    with pytest.raises(ValueError):                               # a rank without cells: refused on every rank alike
+        shard_by_sample(np.repeat(np.arange(3), [1000, 5, 5]), 3, 4)
 
 
 _WORKER = r'''
@@ -121,6 +123,42 @@ def test_multigpu_host_logic_gloo_world2(tmp_path):
     outs = [p.communicate(timeout=180)[0] for p in procs]
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"ok {r}" in o, o
+
+
+def test_library_shard_plan_for_n_gpus():
+    """sqc_fit_args.n_gpus: the library's own sample-aligned sharding (host-only hook): contiguous sample runs in any
+    code order are cut at run boundaries with balanced cell counts; fewer samples than GPUs -> fewer shards;
+    interleaved samples -> 0 (single GPU)."""
+    import ctypes as C
+    from sampleqc_b200 import _abi as A
+    from sampleqc_b200._lib import lib
+    L = lib()
+    rng = np.random.default_rng(3)
+    n_j = rng.integers(50, 4000, size=37)
+    code = rng.permutation(37).astype(np.int32)                   # what factor(sample_ids) produces: runs in non-ascending code order
+    g = np.repeat(code, n_j).astype(np.int32)
+    N, J = int(g.size), 40                                        # codes 37..39 have no cells
+    for n in (2, 3, 8):
+        cells = (C.c_int64 * (n + 1))()
+        owner = np.full(J, -7, dtype=np.int32)
+        got = L.sqc_plan_shards(A.ptr_i(g), N, J, n, cells, A.ptr_i(owner))
+        assert got == n
+        b = list(cells)
+        assert b[0] == 0 and b[-1] == N and all(b[i] < b[i + 1] for i in range(n))
+        starts = np.concatenate([[0], np.cumsum(n_j)])
+        assert all(x in starts for x in b)                        # cuts fall on sample boundaries
+        sizes = np.diff(b)
+        assert sizes.max() - sizes.min() <= 2 * n_j.max()         # balanced up to one sample
+        for j in range(37):                                       # every sample lives in exactly the shard that holds its cells
+            i0 = starts[np.where(code == j)[0][0]]
+            assert b[owner[j]] <= i0 < b[owner[j] + 1]
+        assert list(owner[37:]) == [-1, -1, -1]
+    cells = (C.c_int64 * 9)()
+    assert L.sqc_plan_shards(A.ptr_i(g[:n_j[0] + n_j[1]]), int(n_j[0] + n_j[1]), J, 8, cells, None) == 2      # 2 samples: 2 shards
+    inter = np.tile(np.array([0, 1], dtype=np.int32), 500)
+    assert L.sqc_plan_shards(A.ptr_i(inter), 1000, 2, 2, cells, None) == 0
+    bad = g.copy(); bad[5] = 99
+    assert L.sqc_plan_shards(A.ptr_i(bad), N, J, 2, cells, None) < 0
 
 
 def test_mt_jump_polynomials_move_the_state(tmp_path):

@@ -65,18 +65,47 @@ def test_robust_deterministic():
 
 
 def test_robust_unsorted_groups(oracle):
+    """cells of a sample interleaved: sorted by sample once; with counter keys the stream position follows the
+    sample-sorted storage order, so compare with the oracle on the stably sorted data and map the labels back"""
     from sampleqc_b200 import api
     N, J, K = 6000, 6, 3
     sim, iz, _ = _case(N, J, 3, K)
     perm = np.random.default_rng(0).permutation(N)
     x, g, z0 = np.asfortranarray(sim.x[perm]), sim.groups[perm], iz[perm]
-    # with counter keys the stream position follows the sample-sorted storage order, so compare with the
-    # oracle on the stably sorted data and map the labels back
     order = np.argsort(g, kind="stable")
-    ref = oracle.fit_sampleqc_robust_cpp(np.asfortranarray(x[order]), z0[order], g[order], 3, J, K, N, 10, 0.5, 50, 0)
-    got = api.fit_sampleqc_robust_cpp(x, z0, g, 3, J, K, N, 10, 0.5, 50, 0)
-    np.testing.assert_allclose(got["beta_k"], ref["beta_k"], rtol=RTOL)
-    np.testing.assert_array_equal(got["z"].ravel()[order], ref["z"].ravel())
+    for mode in (0, 1):
+        ref = oracle.fit_sampleqc_robust_cpp(np.asfortranarray(x[order]), z0[order], g[order], 3, J, K, N, 10, 0.5, 50, 0, rng_mode=mode)
+        got = api.fit_sampleqc_robust_cpp(x, z0, g, 3, J, K, N, 10, 0.5, 50, 0, rng_mode=mode)
+        np.testing.assert_allclose(got["beta_k"], ref["beta_k"], rtol=RTOL)
+        np.testing.assert_array_equal(got["z"].ravel()[order], ref["z"].ravel())
+
+
+@pytest.mark.parametrize("variant", ["robust", "mle"])
+def test_sample_runs_in_non_ascending_code_order(oracle, variant):
+    """what fit_sampleqc() sends (R/fit_sampleqc.R:205-216): x is an rbind over samples, but groups =
+    as.integer(factor(sample_ids)) numbers the samples alphabetically — contiguous runs whose codes are not ascending.
+    The reference pairs the m-th randperm key with the m-th cell of a cluster in the CALLER's cell order; compared with
+    the oracle on the unsorted input itself, R-compatible keys, plus R's RNG state after the fit."""
+    from sampleqc_b200 import api
+    N, J, K = 30_000, 7, 3
+    sim, iz, ig = _case(N, J, 3, K, seed=9)
+    code = np.array([4, 0, 6, 2, 5, 1, 3], dtype=np.int32)        # run r carries sample code code[r]
+    g = code[sim.groups]
+    assert np.any(np.diff(g) < 0)
+    if variant == "robust":
+        ref = oracle.fit_sampleqc_robust_cpp(sim.x, iz, g, 3, J, K, N, 10, 0.5, 50, 0, track=True)
+        got = api.fit_sampleqc_robust_cpp(sim.x, iz, g, 3, J, K, N, 10, 0.5, 50, 0, track=True)
+        assert got["n_iter"] == ref["n_iter"]
+        for key in ("mu_0", "alpha_j", "beta_k", "sigma_k", "p_jk", "track_alpha_j", "track_p_jk"):
+            np.testing.assert_allclose(got[key], ref[key], rtol=RTOL, atol=RTOL * np.max(np.abs(ref[key])), err_msg=key)
+        np.testing.assert_array_equal(got["z"], ref["z"])
+        np.testing.assert_array_equal(got["rng_state"], ref["rng_state"])
+    else:
+        ref = oracle.fit_sampleqc_mle_cpp(sim.x, ig, g, 3, J, K, N, 4, 0)
+        got = api.fit_sampleqc_mle_cpp(sim.x, ig, g, 3, J, K, N, 4, 0)
+        for key in ("mu_0", "alpha_j", "beta_k", "sigma_k", "p_k", "p_jk", "gamma_i"):
+            np.testing.assert_allclose(got[key], ref[key], rtol=RTOL, atol=RTOL * np.max(np.abs(ref[key])), err_msg=key)
+        np.testing.assert_array_equal(got["z"], ref["z"])
 
 
 def test_error_classes(oracle):
