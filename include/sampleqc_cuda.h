@@ -176,6 +176,28 @@ typedef struct sqc_init_args {
 SQC_API int sqc_init_clusts(const sqc_init_args* args, double* medians, double* gamma, int32_t* z,
                     char* err, size_t errlen);
 
+/* ---- the resident pipeline: .init_clusts -> fit -> re-centring -> outliers on ONE upload of the cells ------------- */
+/* .fit_one_sampleqc (R/fit_sampleqc.R:195-262) runs .init_clusts (:222), fit_sampleqc_*_cpp (:229-238), the re-centring
+ * (:242-246) and .calc_outliers_dt (:258) on the same x / groups.  A sqc_resident keeps both in HBM: x crosses PCIe once,
+ * the labels of the classification go into the fit without leaving the device, the fitted parameters come back already
+ * re-centred and stay with the handle for the outlier pass.  One GPU; the cells of every sample must be contiguous.    */
+typedef struct sqc_resident sqc_resident;
+SQC_API int  sqc_resident_create(const double* x /* N x D column-major, un-centred */, const int32_t* groups /* N, 0-based */,
+                                 int32_t D, int32_t J, int64_t N, int32_t device, sqc_resident** out, char* err, size_t errlen);
+/* grp_medians (:286-289) -> medians (J x D, may be NULL); with pro != NULL also the classification of all cells under the
+ * mixture fitted on the subsample (:303-316).  gamma (N x K) / z (N, 0-based) may be NULL: labels - and with keep_gamma
+ * the responsibilities - stay on the device as the initial values of the next sqc_resident_fit.                       */
+SQC_API int  sqc_resident_init_clusts(sqc_resident* r, const double* pro, const double* mean /* K x D */, const double* sigma /* D x D x K */,
+                                      int32_t K, int32_t keep_gamma, double* medians, double* gamma, int32_t* z, char* err, size_t errlen);
+/* rows idx[0 .. n) of x minus their samples' medians, n x D column-major: the subsample the caller's mixture is fitted on (:291-300) */
+SQC_API int  sqc_resident_subsample(sqc_resident* r, const int64_t* idx, int64_t n, double* out, char* err, size_t errlen);
+/* the fit on the resident cells.  args->x / groups / D / J / N are ignored; init_z / init_gamma NULL = the resident
+ * classification.  recentre != 0: mu_0, alpha_j, beta_k come back re-centred as R/fit_sampleqc.R:242-246 does.       */
+SQC_API int  sqc_resident_fit(sqc_resident* r, const sqc_fit_args* args, int variant, int32_t recentre, sqc_fit_out* out, char* err, size_t errlen);
+/* .calc_outliers_dt (:419-453) with the (re-centred) parameters of the last sqc_resident_fit; maha (N x K) may be NULL */
+SQC_API int  sqc_resident_outliers(sqc_resident* r, double alpha, double* maha, uint8_t* outlier, double* maha_cut, char* err, size_t errlen);
+SQC_API void sqc_resident_destroy(sqc_resident* r);
+
 /* ---- resident sessions (benchmarks, multi-GPU drivers) --------------------------------- */
 /* A session keeps the cell matrix resident in HBM so that the EM loop can be timed without the
  * host<->device copies, and exposes per-kernel device timings for the roofline report.       */

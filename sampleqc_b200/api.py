@@ -234,3 +234,87 @@ def fp64_peak(device=-1) -> float:
     err = C.create_string_buffer(512)
     check(lib().sqc_fp64_peak(int(device), C.byref(v), err, 512), err)
     return v.value
+
+
+class Resident:
+    """The resident pipeline of .fit_one_sampleqc (reference R/fit_sampleqc.R:195-262): .init_clusts -> fit -> re-centring
+    -> .calc_outliers_dt on ONE upload of the cells (sqc_resident_* in include/sampleqc_cuda.h)."""
+
+    def __init__(self, x, groups, J, device=-1):
+        self._x = A.f64_colmajor(x)
+        self.N, self.D = self._x.shape
+        self.J = int(J)
+        self._g = A.as_i32(groups)
+        self._h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        check(lib().sqc_resident_create(A.ptr_d(self._x), A.ptr_i(self._g), self.D, self.J, self.N, int(device), C.byref(self._h), err, 512), err)
+
+    def medians(self):
+        med = np.zeros((self.J, self.D), order="F")
+        err = C.create_string_buffer(512)
+        check(lib().sqc_resident_init_clusts(self._h, None, None, None, 0, 0, A.ptr_d(med), None, None, err, 512), err)
+        return med
+
+    def subsample(self, idx):
+        idx = np.ascontiguousarray(np.asarray(idx, dtype=np.int64).reshape(-1))
+        out = np.zeros((idx.size, self.D), order="F")
+        err = C.create_string_buffer(512)
+        check(lib().sqc_resident_subsample(self._h, idx.ctypes.data_as(C.POINTER(C.c_int64)), idx.size, A.ptr_d(out), err, 512), err)
+        return out
+
+    def classify(self, pro, mean, sigma, keep_gamma=False, want_gamma=False, want_z=False):
+        """classification of all cells under the caller's mixture; the labels stay resident for fit_robust()"""
+        pr = np.ascontiguousarray(np.asarray(pro, dtype=np.float64).reshape(-1))
+        K = pr.shape[0]
+        mu, sg = A.f64_colmajor(np.asarray(mean, dtype=np.float64).reshape(K, self.D)), A.f64_colmajor(sigma)
+        gamma = np.zeros((self.N, K), order="F") if want_gamma else None
+        z = np.zeros(self.N, dtype=np.int32) if want_z else None
+        err = C.create_string_buffer(512)
+        check(lib().sqc_resident_init_clusts(self._h, A.ptr_d(pr), A.ptr_d(mu), A.ptr_d(sg), K, int(bool(keep_gamma or want_gamma)), None,
+                                             A.ptr_d(gamma) if want_gamma else None, A.ptr_i(z) if want_z else None, err, 512), err)
+        return gamma, z
+
+    def fit_robust(self, K, em_iters, mcd_alpha, mcd_iters, seed, track=False, rng_mode=SQC_RNG_R_COMPAT, init_z=None, recentre=True, out=None):
+        """fit_sampleqc_robust_cpp on the resident cells (init_z None: the resident classification); parameters re-centred"""
+        dummy_x = np.zeros((1, self.D), order="F")
+        args, keep = A.make_fit_args(dummy_x, np.zeros(1, dtype=np.int32), self.D, self.J, K, self.N, em_iters, init_z=init_z, mcd_alpha=mcd_alpha,
+                                     mcd_iters=mcd_iters, seed=seed, track=track, rng_mode=rng_mode)
+        bufs = out if out is not None else A.FitBuffers(self.D, self.J, K, self.N, em_iters, SQC_VARIANT_ROBUST, track)
+        err = C.create_string_buffer(512)
+        check(lib().sqc_resident_fit(self._h, C.byref(args), SQC_VARIANT_ROBUST, int(bool(recentre)), C.byref(bufs.out), err, 512), err)
+        return bufs.as_list()
+
+    def fit_mle(self, K, n_iter, seed, init_gamma=None, recentre=True):
+        dummy_x = np.zeros((1, self.D), order="F")
+        args, keep = A.make_fit_args(dummy_x, np.zeros(1, dtype=np.int32), self.D, self.J, K, self.N, n_iter, init_gamma=init_gamma, seed=seed)
+        bufs = A.FitBuffers(self.D, self.J, K, self.N, n_iter, SQC_VARIANT_MLE)
+        err = C.create_string_buffer(512)
+        check(lib().sqc_resident_fit(self._h, C.byref(args), SQC_VARIANT_MLE, int(bool(recentre)), C.byref(bufs.out), err, 512), err)
+        return bufs.as_list()
+
+    def outliers(self, alpha=0.01, want_maha=True, out_maha=None, out_flags=None):
+        maha = out_maha
+        if want_maha and maha is None:
+            raise ValueError("pass out_maha (N x K, Fortran order) or want_maha=False")
+        flags = out_flags if out_flags is not None else np.zeros(self.N, dtype=np.uint8)
+        cut = C.c_double(0)
+        err = C.create_string_buffer(512)
+        check(lib().sqc_resident_outliers(self._h, float(alpha), A.ptr_d(maha) if want_maha else None, flags.ctypes.data_as(A.c_uint8_p), C.byref(cut), err, 512), err)
+        return maha, flags.astype(bool) if out_flags is None else flags, cut.value
+
+    def close(self):
+        if self._h:
+            lib().sqc_resident_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -31,7 +31,7 @@
 #include "sqc_init.cuh"
 
 #ifndef SQC_MCD_RESERVE_SMS
-#define SQC_MCD_RESERVE_SMS 50   // SMs k_mcd leaves to the key-stream kernels (R-compatible keys only), see session_create
+#define SQC_MCD_RESERVE_SMS 24   // SMs k_mcd leaves to the key-stream kernels (R-compatible keys only), see session_create
 #endif
 #ifndef SQC_FOR_D
 #define SQC_FOR_D(X) X(1) X(2) X(3) X(4) X(5) X(6) X(7) X(8)
@@ -582,7 +582,7 @@ sqc_session* session_create(const sqc_fit_args* a, int variant, InprocGroup* grp
   // ---- upload x first (asynchronous from pinned memory), scan the sample layout on the host meanwhile ----
   Dev& s = S->dev;
   s.x = S->alloc<double>((size_t)N * D, false);
-  CK(cudaMemcpy2DAsync(s.x, (size_t)N * sizeof(double), a->x, (size_t)ld * sizeof(double), (size_t)N * sizeof(double), D, cudaMemcpyHostToDevice, S->st));
+  CK(cudaMemcpy2DAsync(s.x, (size_t)N * sizeof(double), a->x, (size_t)ld * sizeof(double), (size_t)N * sizeof(double), D, cudaMemcpyDefault, S->st));   // (a device pointer in the resident pipeline)
   // Cells of a sample must be contiguous in HBM (tiles never cross a sample boundary).  Three cases:
   //   groups non-decreasing                     -> as is;
   //   every sample one contiguous run, any order -> as is, samples relabelled by order of appearance (rows of alpha_j /
@@ -731,7 +731,7 @@ sqc_session* session_create(const sqc_fit_args* a, int variant, InprocGroup* grp
     int* bad = S->alloc<int>(1);
     {                                               // labels travel as int32 (the export's arma::uvec); narrow on the device
       int* tmp = S->o_z;                               // the output label buffer doubles as the int32 staging area
-      if (sorted) CK(cudaMemcpyAsync(tmp, a->init_z, (size_t)N * sizeof(int), cudaMemcpyHostToDevice, S->st));
+      if (sorted) CK(cudaMemcpyAsync(tmp, a->init_z, (size_t)N * sizeof(int), cudaMemcpyDefault, S->st));
       else { std::vector<int> zz(N); for (long long i = 0; i < N; ++i) zz[i] = a->init_z[S->perm[i]]; CK(cudaMemcpy(tmp, zz.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice)); }
       k_widen_labels<<<std::min<long long>((N + 255) / 256, 4096), 256, 0, S->st>>>(tmp, S->z0, N, K, bad);
       int hb = 0; CK(cudaMemcpyAsync(&hb, bad, sizeof(int), cudaMemcpyDeviceToHost, S->st));
@@ -1078,6 +1078,7 @@ int sqc_outlier_maha(const sqc_maha_args* a, double* maha, uint8_t* outlier, dou
 }
 
 #include "sqc_init_host.inl"
+#include "sqc_pipe_host.inl"
 
 int sqc_xchg_export(int device, void* handle_out, char* err, size_t errlen) {
   return guarded([&] {

@@ -11,7 +11,7 @@ __global__ void k_mle_pack_pk(Dev s, MleBufs m, OutPtrs o, double* out_pk) {
 void mle_alloc(sqc_session& S, const sqc_fit_args* a, MleBufs& m) {
   const int D = S.D, J = S.J, K = S.K; const long long N = S.N; const int T = S.dev.T;
   double* g0 = S.alloc<double>((size_t)N * K, false);
-  if (S.sorted) CK(cudaMemcpy2DAsync(g0, (size_t)N * sizeof(double), a->init_gamma, (size_t)S.ld * sizeof(double), (size_t)N * sizeof(double), K, cudaMemcpyHostToDevice, S.st));
+  if (S.sorted) CK(cudaMemcpy2DAsync(g0, (size_t)N * sizeof(double), a->init_gamma, (size_t)S.ld * sizeof(double), (size_t)N * sizeof(double), K, cudaMemcpyDefault, S.st));
   else {
     std::vector<double> col(N);
     for (int k = 0; k < K; ++k) {
