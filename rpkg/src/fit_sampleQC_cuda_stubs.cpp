@@ -41,6 +41,13 @@ void restore_r_rng(unsigned int seed, const sqc_fit_out& out) {
   GetRNGstate();                                    // internal state <- .Random.seed (R_ext/Random.h)
 }
 
+// options(SampleQC.n_gpus = n): 1 (default) = one GPU, n > 1 = that many, -1 = all visible (SQC_ALL_GPUS).  The export
+// signatures stay those of the reference; fit_sampleqc() needs no change.
+int n_gpus_option() {
+  Function get_option("getOption");
+  return as<int>(get_option("SampleQC.n_gpus", 1));
+}
+
 void check_status(int status, const char* err) {
   if (status != SQC_OK) Rcpp::stop("%s [%s]", err, sqc_status_name(status));
 }
@@ -64,6 +71,7 @@ List fit_sampleqc_robust_cpp(arma::mat x, arma::uvec init_z, arma::uvec groups, 
   a.seed = seed; a.track = track ? 1 : 0;
   a.rng_mode = SQC_RNG_R_COMPAT;                    // arma::randperm keys from R's stream (robust_cpp.cpp:72)
   a.device = -1; a.world = 1; a.N_total = N;
+  a.n_gpus = n_gpus_option();                       // options(SampleQC.n_gpus = n): one call sharded over n GPUs by the library
 
   arma::vec mu_0(D), like_1(em, arma::fill::zeros), like_2(em, arma::fill::zeros);
   arma::mat alpha_j(J, D), beta_k(K, D), p_jk(J, K);
@@ -107,7 +115,7 @@ List fit_sampleqc_mle_cpp(arma::mat x, arma::mat init_gamma_i, arma::uvec groups
   a.abi_version = SQC_ABI_VERSION;
   a.D = D; a.J = J; a.K = K; a.N = N;
   a.x = x.memptr(); a.groups = g.data(); a.init_gamma = init_gamma_i.memptr();
-  a.em_iters = n_iter; a.seed = seed; a.device = -1; a.world = 1; a.N_total = N;
+  a.em_iters = n_iter; a.seed = seed; a.device = -1; a.world = 1; a.N_total = N; a.n_gpus = n_gpus_option();
 
   arma::vec mu_0(D), p_k(K), like_1(it, arma::fill::zeros), like_2(it, arma::fill::zeros);
   arma::mat alpha_j(J, D), beta_k(K, D), p_jk(J, K), gamma_i(N, K);

@@ -26,8 +26,14 @@
 #define SQC_D_NAN 6
 #define SQC_D_SELECT 7
 #define SQC_D_PEER 8          // multi-GPU: another rank failed
+#define SQC_D_TIMEOUT 9       // a wait on another CTA / another rank ran out of its time budget
+#ifndef SQC_WAIT_BUDGET_NS
+#define SQC_WAIT_BUDGET_NS 60000000000ll   // one budget for every in-kernel wait (leader, workers, exchanges), %globaltimer based
+#endif
 
 namespace sqc {
+
+__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
 // ---------------------------------------------------------------------------------------------
 // streaming loads: the cell matrix is read once per pass, keep it out of L1

@@ -67,6 +67,7 @@ const char* device_status_message(int st) {
     case SQC_ERR_NAN: return "sort_index(): detected NaN (robust_cpp.cpp:50)";
     case SQC_ERR_SELECT: return "exact selection could not be resolved (too many exactly tied distances)";
     case SQC_D_PEER: return "another rank of the multi-GPU fit reported an error";
+    case SQC_D_TIMEOUT: return "timed out waiting for another GPU of the fit (or for a worker CTA): a peer failed or never started";
     default: return "device error";
   }
 }
@@ -685,6 +686,7 @@ sqc_session* session_create(const sqc_fit_args* a, int variant, InprocGroup* grp
   s.clu_n = S->alloc<long long>(K); s.clu_off = S->alloc<long long>(K); s.clu_n_glob = S->alloc<long long>(K); s.clu_prefix = S->alloc<long long>(K);
   s.like1 = S->alloc<double>(em + 1); s.like2 = S->alloc<double>(em + 1);
   s.ctl = S->alloc<Control>(1);
+  S->xc.dev.status = &s.ctl->status;                  // (multi-GPU) exchange waits report a timeout here
   S->alpha0 = S->alloc<double>((size_t)J * D);
   if (S->track && variant == SQC_VARIANT_ROBUST) {
     s.track_alpha = S->alloc<double>((size_t)J * D * em); s.track_beta = S->alloc<double>((size_t)K * D * em);
@@ -894,7 +896,7 @@ void session_run(sqc_session* S) {
   } else {
     S->stats.family_bytes[SQC_KF_MLE_PASS] = (double)(2 * it + 1) * pass;
   }
-  if (S->h_ctl.status != 0) fail(S->h_ctl.status == SQC_D_PEER ? SQC_ERR_COMM : S->h_ctl.status, "%s", device_status_message(S->h_ctl.status));
+  if (S->h_ctl.status != 0) fail((S->h_ctl.status == SQC_D_PEER || S->h_ctl.status == SQC_D_TIMEOUT) ? SQC_ERR_COMM : S->h_ctl.status, "%s", device_status_message(S->h_ctl.status));
 }
 
 void reorder_track(const sqc_session* S, sqc_fit_out* o, const int* korder) {

@@ -165,7 +165,6 @@ __device__ __forceinline__ void grid_barrier(GridBar* bar, unsigned int nblocks,
 __device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
   asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ long long gtimer() { long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
 
 __device__ __forceinline__ unsigned long long dist_bits(double d) { return (unsigned long long)__double_as_longlong(d); }
 
@@ -432,11 +431,25 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         my_cells += n; my_bytes += n * ((ph == PH_KEY_HIST ? 0 : 8 * D) + ((keyr && mb.keys) ? 4 : 0));
         // every worker of the serving set arrives once per epoch, whether or not it holds cells of this cluster
         want_arrivals += (unsigned)(sh_clu.serve_all ? NWK : (my_small ? NS : NWK - NS));
-        unsigned long long spins = 0;
-        while (ld_acquire_u32(&mb.arrive[k]) < want_arrivals) { if (++spins > (1ull << 24)) { atomicCAS(&(*mb.status), 0, SQC_D_SELECT); break; } }   // watchdog (seconds)
+        // watchdog: one time budget for leaders, workers and exchanges (a worker or a peer died); the leader then stops
+        unsigned int spins = 0; long long t0w = 0;
+        sh_flag[3] = 0;
+        while (ld_acquire_u32(&mb.arrive[k]) < want_arrivals) {
+          if ((++spins & 0x3fffu) == 0u) {
+            const long long now = gtimer();
+            if (!t0w) t0w = now;
+            else if (now - t0w > SQC_WAIT_BUDGET_NS || *mb.status == SQC_D_TIMEOUT) { atomicCAS(&(*mb.status), 0, SQC_D_TIMEOUT); sh_flag[3] = 1; break; }
+          }
+        }
         __threadfence();
       }
       __syncthreads();
+      if (sh_flag[3]) {                                            // timed out: no post-processing on partial data, no further exchange
+        if (tid == 0) sh_clu.phase = PH_DONE;
+        __syncthreads();
+        ++ep; publish(ep);
+        break;
+      }
       if (tr) { trow[1] = gtimer(); trow[2] = trow[1]; }
       {
       McdClu& cl = sh_clu;
@@ -447,12 +460,14 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         for (int i = tid; i < MCD_NB; i += MCD_THREADS) { sh_hist[i] = mb.hist[k * MCD_NB + i]; mb.hist[k * MCD_NB + i] = 0u; }
         if (tid == 0) {
           const unsigned long long bl = W->cnt_below[k], nn = W->cnt_nan[k];
-          sh_hist[MCD_NB] = (unsigned int)bl; sh_hist[MCD_NB + 1] = (unsigned int)(bl >> 32); sh_hist[MCD_NB + 2] = nn ? 1u : 0u;
+          // the count travels as two 16-bit limbs (a rank holds < 2^31 cells): their sums over <= 8 ranks cannot wrap,
+          // whatever the total number of cells
+          sh_hist[MCD_NB] = (unsigned int)(bl & 0xffffull); sh_hist[MCD_NB + 1] = (unsigned int)(bl >> 16); sh_hist[MCD_NB + 2] = nn ? 1u : 0u;
           W->cnt_below[k] = 0ull;
         }
         __syncthreads();
-        if constexpr (MULTI) xchg_sum_u32(mb.xc, k, sh_hist, MCD_NB + 3);      // (the two halves of `below` cannot carry: < 2^32 cells per rank)
-        const long long below = (long long)sh_hist[MCD_NB] + ((long long)sh_hist[MCD_NB + 1] << 32);
+        if constexpr (MULTI) xchg_sum_u32(mb.xc, k, sh_hist, MCD_NB + 3);
+        const long long below = (long long)sh_hist[MCD_NB] + ((long long)sh_hist[MCD_NB + 1] << 16);
         const bool has_nan = sh_hist[MCD_NB + 2] != 0;
         constexpr int PER = (MCD_NB + MCD_THREADS - 1) / MCD_THREADS;
         unsigned int hv[PER]; long long mine = 0;
@@ -523,7 +538,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         // candidate counts of this thread's regions: same L2 round trip as the partials and the fine histogram
         unsigned int cn[MCD_RPT];
 #pragma unroll
-        for (int i = 0; i < MCD_RPT; ++i) { const int rg = tid * MCD_RPT + i; cn[i] = (rg >= cta_lo * MCD_WARPS && rg < cta_hi * MCD_WARPS) ? ccnt[rg] : 0u; }
+        for (int i = 0; i < MCD_RPT; ++i) { const int rg = i * MCD_THREADS + tid; cn[i] = (rg >= cta_lo * MCD_WARPS && rg < cta_hi * MCD_WARPS) ? ccnt[rg] : 0u; }   // regions dealt round-robin over the threads
         // 1. fine histogram of the candidates: built by the workers with atomics on mb.fhist
         {
           constexpr int FPT = (MCD_NF + 4 + MCD_THREADS - 1) / MCD_THREADS;
@@ -537,7 +552,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         if (direct && wid == 0) {                                    // cells strictly under the band: moment 0 of the partials (exact: counts < 2^53)
           const double cb = warp_sum(part_pre[0]);
           const unsigned long long cnt = (unsigned long long)cb;
-          if (lane == 0) { sh_hist[MCD_NF + 2] = (unsigned int)cnt; sh_hist[MCD_NF + 3] = (unsigned int)(cnt >> 32); }
+          if (lane == 0) { sh_hist[MCD_NF + 2] = (unsigned int)(cnt & 0xffffull); sh_hist[MCD_NF + 3] = (unsigned int)(cnt >> 16); }   // two 16-bit limbs, as above
         }
         __syncthreads();
         if (tr) trow[8] = gtimer();
@@ -549,7 +564,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         for (int i = 0; i < PER; ++i) { hv[i] = (tid * PER + i < MCD_NF) ? sh_hist[tid * PER + i] : 0u; mine += hv[i]; }
         long long ncand_all;
         long long run = block_excl_scan<MCD_THREADS>(mine, sh_scan, &ncand_all);
-        const long long below_all = direct ? ((long long)sh_hist[MCD_NF + 2] + ((long long)sh_hist[MCD_NF + 3] << 32)) : cl.below;
+        const long long below_all = direct ? ((long long)sh_hist[MCD_NF + 2] + ((long long)sh_hist[MCD_NF + 3] << 16)) : cl.below;
         const long long take = cl.h - below_all;                     // candidates (over all ranks) that belong to the h-subset
         if (tid == 0) sh_flag[1] = -1;
         __syncthreads();
@@ -573,53 +588,50 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
           double cs[D];
 #pragma unroll
           for (int d = 0; d < D; ++d) cs[d] = cl.cshift[d];
-          // flat, canonical (region-major) index space over the candidates: prefix of the region counts in shared
-          // memory, then thread t takes candidates t, t + threads, ... (one record load each, all independent)
-          unsigned int* sh_pref = sh_hist + MCD_NF + 8;            // regions + 1 words behind the fine histogram
-          long long mine_c = 0;
+          // every thread walks its own candidate regions (region i * threads + tid), slot by slot; the record loads of a
+          // trip (one slot of up to MCD_PB regions) are all in flight together — the pass is bound by L2 round trips.  The
+          // order a thread adds its members in depends on the regions' contents only: reproducible.
+          unsigned int mx = 0;
 #pragma unroll
-          for (int i = 0; i < MCD_RPT; ++i) { cn[i] = min(cn[i], (unsigned)MCD_CAPW); mine_c += cn[i]; }
-          long long ncand_loc;
-          long long off_c = block_excl_scan<MCD_THREADS>(mine_c, sh_scan, &ncand_loc);
-#pragma unroll
-          for (int i = 0; i < MCD_RPT; ++i) { const int rg = tid * MCD_RPT + i; if (rg < regions) sh_pref[rg] = (unsigned int)off_c; off_c += cn[i]; }
-          if (tid == 0) sh_pref[regions] = (unsigned int)ncand_loc;
-          __syncthreads();
-          // MCD_PB candidates per thread and trip: the record loads of a batch are all in flight together (the pass is
-          // bound by L2 round trips, ~1.5 us each while the workers stream)
+          for (int i = 0; i < MCD_RPT; ++i) { cn[i] = min(cn[i], (unsigned)MCD_CAPW); mx = max(mx, cn[i]); }
           constexpr int MCD_PB = (D <= 4) ? 4 : 2;
-          for (int f0 = tid; f0 < (int)ncand_loc; f0 += MCD_THREADS * MCD_PB) {
-            unsigned long long wv[MCD_PB][2 + D]; int rgs[MCD_PB]; unsigned int sls[MCD_PB]; bool live[MCD_PB];
+          static_assert(MCD_RPT % MCD_PB == 0, "regions per thread in whole batches");
+          for (unsigned int sl = 0; sl < mx; ++sl) {
 #pragma unroll
-            for (int q = 0; q < MCD_PB; ++q) {
-              const int f = f0 + q * MCD_THREADS;
-              live[q] = f < (int)ncand_loc;
-              int lo = 0, hi = regions;                             // the region with sh_pref[rg] <= f < sh_pref[rg + 1]
-              while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sh_pref[mid] <= (unsigned)f) lo = mid; else hi = mid; }
-              rgs[q] = lo; sls[q] = live[q] ? (unsigned)f - sh_pref[lo] : 0u;   // (empty regions share a prefix with their successor: the largest index wins, which is the owner)
-              const unsigned long long* rec = mb.cand_rec + (((long long)k * regions + rgs[q]) * MCD_CAPW + sls[q]) * (2 + D);
+            for (int i0 = 0; i0 < MCD_RPT; i0 += MCD_PB) {
+              bool live[MCD_PB]; bool any = false;
 #pragma unroll
-              for (int e = 0; e < 2 + D; ++e) wv[q][e] = live[q] ? __ldcg(rec + e) : 0ull;
-            }
+              for (int q = 0; q < MCD_PB; ++q) { live[q] = sl < cn[i0 + q]; any = any || live[q]; }
+              if (!any) continue;
+              unsigned long long wv[MCD_PB][2 + D];
 #pragma unroll
-            for (int q = 0; q < MCD_PB; ++q) {
-              if (!live[q]) continue;
-              const unsigned long long bits = wv[q][0];
-              const int fb = (int)((bits - blo) >> fshift);
-              if (fb < fbin) {
-                if (need_mom) {
-                  double r[D];
+              for (int q = 0; q < MCD_PB; ++q) {
+                const int rg = (i0 + q) * MCD_THREADS + tid;
+                const unsigned long long* rec = mb.cand_rec + (((long long)k * regions + rg) * MCD_CAPW + sl) * (2 + D);
 #pragma unroll
-                  for (int d = 0; d < D; ++d) r[d] = __longlong_as_double((long long)wv[q][2 + d]);
-                  Mom<D>::add(tot, r, cs, true);
-                }
-              } else if (fb == fbin) {
-                const int t = atomicAdd(&sh_flag[4], 1);
-                if (t < MCD_TINY) {
-                  sh_tkey[t] = bits; sh_tpos[t] = (unsigned int)wv[q][1]; sh_tref[t] = (unsigned int)(rgs[q] * MCD_CAPW + sls[q]); sh_trank[t] = (unsigned)myrank;
-                  if (t < MCD_TCACHE) {
+                for (int e = 0; e < 2 + D; ++e) wv[q][e] = live[q] ? __ldcg(rec + e) : 0ull;
+              }
 #pragma unroll
-                    for (int d = 0; d < D; ++d) sh_tr[t * D + d] = __longlong_as_double((long long)wv[q][2 + d]);
+              for (int q = 0; q < MCD_PB; ++q) {
+                if (!live[q]) continue;
+                const int rg = (i0 + q) * MCD_THREADS + tid;
+                const unsigned long long bits = wv[q][0];
+                const int fb = (int)((bits - blo) >> fshift);
+                if (fb < fbin) {
+                  if (need_mom) {
+                    double r[D];
+#pragma unroll
+                    for (int d = 0; d < D; ++d) r[d] = __longlong_as_double((long long)wv[q][2 + d]);
+                    Mom<D>::add(tot, r, cs, true);
+                  }
+                } else if (fb == fbin) {
+                  const int t = atomicAdd(&sh_flag[4], 1);
+                  if (t < MCD_TINY) {
+                    sh_tkey[t] = bits; sh_tpos[t] = (unsigned int)wv[q][1]; sh_tref[t] = (unsigned int)(rg * MCD_CAPW + (int)sl); sh_trank[t] = (unsigned)myrank;
+                    if (t < MCD_TCACHE) {
+#pragma unroll
+                      for (int d = 0; d < D; ++d) sh_tr[t * D + d] = __longlong_as_double((long long)wv[q][2 + d]);
+                    }
                   }
                 }
               }
@@ -895,7 +907,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
       }
     }
     __syncthreads();
-    unsigned long long idle = 0;
+    unsigned int idle = 0; long long t_idle = 0;
     for (;;) {
       if (tid < K) sh_ep[tid] = (int)ld_acquire_u32(&mb.epoch[tid]);
       __syncthreads();
@@ -1068,7 +1080,12 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         __syncthreads();
       }
       if (n_done == K) break;
-      if (!any_new && ++idle > (1ull << 23)) break;               // watchdog (seconds): a leader died
+      if (any_new) { idle = 0; t_idle = 0; }
+      else if ((++idle & 0x3fffu) == 0u) {                          // watchdog, same budget as the leaders': a leader died
+        const long long now = gtimer();
+        if (!t_idle) t_idle = now;
+        else if (now - t_idle > SQC_WAIT_BUDGET_NS + 5000000000ll) { if (tid == 0) atomicCAS(&(*mb.status), 0, SQC_D_TIMEOUT); break; }
+      }
     }
   }
 }

@@ -35,6 +35,7 @@ struct XchgDev {
   int world, rank;
   unsigned char* peer[XCHG_MAX_WORLD];               // window base of every rank (own window: local pointer)
   unsigned long long* next_seq;                      // XCHG_CHANNELS counters in LOCAL memory (same value on all ranks)
+  int* status;                                       // the session's device status word: a wait that runs out of its budget says so here
 };
 
 // slot of `src`'s message of exchange `seq` on channel `ch`, inside the window at `base`
@@ -66,14 +67,23 @@ __device__ __forceinline__ void xchg_put(const XchgDev& x, int ch, unsigned long
 __device__ __forceinline__ void xchg_put_f64(const XchgDev& x, int ch, unsigned long long seq, int line, double v) {
   xchg_put(x, ch, seq, line, (unsigned int)__double2loint(v), (unsigned int)__double2hiint(v));
 }
-// wait for line `line` of rank r's message: local polling, tight at first, then with a 1 us back-off; a peer that
-// never sends traps the kernel after about a minute (the host then reports SQC_ERR_CUDA instead of hanging)
+// wait for line `line` of rank r's message: local polling, tight at first, then with a 1 us back-off.  A peer that never
+// sends: after SQC_WAIT_BUDGET_NS the wait gives up, writes SQC_D_TIMEOUT into the session's status word (every later
+// wait then returns at once) and the fit ends with SQC_ERR_COMM — no trap, the CUDA context survives.
 __device__ __forceinline__ ulonglong2 xchg_wait(const XchgDev& x, int ch, unsigned long long seq, int r, int line) {
   const ulonglong2* p = xw_line(x.peer[x.rank], ch, seq, r) + line;
   ulonglong2 v = ld_line(p);
-  unsigned int spins = 0;
+  unsigned int spins = 0; long long t0 = 0;
   while (!line_ready(v, (unsigned int)seq)) {
-    if (++spins > (1u << 16)) { __nanosleep(1000); if (spins > (1u << 16) + 40000000u) __trap(); }
+    if (++spins > (1u << 16)) {
+      __nanosleep(1000);
+      if ((spins & 0x3ffu) == 0u) {
+        if (*(volatile int*)x.status == SQC_D_TIMEOUT) break;
+        const long long now = gtimer();
+        if (!t0) t0 = now;
+        else if (now - t0 > SQC_WAIT_BUDGET_NS) { atomicCAS(x.status, 0, SQC_D_TIMEOUT); break; }
+      }
+    }
     v = ld_line(p);
   }
   return v;

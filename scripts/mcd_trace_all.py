@@ -15,7 +15,7 @@ rng = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 x, g, iz, prm = workload("C3", scale)
 D, J, K, N = prm["D"], prm["J"], prm["K"], prm["N"]
 L = lib(); L.sqc_session_mcd_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
-names = "KH KC DH DC DONE".split()
+names = "KH KC DH DC DONE DI ? ?".split()
 rows = []
 for leader in range(K):
     os.environ["SQC_MCD_TRACE"] = str(leader)
