@@ -198,6 +198,33 @@ SQC_API int  sqc_resident_fit(sqc_resident* r, const sqc_fit_args* args, int var
 SQC_API int  sqc_resident_outliers(sqc_resident* r, double alpha, double* maha, uint8_t* outlier, double* maha_cut, char* err, size_t errlen);
 SQC_API void sqc_resident_destroy(sqc_resident* r);
 
+/* ---- sample-sample maximum mean discrepancy --------------------------------------------- */
+/* mmd_fn(X, Y, sigma), reference src/mmd_fn.cpp:20-91: X n_x x D, Y n_y x D column-major; *mmd = the signed value.
+ * sigma <= 0 -> SQC_ERR_BAD_ARG ("sigma must be > 0", :28-30).                                                        */
+SQC_API int sqc_mmd_fn(const double* X, int64_t n_x, const double* Y, int64_t n_y, int32_t D, double sigma, double* mmd,
+                       int32_t device, char* err, size_t errlen);
+/* .calc_mmd_mat (reference R/calc_pairwise_mmds.R:198-247) in one call: every (i, j) pair x n_times repetitions of
+ * abs(mmd_fn(subsample of sample i, subsample of sample j)) (.dist_fn, :265-280) and their mean per pair.  The row picks
+ * are the caller's (R's sample() draws them, so R's RNG stream stays the caller's): for pair p, repetition t, the picks of
+ * side i are idx_i[(p * n_times + t) * subsample ..], 0-based; a sample with <= subsample rows is used whole and its
+ * picks are ignored (:271, :276).                                                                                    */
+typedef struct sqc_mmd_args {
+  uint32_t abi_version;
+  int32_t  D, n_samples;
+  const double*  mats;       /* the samples' matrices one after the other, each mat_rows[s] x D column-major           */
+  const int64_t* mat_rows;   /* n_samples                                                                              */
+  int64_t  n_pairs;
+  const int32_t* pair_i;     /* n_pairs, 0-based sample indices                                                        */
+  const int32_t* pair_j;
+  int32_t  n_times, subsample;
+  const int32_t* idx_i;      /* n_pairs x n_times x subsample (may be NULL when no sample exceeds subsample rows)      */
+  const int32_t* idx_j;
+  double   sigma;
+  int32_t  device;
+} sqc_mmd_args;
+SQC_API int sqc_mmd_pairs(const sqc_mmd_args* args, double* mmd_mean /* n_pairs */, double* mmd_all /* n_pairs x n_times or NULL */,
+                          char* err, size_t errlen);
+
 /* ---- resident sessions (benchmarks, multi-GPU drivers) --------------------------------- */
 /* A session keeps the cell matrix resident in HBM so that the EM loop can be timed without the
  * host<->device copies, and exposes per-kernel device timings for the roofline report.       */

@@ -45,6 +45,8 @@ def lib():
         L.sqc_oracle_qchisq.argtypes = [C.c_double, C.c_double]
         L.sqc_oracle_qchisq.restype = C.c_double
         L.sqc_oracle_set_cost_faithful.argtypes = [C.c_int]
+        L.sqc_oracle_mmd_fn.argtypes = [A.c_double_p, C.c_int64, A.c_double_p, C.c_int64, C.c_int32, C.c_double, A.c_double_p]
+        L.sqc_oracle_mmd_fn.restype = C.c_int
         L.sqc_oracle_fast_mcd.argtypes = [A.c_double_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_uint32,
                                           A.c_double_p, A.c_double_p, A.c_int32_p, A.c_double_p, C.c_char_p, C.c_size_t]
         L.sqc_oracle_fast_mcd.restype = C.c_int
@@ -93,6 +95,17 @@ def outlier_maha(x, groups, mu_0, alpha_j, beta_k, sigma_k, alpha, fn=None):
     if st != 0:
         raise A.SampleQCError(st, err.value.decode(errors="replace"))
     return maha, out.astype(bool), cut.value
+
+
+def mmd_fn(X, Y, sigma) -> float:
+    """reference src/mmd_fn.cpp:20-91"""
+    xa, ya = A.f64_colmajor(X), A.f64_colmajor(Y)
+    if xa.shape[1] != ya.shape[1]:
+        raise ValueError("X and Y must have same number of columns")       # :31-33
+    out = C.c_double(0)
+    if lib().sqc_oracle_mmd_fn(A.ptr_d(xa), xa.shape[0], A.ptr_d(ya), ya.shape[0], xa.shape[1], float(sigma), C.byref(out)) != 0:
+        raise A.SampleQCError(1, "sigma must be > 0")
+    return out.value
 
 
 def runif(seed: int, n: int) -> np.ndarray:

@@ -98,6 +98,20 @@ class SqcInitArgs(C.Structure):
     ]
 
 
+class SqcMmdArgs(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_uint32),
+        ("D", C.c_int32), ("n_samples", C.c_int32),
+        ("mats", c_double_p), ("mat_rows", C.POINTER(C.c_int64)),
+        ("n_pairs", C.c_int64),
+        ("pair_i", c_int32_p), ("pair_j", c_int32_p),
+        ("n_times", C.c_int32), ("subsample", C.c_int32),
+        ("idx_i", c_int32_p), ("idx_j", c_int32_p),
+        ("sigma", C.c_double),
+        ("device", C.c_int32),
+    ]
+
+
 class SqcRunStats(C.Structure):
     _fields_ = [
         ("n_iter", C.c_int32), ("n_gpu_launches", C.c_int32),

@@ -18,7 +18,7 @@ EXPORTS = (
     "sqc_session_create", "sqc_session_run", "sqc_session_fetch", "sqc_session_stats", "sqc_session_profile",
     "sqc_session_destroy", "sqc_xchg_export", "sqc_xchg_release",
     "sqc_trim", "sqc_abi_version", "sqc_device_count", "sqc_status_name", "sqc_device_qchisq", "sqc_device_rkeys", "sqc_device_rkeys_share", "sqc_device_expneg", "sqc_mt_jump_poly", "sqc_fp64_peak", "sqc_plan_shards",
-    "sqc_resident_create", "sqc_resident_init_clusts", "sqc_resident_subsample", "sqc_resident_fit", "sqc_resident_outliers", "sqc_resident_destroy",
+    "sqc_resident_create", "sqc_resident_init_clusts", "sqc_resident_subsample", "sqc_resident_fit", "sqc_resident_outliers", "sqc_resident_destroy", "sqc_mmd_fn", "sqc_mmd_pairs",
 )
 
 
@@ -86,6 +86,10 @@ def lib():
     L.sqc_resident_outliers.restype = C.c_int
     L.sqc_resident_destroy.argtypes = [C.c_void_p]
     L.sqc_resident_destroy.restype = None
+    L.sqc_mmd_fn.argtypes = [A.c_double_p, C.c_int64, A.c_double_p, C.c_int64, C.c_int32, C.c_double, A.c_double_p, C.c_int32, C.c_char_p, C.c_size_t]
+    L.sqc_mmd_fn.restype = C.c_int
+    L.sqc_mmd_pairs.argtypes = [C.POINTER(A.SqcMmdArgs), A.c_double_p, A.c_double_p, C.c_char_p, C.c_size_t]
+    L.sqc_mmd_pairs.restype = C.c_int
     L.sqc_plan_shards.argtypes = [A.c_int32_p, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int64), A.c_int32_p]
     L.sqc_plan_shards.restype = C.c_int
     L.sqc_mt_jump_poly.argtypes = [C.c_uint64, C.c_void_p]

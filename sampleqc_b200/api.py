@@ -318,3 +318,71 @@ class Resident:
             self.close()
         except Exception:
             pass
+
+
+def mmd_fn(X, Y, sigma, device=-1) -> float:
+    """mmd_fn(X, Y, sigma), reference src/mmd_fn.cpp:20-91 (the Rcpp export of R/RcppExports.R)"""
+    xa, ya = A.f64_colmajor(X), A.f64_colmajor(Y)
+    if xa.shape[1] != ya.shape[1]:
+        raise ValueError("X and Y must have same number of columns")       # :31-33
+    out = C.c_double(0)
+    err = C.create_string_buffer(512)
+    check(lib().sqc_mmd_fn(A.ptr_d(xa), xa.shape[0], A.ptr_d(ya), ya.shape[0], xa.shape[1], float(sigma), C.byref(out), int(device), err, 512), err)
+    return out.value
+
+
+def mmd_subsample_draws(rows, pi, pj, n_times, subsample, seed=22, draw=None):
+    """the row picks .dist_fn's sample() would draw (reference R/calc_pairwise_mmds.R:271-277) for every (pair, repetition,
+    side): int32 arrays P x n_times x subsample.  `draw(n, k)`: the caller's sampler, called pair by pair, repetition by
+    repetition, side i then side j — the order of the R loop; default: numpy, vectorised per sample."""
+    P = len(pi)
+    idx_i = np.zeros((P, n_times, subsample), dtype=np.int32); idx_j = np.zeros_like(idx_i)
+    if draw is not None:
+        for p in range(P):
+            for t in range(n_times):
+                if rows[pi[p]] > subsample:
+                    idx_i[p, t] = draw(int(rows[pi[p]]), subsample)
+                if rows[pj[p]] > subsample:
+                    idx_j[p, t] = draw(int(rows[pj[p]]), subsample)
+        return idx_i, idx_j
+    rng = np.random.default_rng(seed)
+    for side, out in ((pi, idx_i), (pj, idx_j)):
+        for s in np.unique(side):
+            n = int(rows[s])
+            if n <= subsample:
+                continue
+            where = np.nonzero(side == s)[0]
+            for c0 in range(0, where.size, 64):                   # chunks bound the scratch matrix of random keys
+                w = where[c0:c0 + 64]
+                keys = rng.random((w.size * n_times, n))
+                out[w] = np.argpartition(keys, subsample - 1, axis=1)[:, :subsample].reshape(w.size, n_times, subsample)
+    return idx_i, idx_j
+
+
+def calc_mmd_mat(mat_list, n_times, subsample, sigma, draw=None, seed=22, device=-1, return_all=False, timing=None):
+    """.calc_mmd_mat (reference R/calc_pairwise_mmds.R:198-247): the symmetric matrix of mean |MMD| over n_times subsample
+    pairs for every pair of samples, all pairs in ONE device call (`timing`: a dict that receives the seconds of that call)."""
+    import time
+    S = len(mat_list)
+    mats = [A.f64_colmajor(m) for m in mat_list]
+    D = mats[0].shape[1]
+    rows = np.array([m.shape[0] for m in mats], dtype=np.int64)
+    flat = np.concatenate([m.ravel(order="F") for m in mats])
+    pi, pj = np.array([(i, j) for j in range(S) for i in range(j)], dtype=np.int32).reshape(-1, 2).T.copy()      # sample_i < sample_j, :205-206
+    P = pi.size
+    idx_i, idx_j = mmd_subsample_draws(rows, pi, pj, n_times, subsample, seed=seed, draw=draw)
+    a = A.SqcMmdArgs()
+    a.abi_version, a.D, a.n_samples = A.SQC_ABI_VERSION, D, S
+    a.mats, a.mat_rows = A.ptr_d(flat), rows.ctypes.data_as(C.POINTER(C.c_int64))
+    a.n_pairs, a.pair_i, a.pair_j = P, A.ptr_i(pi), A.ptr_i(pj)
+    a.n_times, a.subsample, a.idx_i, a.idx_j = int(n_times), int(subsample), A.ptr_i(idx_i), A.ptr_i(idx_j)
+    a.sigma, a.device = float(sigma), int(device)
+    mean = np.zeros(P); allv = np.zeros((P, n_times))
+    err = C.create_string_buffer(512)
+    t0 = time.perf_counter()
+    check(lib().sqc_mmd_pairs(C.byref(a), A.ptr_d(mean), A.ptr_d(allv), err, 512), err)
+    if timing is not None:
+        timing["device_call_s"] = time.perf_counter() - t0
+    mat = np.zeros((S, S))
+    mat[pi, pj] = mean; mat[pj, pi] = mean                        # the reverse versions, :236-239; diagonal 0 (fill = 0, :244)
+    return (mat, allv, (pi, pj, idx_i, idx_j)) if return_all else mat

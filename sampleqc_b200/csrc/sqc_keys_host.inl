@@ -38,13 +38,10 @@ void key_stream_setup(sqc_session* S) {
     std::vector<unsigned char> hs((size_t)64 * W);
     CK(cudaMemcpyAsync(hs.data(), d_out, hs.size(), cudaMemcpyDeviceToHost, S->st));
     CK(cudaStreamSynchronize(S->st));
-    for (int q = 0; q < W; ++q) {                                   // mapped for the life of the session (closed in its destructor)
+    for (int q = 0; q < W; ++q) {
       if (q == r) { S->key_peer[q] = kb.p; continue; }
-      cudaIpcMemHandle_t ph; memcpy(&ph, hs.data() + (size_t)64 * q, 64);
-      void* p = nullptr;
-      cudaError_t e = cudaIpcOpenMemHandle(&p, ph, cudaIpcMemLazyEnablePeerAccess);
-      if (e != cudaSuccess) fail(SQC_ERR_COMM, "cudaIpcOpenMemHandle (key buffer of rank %d) failed: %s", q, cudaGetErrorString(e));
-      S->key_mapped[q] = p; S->key_peer[q] = (const int*)p;
+      try { S->key_peer[q] = (const int*)ipc_cache().open(S->device, hs.data() + (size_t)64 * q); }       // mapped once per process and peer buffer
+      catch (const std::exception& e) { fail(SQC_ERR_COMM, "key buffer of rank %d: %s", q, e.what()); }
     }
   }
   // jump polynomials: row 0 = call to call (floor(N_total / 624) chunks), row 1 = start of the call to this rank's share

@@ -29,6 +29,7 @@
 #include "sqc_mle.cuh"
 #include "sqc_xchg.cuh"
 #include "sqc_init.cuh"
+#include "sqc_mmd.cuh"
 
 #ifndef SQC_MCD_RESERVE_SMS
 #define SQC_MCD_RESERVE_SMS 24   // SMs k_mcd leaves to the key-stream kernels (R-compatible keys only), see session_create
@@ -329,7 +330,6 @@ struct sqc_session {
     if (st) cudaStreamSynchronize(st);
     if (st_rng) cudaStreamSynchronize(st_rng);
     if (st_rng2) cudaStreamSynchronize(st_rng2);
-    for (int q = 0; q < XCHG_MAX_WORLD; ++q) if (key_mapped[q]) { cudaIpcCloseMemHandle(key_mapped[q]); key_mapped[q] = nullptr; }
     xchg_close(xc);
     for (auto& c : chunks) g_chunks.give(device, c);
     for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -748,7 +748,10 @@ sqc_session* session_create(const sqc_fit_args* a, int variant, InprocGroup* grp
       // it on the side stream (a CTA of k_mcd owns a whole SM, so they cannot share one; without free SMs the generation
       // falls onto the E-step / partition passes and onto the critical path: +50 % per iteration at C3).  k_mcd is
       // HBM / latency bound, not SM bound.
-      int reserve = getenv("SQC_MCD_RESERVE") ? atoi(getenv("SQC_MCD_RESERVE")) : SQC_MCD_RESERVE_SMS;
+      // No more than the generation has blocks (one CTA each): a rank of a multi-GPU fit generates only its share of a call.
+      const long long share = (S->world > 1 && S->N_total >= 624LL * 8 * S->world && !getenv("SQC_KEYS_REPLICATED")) ? (S->N_total + S->world - 1) / S->world : S->N_total;
+      const long long blk = MT_BLOCK_WORDS * std::max<long long>(1, std::min<long long>(3, (share / MT_BLOCK_WORDS + S->mt_target_blocks / 2) / S->mt_target_blocks));
+      int reserve = getenv("SQC_MCD_RESERVE") ? atoi(getenv("SQC_MCD_RESERVE")) : (int)std::min<long long>(SQC_MCD_RESERVE_SMS, (share + blk - 1) / blk + 1);
       reserve = std::max(0, std::min(reserve, S->mcd_grid - 2 * K - 8));
       S->mcd_grid -= reserve;
     }
@@ -1081,6 +1084,7 @@ int sqc_outlier_maha(const sqc_maha_args* a, double* maha, uint8_t* outlier, dou
 
 #include "sqc_init_host.inl"
 #include "sqc_pipe_host.inl"
+#include "sqc_mmd_host.inl"
 
 int sqc_xchg_export(int device, void* handle_out, char* err, size_t errlen) {
   return guarded([&] {

@@ -9,16 +9,18 @@ struct sqc_resident {
   int device = 0, D = 0, J = 0; long long N = 0;
   double* x = nullptr; int* groups = nullptr;                 // device: raw x (N x D column-major), sample index per cell
   double* med = nullptr; bool have_med = false;               // device: J x D medians
-  int* z = nullptr; double* gamma = nullptr; int K_cls = 0;   // device: classification of all cells under the caller's mixture
+  int* z = nullptr; double* gamma = nullptr; int K_cls = 0, K_gam = 0;   // device: classification of all cells under the caller's mixture
   std::vector<int32_t> h_groups; std::vector<long long> bounds;
   bool runs_ok = true;                                        // every sample is one contiguous run of cells
   // parameters of the last fit, re-centred (host): what .calc_outliers_dt receives
   int K_fit = 0; std::vector<double> mu0, alpha, beta, sigma;
   cudaStream_t st = nullptr;
+  std::vector<Chunk> chunks;                                  // from the per-device arena the fits use (cudaMalloc of 100s of MB costs tens of ms)
+  void* take(size_t bytes) { chunks.push_back(g_chunks.take(device, std::max<size_t>(bytes, 256))); return chunks.back().base; }
   ~sqc_resident() {
     if (device >= 0) cudaSetDevice(device);
     if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
-    cudaFree(x); cudaFree(groups); cudaFree(med); cudaFree(z); cudaFree(gamma);
+    for (auto& c : chunks) g_chunks.give(device, c);
   }
 };
 
@@ -31,20 +33,42 @@ int sqc_resident_create(const double* x, const int32_t* groups, int32_t D, int32
     select_device(device, &R->device);
     R->D = D; R->J = J; R->N = N;
     CK(cudaStreamCreateWithFlags(&R->st, cudaStreamNonBlocking));
-    CK(cudaMalloc((void**)&R->x, (size_t)N * D * sizeof(double))); CK(cudaMalloc((void**)&R->groups, (size_t)N * sizeof(int)));
-    CK(cudaMalloc((void**)&R->med, (size_t)J * D * sizeof(double)));
+    R->x = (double*)R->take((size_t)N * D * sizeof(double)); R->groups = (int*)R->take((size_t)N * sizeof(int)); R->med = (double*)R->take((size_t)J * D * sizeof(double));
     // the one upload of the cells (asynchronous when the caller's memory is pinned); the host scans the groups meanwhile
     CK(cudaMemcpyAsync(R->x, x, (size_t)N * D * sizeof(double), cudaMemcpyHostToDevice, R->st));
     CK(cudaMemcpyAsync(R->groups, groups, (size_t)N * sizeof(int), cudaMemcpyHostToDevice, R->st));
-    R->h_groups.assign(groups, groups + N);
+    // host copy + scan of the groups on a few threads (it hides behind the upload): range check, sample sizes, and
+    // "every sample is one contiguous run" (chunk-local run lists, merged in order)
+    R->h_groups.resize((size_t)N);
     R->bounds.assign((size_t)J + 1, 0);
-    std::vector<char> seen(J, 0);
-    int prev = -1;
-    for (long long i = 0; i < N; ++i) {
-      const int g = groups[i];
-      if (g < 0 || g >= J) { cudaStreamSynchronize(R->st); fail(SQC_ERR_BAD_ARG, "groups out of range at cell %lld", i); }
-      R->bounds[(size_t)g + 1]++;
-      if (g != prev) { if (seen[g]) R->runs_ok = false; seen[g] = 1; prev = g; }
+    {
+      const int nth = (N >= (1 << 20)) ? 8 : 1;
+      std::vector<std::vector<long long>> cnt(nth, std::vector<long long>(J, 0));
+      std::vector<std::vector<int>> runs(nth);
+      std::vector<long long> bad(nth, -1); std::vector<char> ovf(nth, 0);
+      auto scan = [&](int t) {
+        const long long i0 = N * t / nth, i1 = N * (t + 1) / nth;
+        memcpy(R->h_groups.data() + i0, groups + i0, (size_t)(i1 - i0) * sizeof(int32_t));
+        int prev = -1;
+        for (long long i = i0; i < i1; ++i) {
+          const int g = groups[i];
+          if ((unsigned)g >= (unsigned)J) { bad[t] = i; return; }
+          cnt[t][g]++;
+          if (g != prev) { if ((long long)runs[t].size() <= J) runs[t].push_back(g); else ovf[t] = 1; prev = g; }
+        }
+      };
+      std::vector<std::thread> th;
+      for (int t = 1; t < nth; ++t) th.emplace_back(scan, t);
+      scan(0);
+      for (auto& x : th) x.join();
+      std::vector<char> seen(J, 0);
+      int prev = -1;
+      for (int t = 0; t < nth; ++t) {
+        if (bad[t] >= 0) { cudaStreamSynchronize(R->st); fail(SQC_ERR_BAD_ARG, "groups out of range at cell %lld", bad[t]); }
+        if (ovf[t]) R->runs_ok = false;
+        for (int j = 0; j < J; ++j) R->bounds[(size_t)j + 1] += cnt[t][j];
+        for (int g : runs[t]) { if (g == prev) continue; if (seen[g]) R->runs_ok = false; seen[g] = 1; prev = g; }
+      }
     }
     if (!R->runs_ok) { cudaStreamSynchronize(R->st); fail(SQC_ERR_BAD_ARG, "the resident pipeline needs the cells of every sample to be contiguous (as fit_sampleqc() builds x, R/fit_sampleqc.R:205-216)"); }
     CK(cudaStreamSynchronize(R->st));
@@ -106,9 +130,9 @@ int sqc_resident_init_clusts(sqc_resident* R, const double* pro, const double* m
         for (int e = 0; e < D * D; ++e) par[(size_t)k * P + D + e] = Li[e];
         par[(size_t)k * P + D + D * D] = c;
       }
-      if (!R->z) CK(cudaMalloc((void**)&R->z, (size_t)N * sizeof(int)));
+      if (!R->z) R->z = (int*)R->take((size_t)N * sizeof(int));
       const bool want_gamma = keep_gamma || gamma;
-      if (want_gamma && (R->K_cls != K || !R->gamma)) { cudaFree(R->gamma); R->gamma = nullptr; CK(cudaMalloc((void**)&R->gamma, (size_t)N * K * sizeof(double))); }
+      if (want_gamma && (R->K_gam < K || !R->gamma)) { R->gamma = (double*)R->take((size_t)N * K * sizeof(double)); R->K_gam = K; }
       double* dpar = nullptr;
       try {
         CK(cudaMalloc((void**)&dpar, par.size() * sizeof(double)));

@@ -18,6 +18,9 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <array>
+#include <map>
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <cuda_runtime.h>
@@ -183,7 +186,36 @@ inline void xchg_export(int device, void* handle_out) {
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   memcpy(handle_out, &h, sizeof h);
 }
+// Peer mappings are kept for the life of the process, keyed by the 64 bytes of the IPC handle (sqc_comm semantics):
+// opening and closing 7 windows and 7 key buffers per fit cost more than the fit itself at 8 GPUs.  A handle names one
+// allocation of one peer process: a peer that restarts or re-allocates presents a new handle and gets a new mapping; the
+// stale one is never used again and is closed by sqc_xchg_release(device).
+struct IpcCache {
+  std::mutex mu; std::map<std::array<unsigned char, 64>, void*> map[64];
+  void* open(int device, const void* handle64) {
+    std::array<unsigned char, 64> key; memcpy(key.data(), handle64, 64);
+    std::lock_guard<std::mutex> lk(mu);
+    auto& m = map[device & 63];
+    auto it = m.find(key);
+    if (it != m.end()) return it->second;
+    cudaIpcMemHandle_t h; memcpy(&h, handle64, sizeof h);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) throw std::runtime_error(std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(e));
+    m.emplace(key, p);
+    return p;
+  }
+  void close_all(int device) {
+    std::lock_guard<std::mutex> lk(mu);
+    for (auto& kv : map[device & 63]) cudaIpcCloseMemHandle(kv.second);
+    map[device & 63].clear();
+  }
+};
+inline IpcCache& ipc_cache() { static IpcCache c; return c; }
+
 inline int xchg_release(int device) {
+  cudaSetDevice(device);
+  ipc_cache().close_all(device);
   XchgLocal& L = xchg_local(device);
   if (L.window) { cudaSetDevice(device); cudaFree(L.window); cudaFree(L.next_seq); L.window = nullptr; L.next_seq = nullptr; }
   return 0;
@@ -198,11 +230,7 @@ inline void xchg_open(Xchg& X, int device, int rank, int world, const void* hand
   X.open = true;                                       // from here on xchg_close releases what has been mapped (also after a failure half way)
   for (int r = 0; r < world; ++r) {
     if (r == rank) { X.dev.peer[r] = L.window; continue; }
-    cudaIpcMemHandle_t h; memcpy(&h, (const char*)handles + (size_t)r * 64, sizeof h);
-    void* p = nullptr;
-    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
-    if (e != cudaSuccess) throw std::runtime_error(std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(e));
-    X.mapped[r] = p; X.dev.peer[r] = (unsigned char*)p;
+    X.dev.peer[r] = (unsigned char*)ipc_cache().open(device, (const char*)handles + (size_t)r * 64);   // mapped once per process and peer
   }
 }
 // one process, one host thread per GPU: the peers' windows are ordinary device pointers (peer access enabled by the caller)
@@ -219,7 +247,7 @@ inline void xchg_open_inproc(Xchg& X, int device, int rank, int world, const int
 }
 inline void xchg_close(Xchg& X) {
   if (!X.open) return;
-  for (int r = 0; r < X.world; ++r) if (X.mapped[r]) { cudaIpcCloseMemHandle(X.mapped[r]); X.mapped[r] = nullptr; }
+  for (int r = 0; r < X.world; ++r) X.mapped[r] = nullptr;       // (the mappings belong to the process-wide cache)
   X.open = false;
 }
 
