@@ -6,7 +6,7 @@
 // Instead rank r generates draws [r Q, (r + 1) Q) of every call into a buffer the peers map (cudaIpc), and the M-step
 // kernel reads a cell's key from its owner over NVLink (4 B per cell in the one or two key rounds of a call).  The
 // buffers' IPC handles travel through the exchange window itself, so the C ABI is unchanged.
-struct KeyBufLocal { int* p = nullptr; size_t ints = 0; };
+struct KeyBufLocal { int* p = nullptr; size_t ints = 0; std::vector<int*> retired; };
 KeyBufLocal& key_buf_local(int device) { static KeyBufLocal b[64]; return b[device & 63]; }
 
 void key_stream_setup(sqc_session* S) {
@@ -18,7 +18,10 @@ void key_stream_setup(sqc_session* S) {
   // own buffer (two calls in flight), kept per device for the life of the process: its IPC handle stays valid
   KeyBufLocal& kb = key_buf_local(S->device);
   if (kb.ints < 2 * (size_t)S->key_q) {
-    if (kb.p) { CK(cudaDeviceSynchronize()); cudaFree(kb.p); kb.p = nullptr; kb.ints = 0; }
+    // a buffer that has been exported stays allocated: peers keep their mapping of it for the life of the process
+    // (IpcCache), and freeing an exported allocation under a live mapping is undefined.  Retired buffers go with
+    // sqc_xchg_release.
+    if (kb.p) { kb.retired.push_back(kb.p); kb.p = nullptr; kb.ints = 0; }
     CK(cudaMalloc((void**)&kb.p, 2 * (size_t)S->key_q * sizeof(int)));
     kb.ints = 2 * (size_t)S->key_q;
   }
@@ -145,10 +148,12 @@ void use_keys(sqc_session* S, int call) {
   if (S->rng_mode == SQC_RNG_R_COMPAT) {
     CK(cudaStreamWaitEvent(S->st, S->ev_key_ready[call & 1], 0));
     if (S->key_q) {
-      // every rank's share of this call must be complete before any rank's M-step kernel reads it: one tiny exchange
-      // behind the wait orders them (the peers' reads end before this kernel's last exchange of the call, so the
-      // buffer may be refilled once the kernel is done - the same event that frees it locally)
-      { Launch L(S, SQC_KF_UPDATE, nullptr, "key_fence"); k_xchg_sum_f64<<<1, 32, 0, S->st>>>(S->xc.dev, XCHG_CH_HOST + 0, S->xg_vec + 8, 1, &S->dev.ctl->cont); L.done(); }
+      // every rank's share of this call must be complete before any rank's M-step kernel reads it.  For calls 0 and >= 2 the
+      // per-iteration exchange in front of the call was enqueued behind the wait for the local share (run_robust) and is the
+      // fence; call 1 has no such exchange in front of it (it follows the initial M-step directly): one tiny exchange of its
+      // own.  (The peers' reads end before this kernel's last exchange of the call, so the buffer may be refilled once the
+      // kernel is done - the same event that frees it locally.)
+      if (call == 1) { Launch L(S, SQC_KF_UPDATE, nullptr, "key_fence"); k_xchg_sum_f64<<<1, 32, 0, S->st>>>(S->xc.dev, XCHG_CH_HOST + 0, S->xg_vec + 8, 1, &S->dev.ctl->cont); L.done(); }
       S->mb.keys = S->keybuf + (size_t)(call & 1) * S->key_q;
       for (int q = 0; q < S->world; ++q) S->mb.key_peer[q] = S->key_peer[q] + (size_t)(call & 1) * S->key_q;
       S->mb.key_q = S->key_q; S->mb.key_qinv = 1.0 / (double)S->key_q;
@@ -157,20 +162,21 @@ void use_keys(sqc_session* S, int call) {
     // the keys of the NEXT call are generated while this call's M-step kernel runs (released only now: kernels that
     // slip onto the SMs during a wait above would hold up the cooperative launch that follows)
     if (!S->rng_after_mcd) enqueue_next_keys(S, call);
+    // ... and so is the state chain of call + 2 (two CTAs on the SMs k_mcd leaves free).  Behind the M-step kernel it ran
+    // beside the next partition pass, and that pass then never finished before the chain's 0.2 ms jump kernel did
+    // (profiles/r2u_timeline_w2_rank0.csv: partition 87 us against 53-70 us without a chain beside it, at any shard size).
+    if (S->key_q && call + 2 <= S->em_iters) {
+      CK(cudaEventRecord(S->ev_post_mcd, S->st));
+      enqueue_chain(S, call + 2, S->ev_post_mcd);             // its share-state slot was last read by the keys of `call`
+    }
   } else S->mb.keys = nullptr;
   S->mb.call_mix = counter_call_mix(S->seed, 0u);
   S->mb.stream_base = (long long)call * S->N_total;
   S->mb.call = call;
 }
-// behind the M-step kernel: the state chain of call + 2 (tiny; a CTA of it in front of the cooperative launch would
-// delay that launch by its whole 0.15 ms)
 void after_mcd_keys(sqc_session* S, int call) {
   if (S->rng_mode != SQC_RNG_R_COMPAT) return;
   if (S->rng_after_mcd) enqueue_next_keys(S, call);
-  if (S->key_q && call + 2 <= S->em_iters) {
-    CK(cudaEventRecord(S->ev_post_mcd, S->st));
-    enqueue_chain(S, call + 2, S->ev_post_mcd);             // its share-state slot was last read by the keys of `call`
-  }
 }
 void release_keys(sqc_session* S, int call) {
   if (S->rng_mode != SQC_RNG_R_COMPAT) return;

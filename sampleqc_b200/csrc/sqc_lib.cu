@@ -749,9 +749,14 @@ sqc_session* session_create(const sqc_fit_args* a, int variant, InprocGroup* grp
       // falls onto the E-step / partition passes and onto the critical path: +50 % per iteration at C3).  k_mcd is
       // HBM / latency bound, not SM bound.
       // No more than the generation has blocks (one CTA each): a rank of a multi-GPU fit generates only its share of a call.
-      const long long share = (S->world > 1 && S->N_total >= 624LL * 8 * S->world && !getenv("SQC_KEYS_REPLICATED")) ? (S->N_total + S->world - 1) / S->world : S->N_total;
+      const bool shares = S->world > 1 && S->N_total >= 624LL * 8 * S->world && !getenv("SQC_KEYS_REPLICATED");
+      const long long share = shares ? (S->N_total + S->world - 1) / S->world : S->N_total;
+      // a rank's share is cut into about as many blocks as SMs are reserved, so that the jump kernel (one CTA per block,
+      // 157 us each) runs in ONE wave: with 73 blocks of a 5 M-key share on 24 SMs it took three (0.42 ms) and the chain
+      // fell behind k_mcd onto the partition pass and the key fence (profiles/r2s_timeline_w2_rank0.csv)
+      if (shares && !getenv("SQC_MT_BLOCKS")) S->mt_target_blocks = SQC_MCD_RESERVE_SMS;
       const long long blk = MT_BLOCK_WORDS * std::max<long long>(1, std::min<long long>(3, (share / MT_BLOCK_WORDS + S->mt_target_blocks / 2) / S->mt_target_blocks));
-      int reserve = getenv("SQC_MCD_RESERVE") ? atoi(getenv("SQC_MCD_RESERVE")) : (int)std::min<long long>(SQC_MCD_RESERVE_SMS, (share + blk - 1) / blk + 1);
+      int reserve = getenv("SQC_MCD_RESERVE") ? atoi(getenv("SQC_MCD_RESERVE")) : (int)std::min<long long>(SQC_MCD_RESERVE_SMS, (share + blk - 1) / blk + 1) + (shares ? 2 : 0);   // + the two CTAs of the state chain
       reserve = std::max(0, std::min(reserve, S->mcd_grid - 2 * K - 8));
       S->mcd_grid -= reserve;
     }
@@ -841,6 +846,9 @@ void run_robust(sqc_session* S) {
   // initial labelling: p_jk (:481), alpha_j (:482), beta_k / Sigma_k (:483)
   do_estep(S, 1);
   post_stats(0);
+  // distributed key stream: every rank's share of a call has to be complete before any rank's M-step kernel reads it.  The
+  // per-iteration exchange that precedes the call doubles as that fence: the stream waits for the local share first.
+  if (S->key_q) CK(cudaStreamWaitEvent(S->st, S->ev_key_ready[0], 0));
   if (S->world > 1) xchg_iteration(S, s, 0);
   { Launch L(S, SQC_KF_UPDATE); k_update_p<<<(J + 127) / 128, 128, 0, S->st>>>(s); L.done(); }
   m_step(0, 0);
@@ -851,6 +859,7 @@ void run_robust(sqc_session* S) {
     m_step(it + 1, 1);                                                                  // like_1 :499, M-step :502, p_jk :504
     do_estep(S, 0);                                                                     // :506, :509, :519
     post_stats(S->world > 1 ? 0 : 1);                                                  // single GPU: :511-521 fused in
+    if (S->key_q && it + 2 <= S->em_iters) CK(cudaStreamWaitEvent(S->st, S->ev_key_ready[(it + 2) & 1], 0));   // keys of the next call (fence, see above)
     if (S->world > 1) xchg_iteration(S, s, 1);     // cluster layout of the next M-step + like / z_delta / status + loop control
   }
   CK(cudaEventRecord(S->ev_loop, S->st));
@@ -1047,36 +1056,45 @@ int sqc_outlier_maha(const sqc_maha_args* a, double* maha, uint8_t* outlier, dou
     // solve(cov) on the host: K tiny inverses (stats::mahalanobis)
     std::vector<double> ainv((size_t)K * D * D);
     for (int k = 0; k < K; ++k) if (!small_inv(a->sigma_k + (size_t)k * D * D, D, ainv.data() + (size_t)k * D * D)) fail(SQC_ERR_SINGULAR, "solve(): system is exactly singular");
-    double *dx = nullptr, *dpar = nullptr, *dm = nullptr; int* dg = nullptr; uint8_t* dout = nullptr; double* dq = nullptr;
-    auto cleanup = [&] { cudaFree(dx); cudaFree(dpar); cudaFree(dm); cudaFree(dg); cudaFree(dout); cudaFree(dq); };
+    // device buffers from the per-device arena the fits use; copies on a stream (asynchronous from pinned memory), the
+    // host checks the groups while x is on its way
+    cudaStream_t st = nullptr;
+    std::vector<Chunk> chunks;
+    auto take = [&](size_t bytes) { chunks.push_back(g_chunks.take(dev, std::max<size_t>(bytes, 256))); return (void*)chunks.back().base; };
+    auto cleanup = [&] { if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); } for (auto& c : chunks) g_chunks.give(dev, c); };
     try {
-      const size_t npar = (size_t)D + (size_t)J * D + (size_t)K * D + (size_t)K * D * D;
-      CK(cudaMalloc((void**)&dx, (size_t)N * D * sizeof(double))); CK(cudaMalloc((void**)&dg, (size_t)N * sizeof(int)));
-      CK(cudaMalloc((void**)&dpar, npar * sizeof(double))); CK(cudaMalloc((void**)&dq, 3 * sizeof(double)));
-      if (maha) CK(cudaMalloc((void**)&dm, (size_t)N * K * sizeof(double)));
-      if (outlier) CK(cudaMalloc((void**)&dout, (size_t)N));
-      CK(cudaMemcpy(dx, a->x, (size_t)N * D * sizeof(double), cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(dg, a->groups, (size_t)N * sizeof(int), cudaMemcpyHostToDevice));
-      double* pm = dpar; double* pa = pm + D; double* pb = pa + (size_t)J * D; double* pi = pb + (size_t)K * D;
-      CK(cudaMemcpy(pm, a->mu_0, D * sizeof(double), cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(pa, a->alpha_j, (size_t)J * D * sizeof(double), cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(pb, a->beta_k, (size_t)K * D * sizeof(double), cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(pi, ainv.data(), (size_t)K * D * D * sizeof(double), cudaMemcpyHostToDevice));
-      double hq[3] = {1.0 - a->alpha, (double)D, 0.0};                  // qchisq(1 - alpha, df = D), :429
-      CK(cudaMemcpy(dq, hq, sizeof hq, cudaMemcpyHostToDevice));
-      k_qchisq<<<1, 32>>>(dq, dq + 1, dq + 2, 1);
-      CK(cudaMemcpy(hq, dq, sizeof hq, cudaMemcpyDeviceToHost));
-      const double cut = hq[2];
+      CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+      const size_t npar = (size_t)D + (size_t)J * D + (size_t)K * D + (size_t)K * D * D + 4;
+      double* dx = (double*)take((size_t)N * D * sizeof(double)); int* dg = (int*)take((size_t)N * sizeof(int));
+      double* dpar = (double*)take(npar * sizeof(double));
+      double* dm = maha ? (double*)take((size_t)N * K * sizeof(double)) : nullptr;
+      uint8_t* dout = outlier ? (uint8_t*)take((size_t)N) : nullptr;
+      CK(cudaMemcpyAsync(dx, a->x, (size_t)N * D * sizeof(double), cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(dg, a->groups, (size_t)N * sizeof(int), cudaMemcpyHostToDevice, st));
+      std::vector<double> hp(npar);
+      double* q = hp.data();
+      memcpy(q, a->mu_0, D * sizeof(double)); q += D;
+      memcpy(q, a->alpha_j, (size_t)J * D * sizeof(double)); q += (size_t)J * D;
+      memcpy(q, a->beta_k, (size_t)K * D * sizeof(double)); q += (size_t)K * D;
+      memcpy(q, ainv.data(), (size_t)K * D * D * sizeof(double)); q += (size_t)K * D * D;
+      q[0] = 1.0 - a->alpha; q[1] = (double)D; q[2] = 0.0;               // qchisq(1 - alpha, df = D), :429
+      CK(cudaMemcpyAsync(dpar, hp.data(), npar * sizeof(double), cudaMemcpyHostToDevice, st));
+      for (long long i = 0; i < N; ++i) if ((unsigned)a->groups[i] >= (unsigned)J) fail(SQC_ERR_BAD_ARG, "groups out of range at cell %lld", i);
+      double* pm = dpar; double* pa = pm + D; double* pb = pa + (size_t)J * D; double* pi = pb + (size_t)K * D; double* pq = pi + (size_t)K * D * D;
+      k_qchisq<<<1, 32, 0, st>>>(pq, pq + 1, pq + 2, 1);
+      double cut = 0.0;
+      CK(cudaMemcpyAsync(&cut, pq + 2, sizeof(double), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
       if (maha_cut) *maha_cut = cut;
-      for (long long i = 0; i < N; ++i) if (a->groups[i] < 0 || a->groups[i] >= J) fail(SQC_ERR_BAD_ARG, "groups out of range");
-      const int grid = (int)std::min<long long>((N + 255) / 256, 148 * 16);
+      int n_sm = 148; CK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+      const int grid = (int)std::min<long long>((N + 255) / 256, (long long)n_sm * 16);   // a few waves of 256-thread CTAs, grid-stride
       const size_t sm = (size_t)K * (D + D * D) * sizeof(double);
-#define SQC_CASE_MAHA(DD) case DD: k_outlier_maha<DD><<<grid, 256, sm>>>(dx, dg, N, J, K, pm, pa, pb, pi, cut, dm, dout); break;
+#define SQC_CASE_MAHA(DD) case DD: k_outlier_maha<DD><<<grid, 256, sm, st>>>(dx, dg, N, J, K, pm, pa, pb, pi, cut, dm, dout); break;
       switch (D) { SQC_FOR_D(SQC_CASE_MAHA) default: fail(SQC_ERR_BAD_ARG, "D = %d not compiled in", D); }
       CK(cudaGetLastError());
-      if (maha) CK(cudaMemcpy(maha, dm, (size_t)N * K * sizeof(double), cudaMemcpyDeviceToHost));
-      if (outlier) CK(cudaMemcpy(outlier, dout, (size_t)N, cudaMemcpyDeviceToHost));
-      CK(cudaDeviceSynchronize());
+      if (maha) CK(cudaMemcpyAsync(maha, dm, (size_t)N * K * sizeof(double), cudaMemcpyDeviceToHost, st));
+      if (outlier) CK(cudaMemcpyAsync(outlier, dout, (size_t)N, cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
     } catch (...) { cleanup(); throw; }
     cleanup();
   }, err, errlen);
@@ -1093,7 +1111,16 @@ int sqc_xchg_export(int device, void* handle_out, char* err, size_t errlen) {
     try { xchg_export(d, handle_out); } catch (const std::exception& e) { fail(SQC_ERR_COMM, "%s", e.what()); }
   }, err, errlen);
 }
-int sqc_xchg_release(int device) { return xchg_release(device); }
+int sqc_xchg_release(int device) {
+  // call it on every rank once no rank will run another multi-GPU fit: it closes this process' mappings of the peers'
+  // windows / key buffers and frees its own
+  const int st = xchg_release(device);
+  KeyBufLocal& kb = key_buf_local(device);
+  for (int* p : kb.retired) cudaFree(p);
+  kb.retired.clear();
+  if (kb.p) { cudaFree(kb.p); kb.p = nullptr; kb.ints = 0; }
+  return st;
+}
 
 int sqc_trim(int device) {
   int n = 0;

@@ -10,7 +10,8 @@ struct sqc_resident {
   double* x = nullptr; int* groups = nullptr;                 // device: raw x (N x D column-major), sample index per cell
   double* med = nullptr; bool have_med = false;               // device: J x D medians
   int* z = nullptr; double* gamma = nullptr; int K_cls = 0, K_gam = 0;   // device: classification of all cells under the caller's mixture
-  std::vector<int32_t> h_groups; std::vector<long long> bounds;
+  std::vector<int32_t> h_groups; std::vector<long long> bounds;   // bounds[j + 1] = cells of sample j
+  std::vector<int> run_order;                                 // sample codes in order of appearance
   bool runs_ok = true;                                        // every sample is one contiguous run of cells
   // parameters of the last fit, re-centred (host): what .calc_outliers_dt receives
   int K_fit = 0; std::vector<double> mu0, alpha, beta, sigma;
@@ -67,7 +68,7 @@ int sqc_resident_create(const double* x, const int32_t* groups, int32_t D, int32
         if (bad[t] >= 0) { cudaStreamSynchronize(R->st); fail(SQC_ERR_BAD_ARG, "groups out of range at cell %lld", bad[t]); }
         if (ovf[t]) R->runs_ok = false;
         for (int j = 0; j < J; ++j) R->bounds[(size_t)j + 1] += cnt[t][j];
-        for (int g : runs[t]) { if (g == prev) continue; if (seen[g]) R->runs_ok = false; seen[g] = 1; prev = g; }
+        for (int g : runs[t]) { if (g == prev) continue; if (seen[g]) R->runs_ok = false; seen[g] = 1; prev = g; R->run_order.push_back(g); }
       }
     }
     if (!R->runs_ok) { cudaStreamSynchronize(R->st); fail(SQC_ERR_BAD_ARG, "the resident pipeline needs the cells of every sample to be contiguous (as fit_sampleqc() builds x, R/fit_sampleqc.R:205-216)"); }
@@ -81,8 +82,8 @@ namespace {
 // start of every sample's run of cells (samples appear in any code order, each in one run)
 void resident_run_bounds(const sqc_resident* R, std::vector<long long>& b0, std::vector<long long>& b1) {
   b0.assign(R->J, 0); b1.assign(R->J, 0);
-  int prev = -1;
-  for (long long i = 0; i < R->N; ++i) { const int g = R->h_groups[(size_t)i]; if (g != prev) { b0[g] = i; prev = g; } b1[g] = i + 1; }
+  long long pos = 0;
+  for (int g : R->run_order) { b0[g] = pos; pos += R->bounds[(size_t)g + 1]; b1[g] = pos; }
 }
 void resident_medians(sqc_resident* R) {
   if (R->have_med) return;

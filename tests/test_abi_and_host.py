@@ -35,11 +35,11 @@ def test_library_exports_every_declared_symbol():
 def test_ctypes_structs_match_header_sizes(tmp_path):
     from sampleqc_b200 import _abi as A
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "sampleqc_cuda.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(sqc_fit_args), sizeof(sqc_fit_out), sizeof(sqc_maha_args), sizeof(sqc_run_stats), sizeof(sqc_init_args));return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include "sampleqc_cuda.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(sqc_fit_args), sizeof(sqc_fit_out), sizeof(sqc_maha_args), sizeof(sqc_run_stats), sizeof(sqc_init_args), sizeof(sqc_mmd_args));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
     sizes = [int(v) for v in subprocess.check_output([str(exe)]).split()]
-    assert sizes == [C.sizeof(A.SqcFitArgs), C.sizeof(A.SqcFitOut), C.sizeof(A.SqcMahaArgs), C.sizeof(A.SqcRunStats), C.sizeof(A.SqcInitArgs)]
+    assert sizes == [C.sizeof(A.SqcFitArgs), C.sizeof(A.SqcFitOut), C.sizeof(A.SqcMahaArgs), C.sizeof(A.SqcRunStats), C.sizeof(A.SqcInitArgs), C.sizeof(A.SqcMmdArgs)]
 
 
 def test_no_cpu_fallback_without_gpu():
