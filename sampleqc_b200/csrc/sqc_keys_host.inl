@@ -40,7 +40,10 @@ void key_stream_setup(sqc_session* S) {
     k_xchg_gather_u64<<<1, 256, 0, S->st>>>(S->xc.dev, XCHG_CH_HOST + 0, d_in, d_out, 8, nullptr);
     std::vector<unsigned char> hs((size_t)64 * W);
     CK(cudaMemcpyAsync(hs.data(), d_out, hs.size(), cudaMemcpyDeviceToHost, S->st));
+    int st_dev = 0;
+    CK(cudaMemcpyAsync(&st_dev, &S->dev.ctl->status, sizeof(int), cudaMemcpyDeviceToHost, S->st));
     CK(cudaStreamSynchronize(S->st));
+    if (st_dev == SQC_D_TIMEOUT) fail(SQC_ERR_COMM, "%s", device_status_message(st_dev));      // a peer never sent its handle
     for (int q = 0; q < W; ++q) {
       if (q == r) { S->key_peer[q] = kb.p; continue; }
       try { S->key_peer[q] = (const int*)ipc_cache().open(S->device, hs.data() + (size_t)64 * q); }       // mapped once per process and peer buffer

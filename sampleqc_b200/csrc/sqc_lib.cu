@@ -687,6 +687,7 @@ sqc_session* session_create(const sqc_fit_args* a, int variant, InprocGroup* grp
   s.like1 = S->alloc<double>(em + 1); s.like2 = S->alloc<double>(em + 1);
   s.ctl = S->alloc<Control>(1);
   S->xc.dev.status = &s.ctl->status;                  // (multi-GPU) exchange waits report a timeout here
+  S->xc.dev.budget_ns = getenv("SQC_WAIT_BUDGET_MS") ? std::max(1LL, atoll(getenv("SQC_WAIT_BUDGET_MS"))) * 1000000LL : SQC_WAIT_BUDGET_NS;
   S->alpha0 = S->alloc<double>((size_t)J * D);
   if (S->track && variant == SQC_VARIANT_ROBUST) {
     s.track_alpha = S->alloc<double>((size_t)J * D * em); s.track_beta = S->alloc<double>((size_t)K * D * em);
@@ -798,6 +799,11 @@ sqc_session* session_create(const sqc_fit_args* a, int variant, InprocGroup* grp
   do_init_passes(S);
   CK(cudaMemcpyAsync(S->alpha0, s.alpha, (size_t)J * D * sizeof(double), cudaMemcpyDeviceToDevice, S->st));
   CK(cudaStreamSynchronize(S->st));
+  if (S->world > 1) {                                 // the column means were exchanged: a peer that never showed up is known by now
+    int st_dev = 0;
+    CK(cudaMemcpy(&st_dev, &s.ctl->status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (st_dev == SQC_D_TIMEOUT) fail(SQC_ERR_COMM, "%s", device_status_message(st_dev));
+  }
   CK(cudaEventCreate(&S->ev_run0)); CK(cudaEventCreate(&S->ev_init)); CK(cudaEventCreate(&S->ev_loop));
   pt.mark("init_passes");
   pt.dump("create");

@@ -438,7 +438,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
           if ((++spins & 0x3fffu) == 0u) {
             const long long now = gtimer();
             if (!t0w) t0w = now;
-            else if (now - t0w > SQC_WAIT_BUDGET_NS || *mb.status == SQC_D_TIMEOUT) { atomicCAS(&(*mb.status), 0, SQC_D_TIMEOUT); sh_flag[3] = 1; break; }
+            else if (now - t0w > mb.xc.budget_ns || *mb.status == SQC_D_TIMEOUT) { atomicCAS(&(*mb.status), 0, SQC_D_TIMEOUT); sh_flag[3] = 1; break; }
           }
         }
         __threadfence();
@@ -1084,7 +1084,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
       else if ((++idle & 0x3fffu) == 0u) {                          // watchdog, same budget as the leaders': a leader died
         const long long now = gtimer();
         if (!t_idle) t_idle = now;
-        else if (now - t_idle > SQC_WAIT_BUDGET_NS + 5000000000ll) { if (tid == 0) atomicCAS(&(*mb.status), 0, SQC_D_TIMEOUT); break; }
+        else if (now - t_idle > mb.xc.budget_ns + 5000000000ll) { if (tid == 0) atomicCAS(&(*mb.status), 0, SQC_D_TIMEOUT); break; }
       }
     }
   }

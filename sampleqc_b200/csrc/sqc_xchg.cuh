@@ -39,6 +39,7 @@ struct XchgDev {
   unsigned char* peer[XCHG_MAX_WORLD];               // window base of every rank (own window: local pointer)
   unsigned long long* next_seq;                      // XCHG_CHANNELS counters in LOCAL memory (same value on all ranks)
   int* status;                                       // the session's device status word: a wait that runs out of its budget says so here
+  long long budget_ns;                               // time budget of every in-kernel wait (SQC_WAIT_BUDGET_NS; SQC_WAIT_BUDGET_MS in the environment overrides)
 };
 
 // slot of `src`'s message of exchange `seq` on channel `ch`, inside the window at `base`
@@ -78,13 +79,13 @@ __device__ __forceinline__ ulonglong2 xchg_wait(const XchgDev& x, int ch, unsign
   ulonglong2 v = ld_line(p);
   unsigned int spins = 0; long long t0 = 0;
   while (!line_ready(v, (unsigned int)seq)) {
-    if (++spins > (1u << 16)) {
-      __nanosleep(1000);
-      if ((spins & 0x3ffu) == 0u) {
-        if (*(volatile int*)x.status == SQC_D_TIMEOUT) break;
+    if ((++spins & 0xffu) == 0u) {
+      if (*(volatile int*)x.status == SQC_D_TIMEOUT) break;      // somebody has given up already: every wait returns at once
+      if (spins > (1u << 16)) {
+        __nanosleep(1000);
         const long long now = gtimer();
         if (!t0) t0 = now;
-        else if (now - t0 > SQC_WAIT_BUDGET_NS) { atomicCAS(x.status, 0, SQC_D_TIMEOUT); break; }
+        else if (now - t0 > x.budget_ns) { atomicCAS(x.status, 0, SQC_D_TIMEOUT); break; }
       }
     }
     v = ld_line(p);
@@ -201,7 +202,7 @@ struct IpcCache {
     cudaIpcMemHandle_t h; memcpy(&h, handle64, sizeof h);
     void* p = nullptr;
     cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
-    if (e != cudaSuccess) throw std::runtime_error(std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(e));
+    if (e != cudaSuccess) { cudaGetLastError(); throw std::runtime_error(std::string("cudaIpcOpenMemHandle failed: ") + cudaGetErrorString(e)); }
     m.emplace(key, p);
     return p;
   }

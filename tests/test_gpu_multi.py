@@ -79,3 +79,15 @@ def test_one_call_n_gpus_failure_is_agreed(oracle):
     with pytest.raises(SampleQCError) as e:
         api.fit_sampleqc_robust_cpp(sim.x, iz, bad, D, J, K, N, 5, 0.5, 50, 0, n_gpus=2)
     assert e.value.status == 1
+
+
+def test_missing_peer_times_out_without_a_trap():
+    """a rank whose peer never runs gives up with SQC_ERR_COMM after the wait budget; its CUDA context survives"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29534", os.path.join(ROOT, "scripts", "mgpu_timeout_check.py")]
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "MGPU TIMEOUT CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
