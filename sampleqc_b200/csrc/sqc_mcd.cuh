@@ -858,6 +858,20 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
                   if (sh_pD1[hi] * 2.0 * w <= SQC_MCD_DIRECT_CAP * cap_scale && w < wband && w < 0.2) { wband = w; tband = c1; }
                 }
               }
+              //  (c) while the labels still move from call to call the thresholds shift as a whole, but their STEP from one
+              //      C-step index to the next repeats: this call's last threshold times the ratio the previous call showed
+              //      between the same two indices (only where that ratio is close to 1: the settled tail and the final q-pass).
+              if (SQC_MCD_PREDICT && cl.t_prev && cl.iters >= 1) {
+                const int hi = go_final ? MCD_HMAX : (cl.iters < MCD_HMAX ? cl.iters : -1), lo = cl.iters - 1;
+                if (hi >= 0 && lo < MCD_HMAX && sh_pT1[hi] && sh_pT1[lo]) {
+                  const double ratio = __longlong_as_double((long long)sh_pT1[hi]) / __longlong_as_double((long long)sh_pT1[lo]);
+                  const double w = 0.5 * fabs(ratio - 1.0) + 3.0 / sqrt((double)cl.n) + 2e-4;
+                  const double dens_c = sh_pD1[hi] > 0.0 ? sh_pD1[hi] : cl.dens;
+                  if (fabs(ratio - 1.0) < 0.01 && dens_c * 2.0 * w <= SQC_MCD_DIRECT_CAP * cap_scale && w < wband) {
+                    wband = w; tband = __longlong_as_double((long long)cl.t_prev) * ratio;
+                  }
+                }
+              }
               if (wband < 1e300 && SQC_MCD_DIRECT) {
                 const double t = tband;
                 cl.band_c = t; cl.band_w = wband;

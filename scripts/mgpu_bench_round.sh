@@ -1,5 +1,5 @@
 #!/bin/bash
-# r2 visit M (N GPUs): sharded parity (process per GPU), bench --gpus N with the default flags (strong + weak extra, MLE, C5 at N = 8)
+# N GPUs: sharded parity (process per GPU), bench --gpus N with the default flags (strong + weak extra, MLE, C5 at N = 8)
 TAG=${1:-r2q}; NG=${2:-8}
 mkdir -p gpurun_out
 nvidia-smi -L | wc -l

@@ -1,5 +1,5 @@
 #!/bin/bash
-# r2 visit R (2 GPUs): the whole GPU suite on a 2-GPU box (multi tests run), timeout check, default 2-GPU bench
+# 2 GPUs: the whole GPU suite on a 2-GPU box (multi tests run), timeout check, default 2-GPU bench
 TAG=${1:-r2x}
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_${TAG}_2gpu.log 2>&1; tail -6 gpurun_out/pytest_gpu_${TAG}_2gpu.log | cut -c1-300

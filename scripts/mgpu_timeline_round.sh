@@ -1,5 +1,5 @@
 #!/bin/bash
-# r2 visit Q (2 GPUs): robust-only timeline after the key-stream share / fence changes; parity
+# 2 GPUs: robust-only timeline after the key-stream share / fence changes; parity
 TAG=${1:-r2u}
 mkdir -p gpurun_out
 SQC_TIMELINE=gpurun_out/tl_${TAG}_w2 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29581 bench.py --gpus 2 --steps 3 --warmup 3 --no-extra --no-e2e > gpurun_out/bench_${TAG}_w2.json 2> gpurun_out/bench_${TAG}_w2.err; tail -2 gpurun_out/bench_${TAG}_w2.err
