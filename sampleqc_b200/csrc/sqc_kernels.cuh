@@ -253,14 +253,16 @@ __global__ void __launch_bounds__(EST_THREADS, (D <= 4) ? SQC_EST_MINB : 2) k_es
   const int j = s.tile_sample[t], start = s.tile_start[t], len = s.tile_len[t];
   // the cell loads go out first; the constants are copied while they are in flight
   double xp[CPT][D]; int zo[CPT]; bool valid[CPT];
+  {
+    const double* xb = s.x + (long long)start + tid;         // one base per thread: the cell slots and columns are constant offsets
+    const uint8_t* zb = s.z + (long long)start + tid;
 #pragma unroll
-  for (int c = 0; c < CPT; ++c) {
-    const int i = c * EST_THREADS + tid;
-    valid[c] = i < len;
-    const long long gi = (long long)start + (valid[c] ? i : 0);
+    for (int c = 0; c < CPT; ++c) {
+      valid[c] = c * EST_THREADS + tid < len;
 #pragma unroll
-    for (int d = 0; d < D; ++d) xp[c][d] = ld_stream(s.x + (long long)d * s.N + gi);
-    zo[c] = (int)ld_stream_u8(s.z + gi);
+      for (int d = 0; d < D; ++d) xp[c][d] = valid[c] ? ld_stream(xb + (long long)d * s.N + c * EST_THREADS) : 0.0;
+      zo[c] = valid[c] ? (int)ld_stream_u8(zb + c * EST_THREADS) : 0;
+    }
   }
   const bool slow_tile = s.dens_slow[j] != 0;
   if (tid < 2) sh_flag[tid] = 0;
@@ -448,14 +450,16 @@ __global__ void __launch_bounds__(EST_THREADS, (D <= 4) ? SQC_PART_MINB : 3) k_p
   if (t == 0 && tid < 2 * SQC_MAXK + 1) s.mcd_sync[tid] = 0u;      // epochs, arrivals and status word of the k_mcd launch that follows
   const int j = s.tile_sample[t], start = s.tile_start[t], len = s.tile_len[t];
   double xp[CPT][D]; int zo[CPT]; bool valid[CPT];
+  {
+    const double* xb = s.x + (long long)start + tid;
+    const uint8_t* zb = s.z + (long long)start + tid;
 #pragma unroll
-  for (int c = 0; c < CPT; ++c) {
-    const int i = c * EST_THREADS + tid;
-    valid[c] = i < len;
-    const long long gi = (long long)start + (valid[c] ? i : 0);
+    for (int c = 0; c < CPT; ++c) {
+      valid[c] = c * EST_THREADS + tid < len;
 #pragma unroll
-    for (int d = 0; d < D; ++d) xp[c][d] = ld_stream(s.x + (long long)d * s.N + gi);
-    zo[c] = valid[c] ? (int)ld_stream_u8(s.z + gi) : -1;
+      for (int d = 0; d < D; ++d) xp[c][d] = valid[c] ? ld_stream(xb + (long long)d * s.N + c * EST_THREADS) : 0.0;
+      zo[c] = valid[c] ? (int)ld_stream_u8(zb + c * EST_THREADS) : -1;
+    }
   }
   stage_dens<D>(s, j, cons, tab, aj, LIKE != 0);
   // per (iteration c, warp, component) counts -> exclusive prefix in tile order (c, warp, lane)

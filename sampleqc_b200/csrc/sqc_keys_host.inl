@@ -11,7 +11,7 @@ KeyBufLocal& key_buf_local(int device) { static KeyBufLocal b[64]; return b[devi
 
 void key_stream_setup(sqc_session* S) {
   const int W = S->world, r = S->rank;
-  if (!mtpoly::self_check()) fail(SQC_ERR_COMM, "distributed key stream: jump polynomial derivation failed its self-check");
+  { static std::mutex mu; std::lock_guard<std::mutex> lk(mu); if (!mtpoly::self_check()) fail(SQC_ERR_COMM, "distributed key stream: jump polynomial derivation failed its self-check"); }
   const long long per = (S->N_total + W - 1) / W;
   S->key_q = ((per + MT_N - 1) / MT_N) * MT_N;
   S->key_mine = std::max<long long>(0, std::min<long long>(S->key_q, S->N_total - (long long)r * S->key_q));
@@ -52,7 +52,9 @@ void key_stream_setup(sqc_session* S) {
   }
   // jump polynomials: row 0 = call to call (floor(N_total / 624) chunks), row 1 = start of the call to this rank's share
   static std::map<unsigned long long, std::vector<uint32_t>> rows;      // derived once per distance
+  static std::mutex rows_mu;                                            // (the ranks of an in-process fit are threads)
   auto row = [&](unsigned long long words) -> const std::vector<uint32_t>& {
+    std::lock_guard<std::mutex> lk(rows_mu);
     auto it = rows.find(words);
     if (it == rows.end()) { std::vector<uint32_t> v(MT_N); mtpoly::xpow(words - 1ull, v.data()); it = rows.emplace(words, std::move(v)).first; }
     return it->second;
