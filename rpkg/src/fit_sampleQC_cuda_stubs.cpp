@@ -186,3 +186,39 @@ List init_clusts_cuda(arma::mat x, arma::uvec groups, int J, arma::vec pro, arma
   for (int i = 0; i < N; ++i) init_z[i] = z[i];                   // 0-based, as init_z = classification - 1 (:314)
   return List::create(Named("grp_medians") = medians, Named("init_gamma") = gamma, Named("init_z") = init_z);
 }
+
+// mmd_fn (reference src/mmd_fn.cpp:20-91): same signature, same errors; the three kernel sums run on the device.
+// Replaces src/mmd_fn.cpp in the package (optional: the reference file stays valid).
+// [[Rcpp::export]]
+double mmd_fn(arma::mat X, arma::mat Y, double sigma) {
+  if (sigma <= 0) throw std::invalid_argument("sigma must be > 0");                            // :28-30
+  if (X.n_cols != Y.n_cols) throw std::invalid_argument("X and Y must have same number of columns");   // :31-33
+  double mmd = 0.0;
+  char err[512];
+  check_status(sqc_mmd_fn(X.memptr(), X.n_rows, Y.memptr(), Y.n_rows, (int)X.n_cols, sigma, &mmd, -1, err, sizeof err), err);
+  return mmd;
+}
+
+// .calc_mmd_mat's pair loop (reference R/calc_pairwise_mmds.R:216-233) in ONE device call: mat_list as in R (one
+// matrix per sample), pairs (i < j, 1-based as ij_grid holds them), and the row picks .dist_fn's sample() draws
+// (:271-277) pre-drawn by the R caller in the loop's order — idx_i / idx_j: n_pairs * n_times * subsample, 1-based,
+// ignored for samples with <= subsample rows.  Returns mean(abs(mmd)) per pair (:231, :279).
+// [[Rcpp::export]]
+NumericVector calc_mmd_pairs_cuda(List mat_list, IntegerVector pair_i, IntegerVector pair_j, int n_times, int subsample,
+                                  IntegerVector idx_i, IntegerVector idx_j, double sigma) {
+  const int S = mat_list.size(); const R_xlen_t P = pair_i.size();
+  std::vector<int64_t> rows(S); std::vector<double> flat; int D = 0;
+  for (int s = 0; s < S; ++s) { NumericMatrix m = mat_list[s]; rows[s] = m.nrow(); D = m.ncol(); flat.insert(flat.end(), m.begin(), m.end()); }
+  std::vector<int32_t> pi(P), pj(P), ii(idx_i.size()), ij(idx_j.size());
+  for (R_xlen_t p = 0; p < P; ++p) { pi[p] = pair_i[p] - 1; pj[p] = pair_j[p] - 1; }
+  for (R_xlen_t e = 0; e < idx_i.size(); ++e) ii[e] = idx_i[e] - 1;
+  for (R_xlen_t e = 0; e < idx_j.size(); ++e) ij[e] = idx_j[e] - 1;
+  sqc_mmd_args a = {};
+  a.abi_version = SQC_ABI_VERSION; a.D = D; a.n_samples = S; a.mats = flat.data(); a.mat_rows = rows.data();
+  a.n_pairs = P; a.pair_i = pi.data(); a.pair_j = pj.data(); a.n_times = n_times; a.subsample = subsample;
+  a.idx_i = ii.empty() ? nullptr : ii.data(); a.idx_j = ij.empty() ? nullptr : ij.data(); a.sigma = sigma; a.device = -1;
+  NumericVector mean(P);
+  char err[512];
+  check_status(sqc_mmd_pairs(&a, mean.begin(), nullptr, err, sizeof err), err);
+  return mean;
+}
