@@ -91,3 +91,24 @@ def test_missing_peer_times_out_without_a_trap():
     out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "MGPU TIMEOUT CHECK OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_one_call_n_gpus_small_and_degenerate_inputs(oracle):
+    """n_gpus > 1 on inputs the sharding has to adapt to: a single sample (one shard: the single-GPU path), fewer samples
+    than GPUs, and a data set so small that the key stream is replicated instead of shared out"""
+    import numpy as np
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from sampleqc_b200 import api
+    from sampleqc_b200.simulate import init_clusts, simulate_qcs
+    for N, J, K in ((20_000, 1, 2), (3_000, 2, 2), (9_000, 3, 3)):
+        sim = simulate_qcs(N, J, K, 3, seed=31 + J)
+        iz, _ = init_clusts(sim.x, sim.groups, J, K, seed=31 + J)
+        ref = oracle.fit_sampleqc_robust_cpp(sim.x, iz, sim.groups, 3, J, K, N, 6, 0.5, 50, 0)
+        got = api.fit_sampleqc_robust_cpp(sim.x, iz, sim.groups, 3, J, K, N, 6, 0.5, 50, 0, n_gpus=-1)      # SQC_ALL_GPUS
+        assert got["n_iter"] == ref["n_iter"]
+        for key in ("mu_0", "alpha_j", "beta_k", "sigma_k", "p_jk"):
+            np.testing.assert_allclose(got[key], ref[key], rtol=1e-8, atol=1e-8 * np.max(np.abs(ref[key])), err_msg=f"{key} N={N} J={J}")
+        np.testing.assert_array_equal(got["z"], ref["z"])
+        np.testing.assert_array_equal(got["rng_state"], ref["rng_state"])
