@@ -101,7 +101,8 @@ typedef struct sqc_fit_args {
    * cells by sample over GPUs 0 .. n-1 of this process (one host thread per GPU, peer access instead of IPC handles);
    * SQC_ALL_GPUS: every visible GPU (at most 8).  Fewer GPUs are used when there are fewer samples than GPUs; a data
    * set whose samples are interleaved cell by cell is fitted on one GPU.  Results are those of the one-GPU fit
-   * (sharded fit == oracle, tests/test_gpu_multi.py).                                                       */
+   * (sharded fit == oracle, tests/test_gpu_multi.py).  Calls with n_gpus > 1 from different host threads take
+   * turns (a GPU has one exchange window per process); single-GPU calls run concurrently.                    */
   int32_t  n_gpus;
 } sqc_fit_args;
 #define SQC_ALL_GPUS (-1)

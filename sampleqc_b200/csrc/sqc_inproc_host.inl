@@ -74,13 +74,16 @@ int fit_inproc(const sqc_fit_args* a, sqc_fit_out* o, int variant, int n_req, ch
   if (st0 != SQC_OK) return st0;
   if (sh.size() < 2) return -1000;                                   // one shard / interleaved samples: the caller takes the single-GPU path
   const int W = (int)sh.size(), D = a->D, K = a->K, J = a->J, em = std::max(a->em_iters, 0); const long long N = a->N;
+  static std::mutex inproc_mu;                                       // the exchange window of a GPU is one per process:
+  std::lock_guard<std::mutex> one_fit(inproc_mu);                    // multi-GPU fits of different host threads take turns
   InprocGroup grp; grp.world = W;
   for (int q = 0; q < W; ++q) grp.device[q] = q;
   struct RankOut { std::vector<double> alpha, p_jk, gamma, tr_alpha, tr_p; sqc_fit_out o{}; int code = SQC_OK; std::string msg; };
   std::vector<RankOut> ro(W);
   std::vector<std::thread> th;
+  th.reserve(W);
   for (int q = 0; q < W; ++q) {
-    th.emplace_back([&, q] {
+    try { th.emplace_back([&, q] {
       RankOut& R = ro[q]; const InprocShard& s = sh[q];
       const int Jl = (int)s.codes.size(); const long long Nl = s.i1 - s.i0;
       sqc_fit_args b = *a;
@@ -113,7 +116,11 @@ int fit_inproc(const sqc_fit_args* a, sqc_fit_out* o, int variant, int n_req, ch
       }, e2, sizeof e2);
       if (R.code != SQC_OK) { grp.abort(); R.msg = e2; }
       delete S;
-    });
+    }); }
+    catch (const std::exception& e) {                               // no thread for this rank: the others give up at their next sync
+      grp.abort(); ro[q].code = SQC_ERR_CUDA; ro[q].msg = std::string("could not start a host thread: ") + e.what();
+      break;
+    }
   }
   for (auto& t : th) t.join();
   for (int q = 0; q < W; ++q) if (ro[q].code != SQC_OK && (first_code == SQC_OK || first_code == SQC_ERR_COMM)) { first_code = ro[q].code; first_err = ro[q].msg; }

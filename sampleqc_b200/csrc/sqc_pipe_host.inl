@@ -9,12 +9,12 @@ struct sqc_resident {
   int device = 0, D = 0, J = 0; long long N = 0;
   double* x = nullptr; int* groups = nullptr;                 // device: raw x (N x D column-major), sample index per cell
   double* med = nullptr; bool have_med = false;               // device: J x D medians
-  int* z = nullptr; double* gamma = nullptr; int K_cls = 0, K_gam = 0;   // device: classification of all cells under the caller's mixture
+  int* z = nullptr; double* gamma = nullptr; int K_cls = 0, K_gam = 0, K_gcls = 0;   // device: classification of all cells under the caller's mixture (K_gcls: K the resident gamma belongs to, 0 = none)
   std::vector<int32_t> h_groups; std::vector<long long> bounds;   // bounds[j + 1] = cells of sample j
   std::vector<int> run_order;                                 // sample codes in order of appearance
   bool runs_ok = true;                                        // every sample is one contiguous run of cells
   // parameters of the last fit, re-centred (host): what .calc_outliers_dt receives
-  int K_fit = 0; std::vector<double> mu0, alpha, beta, sigma;
+  int K_fit = 0; bool recentred = false; std::vector<double> mu0, alpha, beta, sigma;
   cudaStream_t st = nullptr;
   std::vector<Chunk> chunks;                                  // from the per-device arena the fits use (cudaMalloc of 100s of MB costs tens of ms)
   void* take(size_t bytes) { chunks.push_back(g_chunks.take(device, std::max<size_t>(bytes, 256))); return chunks.back().base; }
@@ -148,7 +148,7 @@ int sqc_resident_init_clusts(sqc_resident* R, const double* pro, const double* m
         CK(cudaStreamSynchronize(R->st));
       } catch (...) { cudaFree(dpar); throw; }
       cudaFree(dpar);
-      R->K_cls = K;
+      R->K_cls = K; R->K_gcls = want_gamma ? K : 0;
     }
     CK(cudaStreamSynchronize(R->st));
   }, err, errlen);
@@ -191,7 +191,7 @@ int sqc_resident_fit(sqc_resident* R, const sqc_fit_args* args, int variant, int
       a.init_z = R->z;                                            // device pointer: copied device to device
     }
     if (variant == SQC_VARIANT_MLE && !a.init_gamma) {
-      if (!R->gamma || R->K_cls != a.K) fail(SQC_ERR_BAD_ARG, "no resident responsibilities with K = %d: call sqc_resident_init_clusts with keep_gamma", a.K);
+      if (!R->gamma || R->K_gcls != a.K) fail(SQC_ERR_BAD_ARG, "no resident responsibilities with K = %d: call sqc_resident_init_clusts with keep_gamma", a.K);
       a.init_gamma = R->gamma;
     }
     S = session_create(&a, variant);                            // x: device-to-device, the session centres its own copy
@@ -209,7 +209,7 @@ int sqc_resident_fit(sqc_resident* R, const sqc_fit_args* args, int variant, int
         for (int k = 0; k < K; ++k) o->beta_k[k + (size_t)K * d] -= bm;
       }
     }
-    R->K_fit = K;
+    R->K_fit = K; R->recentred = recentre != 0;
     R->mu0.assign(o->mu_0, o->mu_0 + D); R->alpha.assign(o->alpha_j, o->alpha_j + (size_t)J * D);
     R->beta.assign(o->beta_k, o->beta_k + (size_t)K * D); R->sigma.assign(o->sigma_k, o->sigma_k + (size_t)K * D * D);
   }, err, errlen);
@@ -222,6 +222,7 @@ int sqc_resident_fit(sqc_resident* R, const sqc_fit_args* args, int variant, int
 int sqc_resident_outliers(sqc_resident* R, double alpha, double* maha, uint8_t* outlier, double* maha_cut, char* err, size_t errlen) {
   return guarded([&] {
     if (!R || R->K_fit < 1) fail(SQC_ERR_BAD_ARG, "no fit on this handle yet");
+    if (!R->recentred) fail(SQC_ERR_BAD_ARG, "the last fit on this handle was not re-centred (recentre = 0): its parameters do not apply to the raw x");
     CK(cudaSetDevice(R->device));
     const int D = R->D, J = R->J, K = R->K_fit; const long long N = R->N;
     std::vector<double> ainv((size_t)K * D * D);
@@ -243,6 +244,7 @@ int sqc_resident_outliers(sqc_resident* R, double alpha, double* maha, uint8_t* 
       CK(cudaMemcpyAsync(dpar, hp.data(), npar * sizeof(double), cudaMemcpyHostToDevice, R->st));
       double* pm = dpar; double* pa = pm + D; double* pb = pa + (size_t)J * D; double* pi = pb + (size_t)K * D; double* pq = pi + (size_t)K * D * D;
       k_qchisq<<<1, 32, 0, R->st>>>(pq, pq + 1, pq + 2, 1);
+      CK(cudaGetLastError());
       double cut = 0.0;
       CK(cudaMemcpyAsync(&cut, pq + 2, sizeof(double), cudaMemcpyDeviceToHost, R->st));
       CK(cudaStreamSynchronize(R->st));

@@ -124,3 +124,39 @@ def test_subset_size_errors_match(oracle):
         with pytest.raises(SampleQCError) as e:              # h = int((n + D + 1) * 0) = 0: empty subset
             fn(x, z, g, 3, 2, 2, N, 3, 0.0, 10, 0)
         assert e.value.status == 3
+
+
+def test_concurrent_single_gpu_fits_from_two_host_threads():
+    """two host threads fitting different data on the same GPU at the same time get the results of the same calls made
+    one after the other (per-session device state; the arena and the polynomial cache are the only shared objects)"""
+    import threading
+    from sampleqc_b200 import api
+    from sampleqc_b200.simulate import init_clusts, simulate_qcs
+    jobs = []
+    for seed, (N, J, K) in enumerate(((150_000, 12, 3), (90_000, 7, 2))):
+        sim = simulate_qcs(N, J, K, 3, seed=70 + seed)
+        iz, ig = init_clusts(sim.x, sim.groups, J, K, seed=70 + seed)
+        jobs.append((sim, iz, ig, N, J, K))
+
+    def run(job, variant):
+        sim, iz, ig, N, J, K = job
+        if variant == "robust":
+            return api.fit_sampleqc_robust_cpp(sim.x, iz, sim.groups, 3, J, K, N, 8, 0.5, 50, 0)
+        return api.fit_sampleqc_mle_cpp(sim.x, ig, sim.groups, 3, J, K, N, 5, 0)
+
+    plan = [(jobs[0], "robust"), (jobs[1], "robust"), (jobs[0], "mle")]
+    alone = [run(j, v) for j, v in plan]
+    for _ in range(3):
+        res, errs = [None] * len(plan), []
+        def work(i):
+            try:
+                res[i] = run(*plan[i])
+            except Exception as e:                                # noqa: BLE001 - reported below
+                errs.append(e)
+        th = [threading.Thread(target=work, args=(i,)) for i in range(len(plan))]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        assert not errs, errs
+        for a, b in zip(alone, res):
+            for key in ("mu_0", "alpha_j", "beta_k", "sigma_k", "p_jk", "z"):
+                np.testing.assert_array_equal(a[key], b[key], err_msg=key)

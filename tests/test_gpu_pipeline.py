@@ -68,3 +68,35 @@ def test_resident_rejects_interleaved_samples():
     with pytest.raises(SampleQCError) as e:
         api.Resident(x, g, 2)
     assert e.value.status == 1
+
+
+def test_resident_refuses_steps_whose_inputs_are_not_on_the_handle():
+    """outliers after a fit that was not re-centred, an MLE fit after a classification that kept no responsibilities,
+    a robust fit with a K the resident labels were not made for: errors, not stale device buffers"""
+    from sampleqc_b200 import api
+    from sampleqc_b200._abi import SampleQCError
+    from sampleqc_b200.simulate import simulate_qcs
+    N, J, K, D = 40_000, 6, 2, 3
+    sim = simulate_qcs(N, J, 2, D, seed=4)
+    with api.Resident(sim.x, sim.groups, J) as R:
+        idx, fit = _mixture(sim.x, sim.groups, J, K, 4)
+        gm = fit(R.subsample(idx))
+        with pytest.raises(SampleQCError):                        # no fit yet
+            R.outliers(want_maha=False)
+        sigma = np.ascontiguousarray(np.transpose(gm.covariances_, (1, 2, 0)))          # D x D x K, as mclust returns it
+        R.classify(gm.weights_, gm.means_, sigma, keep_gamma=True)
+        R.fit_mle(K, 3, 0)
+        R.classify(gm.weights_, gm.means_, sigma, keep_gamma=False)
+        with pytest.raises(SampleQCError) as e:
+            R.fit_mle(K, 3, 0)                                    # the responsibilities of the first classification are not offered again
+        assert e.value.status == 1
+        with pytest.raises(SampleQCError) as e:
+            R.fit_robust(K + 1, 3, 0.5, 20, 0)                    # labels are for K components
+        assert e.value.status == 1
+        R.fit_robust(K, 3, 0.5, 20, 0, recentre=False)
+        with pytest.raises(SampleQCError) as e:
+            R.outliers(want_maha=False)
+        assert e.value.status == 1
+        R.fit_robust(K, 3, 0.5, 20, 0)
+        _, flags, cut = R.outliers(want_maha=False)
+        assert flags.shape == (N,) and cut > 0
