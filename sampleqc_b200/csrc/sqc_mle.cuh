@@ -23,90 +23,156 @@ enum { MLE_INIT = 0, MLE_A = 1, MLE_B = 2, MLE_LIKE = 3 };
 struct MleBufs {
   const double* gamma0 = nullptr;   // N x K column-major, the caller's init_gamma_i
   double* gamma = nullptr;          // N x K column-major, returned gamma_i
-  double* t_mom = nullptr;          // T x K x NMOM(D) per-tile partials (pass A uses the first 1 + D of each)
+  double* t_mom = nullptr;          // K x NMOM(D) x T per-tile partials, tile-minor (pass A uses the first 1 + D of each component)
   double* t_ll = nullptr;           // T per-tile log-likelihood partials
   double* mom = nullptr;            // K x NMOM(D) reduced moments
   double* g_jk = nullptr;           // J x K: sum of gamma per (sample, component)
   double* x_jk = nullptr;           // J x K x D
   double* p_k = nullptr;            // K
   double* coef = nullptr;           // K: p_k * normaliser
-  int* iter = nullptr;              // device iteration counter / flags: [0] = iteration, [1] = status
+  int* iter = nullptr;              // device iteration counter / flags: [0] = iteration, [1] = status, [2] = weights outside the fast densities' range
   int last_store = 0;               // pass B: store gamma / argmax (host sets it for the last iteration)
 };
 
-template <int D> struct MlePar { static constexpr int SZ = D + SQC_TRI(D) + 1; };
+// warp totals of NM per-lane values, stored to dst[0 .. NM): recursive halving in groups of <= 16 values
+template <int NM, int G0 = 0>
+__device__ __forceinline__ void warp_sum_store(const double (&acc)[NM], int lane, double* dst) {
+  if constexpr (G0 < NM) {
+    constexpr int n = (NM - G0 < 16) ? NM - G0 : 16;
+    constexpr int NP = n <= 1 ? 1 : n <= 2 ? 2 : n <= 4 ? 4 : n <= 8 ? 8 : 16;
+    double v[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) v[i] = (i < n) ? acc[G0 + (i < n ? i : 0)] : 0.0;
+    warp_sum_vec<NP>(v, lane);
+    constexpr int STR = 32 / NP;
+    if ((lane & (STR - 1)) == 0 && lane / STR < n) dst[G0 + lane / STR] = v[0];
+    warp_sum_store<NM, G0 + 16>(acc, lane, dst);
+  }
+}
+
+// the reference's arithmetic for one cell (mean formed first, general exp with gradual underflow): the slow path of the
+// densities, for cells whose likelihood is not safely inside the normal range and for weights outside the range the fast
+// path's exponent arithmetic is safe for.  Plain pointers (see dens_slow).  dcell != NULL: the K densities go to
+// dcell[k * dstride].
+template <int D> __device__ __noinline__ double mle_dens_slow(const double* xcell, long long N, const double* aj, const double* beta, const double* linv,
+                                                              const double* coef, int K, double* dcell, int dstride) {
+  double x[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) x[d] = xcell[(long long)d * N];
+  double like = 0.0;
+  for (int k = 0; k < K; ++k) {
+    double v[D], lt[SQC_TRI(D)];
+#pragma unroll
+    for (int d = 0; d < D; ++d) v[d] = x[d] - (aj[d] + beta[k * D + d]);              // mu_ik = alpha_j + beta_k, :168-170
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+      for (int c = 0; c <= r; ++c) lt[r * (r + 1) / 2 + c] = linv[k * D * D + r + D * c];
+    const double dens = coef[k] * exp_neg(-0.5 * maha_tri<D>(v, lt));                 // p_k * dmvnorm(x, mu, Sigma), :171
+    like += dens;
+    if (dcell) dcell[k * dstride] = dens;
+  }
+  return like;
+}
 
 #ifndef SQC_MLE_MINB
 #define SQC_MLE_MINB 3
 #endif
+// One CTA per sample-aligned tile.  The densities use the E-step's arithmetic (sqc_kernels.cuh): affine whitening
+// y = L_k^-1 (x - alpha_j) - c_k, exp(-q/2) by table + degree-4 polynomial with the weight p_k (2 pi)^(-D/2) det^(-1/2)
+// folded into the table (constants derived once per M-step by k_mle_update), the reference's own arithmetic for the
+// cells the fast path is not safe for.  gamma = density / likelihood is one reciprocal per cell and a product per
+// component.  Per-component moment sums: registers -> recursive-halving warp sums -> one fixed-order sum over the
+// warps per tile (bit-reproducible), tile partials stored tile-minor so that the reductions read them contiguously.
 template <int D, int MODE>
 __global__ void __launch_bounds__(EST_THREADS, SQC_MLE_MINB) k_mle_pass(Dev s, MleBufs m) {
-  constexpr int CPT = TileCfg<D>::CPT, TILE = TileCfg<D>::TILE, SZ = MlePar<D>::SZ, NW = EST_THREADS / 32;
-  constexpr int NM = (MODE == MLE_A) ? (1 + D) : SQC_NMOM(D);
+  constexpr int CPT = TileCfg<D>::CPT, TILE = TileCfg<D>::TILE, SZ = DensK<D>::SZ, NW = EST_THREADS / 32;
+  constexpr int NM = (MODE == MLE_A) ? (1 + D) : SQC_NMOM(D), NMF = SQC_NMOM(D);
   extern __shared__ double sh_dyn[];
-  double* sh_par = sh_dyn;                                   // K * SZ
-  double* sh_red = sh_par + s.K * SZ;                        // NW * NM
-  double* sh_d = sh_red + NW * SQC_NMOM(D);                  // K * TILE densities (not for MLE_LIKE / MLE_INIT)
+  const int K = s.K;
+  double* cons = sh_dyn;                                     // K * SZ
+  double* tab = cons + K * SZ;                               // K * 32
+  double* sh_red = tab + K * 32;                             // NW * K * NM
+  double* sh_d = sh_red + NW * K * NMF;                      // K * TILE densities (MLE_A / MLE_B)
   __shared__ double sh_w[NW];
-  const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5, K = s.K;
+  const int t = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int j = s.tile_sample[t], start = s.tile_start[t], len = s.tile_len[t];
-  if (MODE != MLE_INIT) {
-    for (int idx = tid; idx < K * SZ; idx += EST_THREADS) {
-      const int k = idx / SZ, e = idx % SZ;
-      double v;
-      if (e < D) v = s.alpha[j * D + e] + s.beta[k * D + e];          // mu_ik = alpha_j + beta_k, :168-170
-      else if (e < D + SQC_TRI(D)) {
-        int tt = e - D, r = 0;
-        while ((r + 1) * (r + 2) / 2 <= tt) ++r;
-        v = s.linv[k * D * D + r + D * (tt - r * (r + 1) / 2)];
-      } else v = m.coef[k];
-      sh_par[idx] = v;
+  double xv[CPT][D]; bool valid[CPT];
+  {
+    const double* xb = s.x + (long long)start + tid;
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      valid[c] = c * EST_THREADS + tid < len;
+#pragma unroll
+      for (int d = 0; d < D; ++d) xv[c][d] = valid[c] ? ld_stream(xb + (long long)d * s.N + c * EST_THREADS) : 0.0;
     }
   }
-  double xv[CPT][D]; bool valid[CPT];
-#pragma unroll
-  for (int c = 0; c < CPT; ++c) {
-    const int i = c * EST_THREADS + tid;
-    valid[c] = i < len;
-    const long long gi = (long long)start + (valid[c] ? i : 0);
-#pragma unroll
-    for (int d = 0; d < D; ++d) xv[c][d] = ld_stream(s.x + (long long)d * s.N + gi);
-  }
-  __syncthreads();
-  double like[CPT];
-#pragma unroll
-  for (int c = 0; c < CPT; ++c) like[c] = 0.0;
+  bool slow_all = false;
   if (MODE != MLE_INIT) {
+    for (int idx = tid; idx < K * SZ; idx += EST_THREADS) cons[idx] = s.dens_cons[idx];
+    for (int idx = tid; idx < K * 32; idx += EST_THREADS) tab[idx] = s.dens_tab[(idx >> 5) * DENS_TAB + (idx & 31)];
+    slow_all = m.iter[2] != 0;
+  }
+  double aj[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) aj[d] = s.alpha[j * D + d];
+  __syncthreads();
+  // x - alpha_j: what the densities and the moments of pass B / INIT are computed from (pass A sums the raw x)
+  double xp[CPT][D];
+#pragma unroll
+  for (int c = 0; c < CPT; ++c)
+#pragma unroll
+    for (int d = 0; d < D; ++d) xp[c][d] = xv[c][d] - aj[d];
+  double rl[CPT];                                            // 1 / likelihood
+#pragma unroll
+  for (int c = 0; c < CPT; ++c) rl[c] = 1.0;
+  if (MODE != MLE_INIT) {
+    double like[CPT];
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) like[c] = 0.0;
     for (int k = 0; k < K; ++k) {
-      const double* pk = sh_par + k * SZ;
-      double mu[D], lt[SQC_TRI(D)];
-#pragma unroll
-      for (int d = 0; d < D; ++d) mu[d] = pk[d];
-#pragma unroll
-      for (int e = 0; e < SQC_TRI(D); ++e) lt[e] = pk[D + e];
-      const double coef = pk[D + SQC_TRI(D)];
+      const double* pk = cons + k * SZ;
+      const double* tk = tab + k * 32;
 #pragma unroll
       for (int c = 0; c < CPT; ++c) {
-        double v[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) v[d] = xv[c][d] - mu[d];
-        const double dens = coef * exp_neg(-0.5 * maha_tri<D>(v, lt));   // p_k * dmvnorm(x, mu, Sigma), :171
+        const double dens = dens_term(maha_affine<D>(xp[c], pk), tk, 0.0);           // p_k * dmvnorm(x, mu, Sigma), :171
         like[c] += dens;
         if (MODE != MLE_LIKE) sh_d[k * TILE + c * EST_THREADS + tid] = dens;
       }
+    }
+    bool suspect = slow_all; int slowmask = 0;
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) suspect = suspect || (valid[c] && !(like[c] >= DENS_SAFE));
+    if (suspect) {                                           // rare: one test per thread on the fast path
+#pragma unroll
+      for (int c = 0; c < CPT; ++c)
+        if (valid[c] && (slow_all || !(like[c] >= DENS_SAFE))) {
+          like[c] = mle_dens_slow<D>(s.x + (long long)start + c * EST_THREADS + tid, s.N, s.alpha + j * D, s.beta, s.linv, m.coef, K,
+                                     (MODE != MLE_LIKE) ? sh_d + c * EST_THREADS + tid : nullptr, TILE);
+          slowmask |= 1 << c;
+        }
     }
     // log-likelihood of the parameters used (calc_log_likelihood :191-222)
     double ll = sum_log<CPT>(like, valid);
     ll = warp_sum(ll);
     if (lane == 0) sh_w[w] = ll;
-    __syncthreads();
-    if (tid == 0) { double a = 0.0; for (int ww = 0; ww < NW; ++ww) a += sh_w[ww]; m.t_ll[t] = a; }
-    if (MODE == MLE_LIKE) return;
+    if (MODE == MLE_LIKE) {
+      __syncthreads();
+      if (tid == 0) { double a = 0.0; for (int ww = 0; ww < NW; ++ww) a += sh_w[ww]; m.t_ll[t] = a; }
+      return;
+    }
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) rl[c] = 1.0 / like[c];
+    if (slowmask) {                                          // those cells divide as the reference does (:181-183): 0 / 0 = NaN, subnormal likelihoods
+#pragma unroll
+      for (int c = 0; c < CPT; ++c)
+        if (slowmask & (1 << c)) {
+          for (int k = 0; k < K; ++k) sh_d[k * TILE + c * EST_THREADS + tid] = sh_d[k * TILE + c * EST_THREADS + tid] / like[c];
+          rl[c] = 1.0;
+        }
+    }
   }
   // per-component weighted sums over the tile
-  double aj[D];
-#pragma unroll
-  for (int d = 0; d < D; ++d) aj[d] = (MODE == MLE_A) ? 0.0 : s.alpha[j * D + d];
   double gbest[CPT]; int kbest[CPT];
 #pragma unroll
   for (int c = 0; c < CPT; ++c) { gbest[c] = -1.0; kbest[c] = -1; }
@@ -122,15 +188,15 @@ __global__ void __launch_bounds__(EST_THREADS, SQC_MLE_MINB) k_mle_pass(Dev s, M
       const long long gi = (long long)start + c * EST_THREADS + tid;
       double g;
       if (MODE == MLE_INIT) g = valid[c] ? ld_stream(m.gamma0 + (long long)k * s.N + gi) : 0.0;
-      else g = sh_d[k * TILE + c * EST_THREADS + tid] / like[c];               // :181-183
+      else g = sh_d[k * TILE + c * EST_THREADS + tid] * rl[c];                       // :181-183
       if (MODE == MLE_B && m.last_store && valid[c]) {
         m.gamma[(long long)k * s.N + gi] = g;
-        if (g > gbest[c]) { gbest[c] = g; kbest[c] = k; }                      // extract_z :234-238
+        if (g > gbest[c]) { gbest[c] = g; kbest[c] = k; }                            // extract_z :234-238
       }
       if (!valid[c]) g = 0.0;
       double wv[D];
 #pragma unroll
-      for (int d = 0; d < D; ++d) wv[d] = (xv[c][d] - aj[d]) - cs[d];
+      for (int d = 0; d < D; ++d) wv[d] = (MODE == MLE_A) ? xv[c][d] : xp[c][d] - cs[d];
       acc[0] += g;
 #pragma unroll
       for (int d = 0; d < D; ++d) acc[1 + d] = fma(g, wv[d], acc[1 + d]);
@@ -144,17 +210,17 @@ __global__ void __launch_bounds__(EST_THREADS, SQC_MLE_MINB) k_mle_pass(Dev s, M
         }
       }
     }
-#pragma unroll
-    for (int e = 0; e < NM; ++e) { const double a = warp_sum(acc[e]); if (lane == 0) sh_red[w * NM + e] = a; }
-    __syncthreads();
-    if (tid < NM) {
-      double a = 0.0;
-#pragma unroll
-      for (int ww = 0; ww < NW; ++ww) a += sh_red[ww * NM + tid];
-      m.t_mom[((long long)t * K + k) * SQC_NMOM(D) + tid] = a;
-    }
-    __syncthreads();
+    warp_sum_store<NM>(acc, lane, sh_red + (w * K + k) * NM);
   }
+  __syncthreads();
+  for (int idx = tid; idx < K * NM; idx += EST_THREADS) {
+    const int k = idx / NM, e = idx % NM;
+    double a = 0.0;
+#pragma unroll
+    for (int ww = 0; ww < NW; ++ww) a += sh_red[(ww * K + k) * NM + e];
+    m.t_mom[((size_t)k * NMF + e) * s.T + t] = a;
+  }
+  if (MODE != MLE_INIT && tid == 0) { double a = 0.0; for (int ww = 0; ww < NW; ++ww) a += sh_w[ww]; m.t_ll[t] = a; }
   if (MODE == MLE_B && m.last_store) {
 #pragma unroll
     for (int c = 0; c < CPT; ++c) if (valid[c]) {
@@ -176,7 +242,8 @@ __global__ void k_mle_sample(Dev s, MleBufs m) {
   for (int e = lane; e < K * (1 + D); e += 32) {
     const int k = e / (1 + D), c = e % (1 + D);
     double a = 0.0;
-    for (int t = t0; t < t1; ++t) a += m.t_mom[((long long)t * K + k) * NMF + c];
+    const double* src = m.t_mom + ((size_t)k * NMF + c) * s.T;
+    for (int t = t0; t < t1; ++t) a += src[t];
     if (c == 0) m.g_jk[j * K + k] = a; else m.x_jk[((long long)j * K + k) * D + (c - 1)] = a;
   }
   if (!WITH_ALPHA) return;
@@ -198,25 +265,18 @@ __global__ void k_mle_sample(Dev s, MleBufs m) {
   }
 }
 
-// fixed-order reduction over tiles: block k sums the NMOM moments of component k; block K sums the
-// log-likelihood partials into like[slot] (slot < 0: discard)
-__global__ void __launch_bounds__(1024) k_mle_reduce(Dev s, MleBufs m, double* like, int slot) {
-  __shared__ double sh[32];
-  const int K = s.K, NMF = SQC_NMOM(s.D);
-  if ((int)blockIdx.x == K) {
-    double a = 0.0;
-    for (int t = threadIdx.x; t < s.T; t += 1024) a += m.t_ll[t];
-    const double r = block_sum<1024>(a, sh);
-    if (threadIdx.x == 0 && slot >= 0) like[slot] = r;
-    return;
-  }
-  const int k = blockIdx.x;
-  for (int e = 0; e < NMF; ++e) {
-    double a = 0.0;
-    for (int t = threadIdx.x; t < s.T; t += 1024) a += m.t_mom[((long long)t * K + k) * NMF + e];
-    const double r = block_sum<1024>(a, sh);
-    if (threadIdx.x == 0) m.mom[k * NMF + e] = r;
-    __syncthreads();
+// fixed-order reduction over tiles: block b < K * NMOM sums moment b = k * NMOM + e (contiguous over the tiles); block
+// K * NMOM sums the log-likelihood partials into like[slot] (slot < 0: discard)
+__global__ void __launch_bounds__(256) k_mle_reduce(Dev s, MleBufs m, double* like, int slot) {
+  __shared__ double sh[8];
+  const int b = blockIdx.x, nm = s.K * SQC_NMOM(s.D);
+  const double* src = (b == nm) ? m.t_ll : m.t_mom + (size_t)b * s.T;
+  double a = 0.0;
+  for (int t = threadIdx.x; t < s.T; t += 256) a += src[t];
+  const double r = block_sum<256>(a, sh);
+  if (threadIdx.x == 0) {
+    if (b == nm) { if (slot >= 0) like[slot] = r; }
+    else m.mom[b] = r;
   }
 }
 
@@ -233,6 +293,8 @@ __global__ void k_mle_update(Dev s, MleBufs m, int derive_only) {
   const int D = s.D, K = s.K, NMF = SQC_NMOM(D);
   __shared__ double tot;
   if (threadIdx.x == 0) { double a = 0.0; for (int k = 0; k < K; ++k) a += m.mom[k * NMF]; tot = a; }
+  __syncthreads();
+  if (threadIdx.x == 0) m.iter[2] = 0;
   __syncthreads();
   const int k = threadIdx.x;
   if (k >= K) return;
@@ -257,7 +319,17 @@ __global__ void k_mle_update(Dev s, MleBufs m, int derive_only) {
   const double det = small_det(Sg, D);
   for (int e2 = 0; e2 < D * D; ++e2) { s.linv[k * D * D + e2] = Li[e2]; s.ainv[k * D * D + e2] = Ai[e2]; }
   s.Pk[k] = 1.0 / sqrt(pow(6.283185307179586476925286766559, (double)D) * det);
-  m.coef[k] = m.p_k[k] * s.Pk[k];
+  const double coef = m.p_k[k] * s.Pk[k];
+  m.coef[k] = coef;
+  // constants of the passes' fast densities (sqc_kernels.cuh): L^-1 packed, c = L^-1 beta, the weight folded into the exp table
+  double* ck = s.dens_cons + k * (SQC_TRI(D) + D);
+  for (int r = 0; r < D; ++r) {
+    double c = 0.0;
+    for (int cc = 0; cc <= r; ++cc) { const double l = Li[r + D * cc]; ck[r * (r + 1) / 2 + cc] = l; c = fma(l, s.beta[k * D + cc], c); }
+    ck[SQC_TRI(D) + r] = c;
+  }
+  for (int i = 0; i < 32; ++i) s.dens_tab[k * DENS_TAB + i] = coef * c_exp_tab[i];
+  if (!(coef > 1e-20 && coef < 1e20)) atomicOr(&m.iter[2], 1);     // outside the range the fast path's exponent arithmetic is safe for
 }
 
 // p_jk = G_jk / sum_k G_jk (extract_p_jk :248-273), stored where the robust path keeps p_jk
@@ -270,7 +342,7 @@ __global__ void k_mle_pjk(Dev s, MleBufs m) {
 }
 
 template <int D> size_t mle_smem(int K, int mode) {
-  size_t n = (size_t)K * MlePar<D>::SZ + (size_t)(EST_THREADS / 32) * SQC_NMOM(D);
+  size_t n = (size_t)K * DensK<D>::SZ + (size_t)K * 32 + (size_t)(EST_THREADS / 32) * K * SQC_NMOM(D);
   if (mode == MLE_A || mode == MLE_B) n += (size_t)K * TileCfg<D>::TILE;
   return n * sizeof(double);
 }

@@ -47,7 +47,7 @@ void mle_run(sqc_session* S) {
   auto reduce = [&](int ll_only, double* like, int slot) {
     Launch L(S, SQC_KF_UPDATE);
     if (ll_only) k_mle_reduce_ll<<<1, 1024, 0, S->st>>>(s, m, like, slot);
-    else k_mle_reduce<<<K + 1, 1024, 0, S->st>>>(s, m, like, slot);
+    else k_mle_reduce<<<K * SQC_NMOM(D) + 1, 256, 0, S->st>>>(s, m, like, slot);
     L.done();
     if (S->world > 1) xchg_allreduce_mle(S, s, m, ll_only, like, slot);
   };
