@@ -106,10 +106,8 @@ int fit_inproc(const sqc_fit_args* a, sqc_fit_out* o, int variant, int n_req, ch
       sqc_session* S = nullptr;
       char e2[512] = {0};
       R.code = guarded([&] {
-        bool made = false;
-        try { S = session_create(&b, variant, &grp, N); made = true; }
+        try { S = session_create(&b, variant, &grp, N); }
         catch (...) { grp.abort(); throw; }
-        (void)made;
         if (!grp.sync(true)) fail(SQC_ERR_COMM, "another GPU of the fit failed while the sessions were built");
         session_run(S);
         session_fetch(S, &lo);

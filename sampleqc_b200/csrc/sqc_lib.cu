@@ -511,7 +511,8 @@ void do_after_mstep(sqc_session* S, int with_p) {
 }
 #define SQC_CASE_MLE(DD) case DD: mle_launch_pass<DD>(S->dev, S->ml, which, S->st); break;
 void do_mle_pass(sqc_session* S, int which) {
-  Launch L(S, SQC_KF_MLE_PASS);
+  static const char* tags[] = {"pass_init", "pass_a", "pass_b", "pass_like"};
+  Launch L(S, SQC_KF_MLE_PASS, nullptr, tags[which & 3]);
   switch (S->D) { SQC_FOR_D(SQC_CASE_MLE) default: fail(SQC_ERR_BAD_ARG, "D = %d not compiled in", S->D); }
   L.done();
 }

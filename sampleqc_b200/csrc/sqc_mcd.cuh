@@ -294,11 +294,8 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
   __shared__ double sh_out[NM];
   __shared__ double sh_tr[MCD_TCACHE * D];      // residuals of the first tie candidates (leader)
   __shared__ unsigned short sh_tord[MCD_TINY];  // tie members in (key, rank, position) order
-  __shared__ long long sh_cstart[SQC_MAXK + 1];
   __shared__ long long sh_scan[33];
   __shared__ int sh_flag[6];
-  __shared__ int sh_ph[SQC_MAXK];
-  __shared__ long long sh_n[SQC_MAXK];
   __shared__ unsigned long long sh_u64[4];
   __shared__ unsigned long long sh_pT1[MCD_HMAX + 1], sh_pT2[MCD_HMAX + 1];   // leader: thresholds of the previous two calls by C-step index (0 = none)
   __shared__ double sh_pD1[MCD_HMAX + 1];

@@ -18,7 +18,7 @@
 
 namespace sqc {
 
-enum { MLE_INIT = 0, MLE_A = 1, MLE_B = 2, MLE_LIKE = 3 };
+enum { MLE_INIT = 0, MLE_A = 1, MLE_B = 2, MLE_LIKE = 3, MLE_B_LAST = 4 };   // MLE_B_LAST: pass B of the last iteration (stores gamma, argmax)
 
 struct MleBufs {
   const double* gamma0 = nullptr;   // N x K column-major, the caller's init_gamma_i
@@ -31,7 +31,7 @@ struct MleBufs {
   double* p_k = nullptr;            // K
   double* coef = nullptr;           // K: p_k * normaliser
   int* iter = nullptr;              // device iteration counter / flags: [0] = iteration, [1] = status, [2] = weights outside the fast densities' range
-  int last_store = 0;               // pass B: store gamma / argmax (host sets it for the last iteration)
+  int last_store = 0;               // pass B: store gamma / argmax (host sets it for the last iteration: MLE_B_LAST is launched)
 };
 
 // warp totals of NM per-lane values, stored to dst[0 .. NM): recursive halving in groups of <= 16 values
@@ -156,72 +156,77 @@ __global__ void __launch_bounds__(EST_THREADS, SQC_MLE_MINB) k_mle_pass(Dev s, M
     double ll = sum_log<CPT>(like, valid);
     ll = warp_sum(ll);
     if (lane == 0) sh_w[w] = ll;
-    if (MODE == MLE_LIKE) {
-      __syncthreads();
-      if (tid == 0) { double a = 0.0; for (int ww = 0; ww < NW; ++ww) a += sh_w[ww]; m.t_ll[t] = a; }
-      return;
-    }
+    if constexpr (MODE != MLE_LIKE) {
 #pragma unroll
-    for (int c = 0; c < CPT; ++c) rl[c] = 1.0 / like[c];
-    if (slowmask) {                                          // those cells divide as the reference does (:181-183): 0 / 0 = NaN, subnormal likelihoods
+      for (int c = 0; c < CPT; ++c) rl[c] = 1.0 / like[c];
+      if (slowmask) {                                        // those cells divide as the reference does (:181-183): 0 / 0 = NaN, subnormal likelihoods
 #pragma unroll
-      for (int c = 0; c < CPT; ++c)
-        if (slowmask & (1 << c)) {
-          for (int k = 0; k < K; ++k) sh_d[k * TILE + c * EST_THREADS + tid] = sh_d[k * TILE + c * EST_THREADS + tid] / like[c];
-          rl[c] = 1.0;
-        }
+        for (int c = 0; c < CPT; ++c)
+          if (slowmask & (1 << c)) {
+            for (int k = 0; k < K; ++k) sh_d[k * TILE + c * EST_THREADS + tid] = sh_d[k * TILE + c * EST_THREADS + tid] / like[c];
+            rl[c] = 1.0;
+          }
+      }
     }
   }
-  // per-component weighted sums over the tile
-  double gbest[CPT]; int kbest[CPT];
+  double gbest[MODE == MLE_B_LAST ? CPT : 1]; int kbest[MODE == MLE_B_LAST ? CPT : 1];
+  if constexpr (MODE != MLE_LIKE) {
+    // per-component weighted sums over the tile
+    if constexpr (MODE == MLE_B_LAST) {
 #pragma unroll
-  for (int c = 0; c < CPT; ++c) { gbest[c] = -1.0; kbest[c] = -1; }
-  for (int k = 0; k < K; ++k) {
-    double acc[NM];
+      for (int c = 0; c < CPT; ++c) { gbest[c] = -1.0; kbest[c] = -1; }
+    }
+    for (int k = 0; k < K; ++k) {
+      double acc[NM];
 #pragma unroll
-    for (int e = 0; e < NM; ++e) acc[e] = 0.0;
-    double cs[D];
+      for (int e = 0; e < NM; ++e) acc[e] = 0.0;
+      double cs[D];
 #pragma unroll
-    for (int d = 0; d < D; ++d) cs[d] = (MODE == MLE_A) ? 0.0 : s.beta[k * D + d];   // moment shift: current beta_k
+      for (int d = 0; d < D; ++d) cs[d] = (MODE == MLE_A) ? 0.0 : s.beta[k * D + d];   // moment shift: current beta_k
 #pragma unroll
-    for (int c = 0; c < CPT; ++c) {
-      const long long gi = (long long)start + c * EST_THREADS + tid;
-      double g;
-      if (MODE == MLE_INIT) g = valid[c] ? ld_stream(m.gamma0 + (long long)k * s.N + gi) : 0.0;
-      else g = sh_d[k * TILE + c * EST_THREADS + tid] * rl[c];                       // :181-183
-      if (MODE == MLE_B && m.last_store && valid[c]) {
-        m.gamma[(long long)k * s.N + gi] = g;
-        if (g > gbest[c]) { gbest[c] = g; kbest[c] = k; }                            // extract_z :234-238
-      }
-      if (!valid[c]) g = 0.0;
-      double wv[D];
+      for (int c = 0; c < CPT; ++c) {
+        const long long gi = (long long)start + c * EST_THREADS + tid;
+        double g;
+        if (MODE == MLE_INIT) g = valid[c] ? ld_stream(m.gamma0 + (long long)k * s.N + gi) : 0.0;
+        else g = sh_d[k * TILE + c * EST_THREADS + tid] * rl[c];                       // :181-183
+        if constexpr (MODE == MLE_B_LAST) {
+          if (valid[c]) {
+            m.gamma[(long long)k * s.N + gi] = g;
+            if (g > gbest[c]) { gbest[c] = g; kbest[c] = k; }                          // extract_z :234-238
+          }
+        }
+        if (!valid[c]) g = 0.0;
+        double wv[D];
 #pragma unroll
-      for (int d = 0; d < D; ++d) wv[d] = (MODE == MLE_A) ? xv[c][d] : xp[c][d] - cs[d];
-      acc[0] += g;
+        for (int d = 0; d < D; ++d) wv[d] = (MODE == MLE_A) ? xv[c][d] : xp[c][d] - cs[d];
+        acc[0] += g;
 #pragma unroll
-      for (int d = 0; d < D; ++d) acc[1 + d] = fma(g, wv[d], acc[1 + d]);
-      if (MODE != MLE_A) {
-        int e = 1 + D;
+        for (int d = 0; d < D; ++d) acc[1 + d] = fma(g, wv[d], acc[1 + d]);
+        if (MODE != MLE_A) {
+          int e = 1 + D;
 #pragma unroll
-        for (int a = 0; a < D; ++a) {
-          const double ga = g * wv[a];
+          for (int a = 0; a < D; ++a) {
+            const double ga = g * wv[a];
 #pragma unroll
-          for (int b = a; b < D; ++b) { acc[e] = fma(ga, wv[b], acc[e]); ++e; }
+            for (int b = a; b < D; ++b) { acc[e] = fma(ga, wv[b], acc[e]); ++e; }
+          }
         }
       }
+      warp_sum_store<NM>(acc, lane, sh_red + (w * K + k) * NM);
     }
-    warp_sum_store<NM>(acc, lane, sh_red + (w * K + k) * NM);
   }
   __syncthreads();
-  for (int idx = tid; idx < K * NM; idx += EST_THREADS) {
-    const int k = idx / NM, e = idx % NM;
-    double a = 0.0;
+  if constexpr (MODE != MLE_LIKE) {
+    for (int idx = tid; idx < K * NM; idx += EST_THREADS) {
+      const int k = idx / NM, e = idx % NM;
+      double a = 0.0;
 #pragma unroll
-    for (int ww = 0; ww < NW; ++ww) a += sh_red[(ww * K + k) * NM + e];
-    m.t_mom[((size_t)k * NMF + e) * s.T + t] = a;
+      for (int ww = 0; ww < NW; ++ww) a += sh_red[(ww * K + k) * NM + e];
+      m.t_mom[((size_t)k * NMF + e) * s.T + t] = a;
+    }
   }
   if (MODE != MLE_INIT && tid == 0) { double a = 0.0; for (int ww = 0; ww < NW; ++ww) a += sh_w[ww]; m.t_ll[t] = a; }
-  if (MODE == MLE_B && m.last_store) {
+  if constexpr (MODE == MLE_B_LAST) {
 #pragma unroll
     for (int c = 0; c < CPT; ++c) if (valid[c]) {
       if (kbest[c] < 0) { atomicCAS(&m.iter[1], 0, SQC_D_NAN); kbest[c] = 0; }  // idx(-1): index out of bounds
@@ -233,8 +238,17 @@ __global__ void __launch_bounds__(EST_THREADS, SQC_MLE_MINB) k_mle_pass(Dev s, M
 // per-sample reduction of the pass-A partials and the alpha_j solve (max_alpha_j_given_others :26-64):
 //   denom_j = sum_k G_jk inv(Sigma_k), numer_j = sum_k inv(Sigma_k) (X_jk - G_jk beta_k)
 // one warp per sample; WITH_ALPHA = 0 only reduces G_jk (extract_p_jk)
+// like != NULL: one more block (the last) sums the tiles' log-likelihood partials into like[slot] (slot < 0: discard)
 template <int WITH_ALPHA>
-__global__ void k_mle_sample(Dev s, MleBufs m) {
+__global__ void __launch_bounds__(256) k_mle_sample(Dev s, MleBufs m, double* like, int slot) {
+  if (like && blockIdx.x == gridDim.x - 1) {
+    __shared__ double sh[8];
+    double a = 0.0;
+    for (int t = threadIdx.x; t < s.T; t += 256) a += m.t_ll[t];
+    const double r = block_sum<256>(a, sh);
+    if (threadIdx.x == 0 && slot >= 0) like[slot] = r;
+    return;
+  }
   const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (j >= s.J) return;
   const int D = s.D, K = s.K, NMF = SQC_NMOM(D);
@@ -267,8 +281,12 @@ __global__ void k_mle_sample(Dev s, MleBufs m) {
 
 // fixed-order reduction over tiles: block b < K * NMOM sums moment b = k * NMOM + e (contiguous over the tiles); block
 // K * NMOM sums the log-likelihood partials into like[slot] (slot < 0: discard)
+__device__ __forceinline__ void mle_update_body(const Dev& s, const MleBufs& m, int derive_only);
+// UPDATE = 1 (single GPU): the block that finishes last goes on to the M-step update (k_mle_update) — one launch less
+template <int UPDATE>
 __global__ void __launch_bounds__(256) k_mle_reduce(Dev s, MleBufs m, double* like, int slot) {
   __shared__ double sh[8];
+  __shared__ int sh_last;
   const int b = blockIdx.x, nm = s.K * SQC_NMOM(s.D);
   const double* src = (b == nm) ? m.t_ll : m.t_mom + (size_t)b * s.T;
   double a = 0.0;
@@ -278,6 +296,15 @@ __global__ void __launch_bounds__(256) k_mle_reduce(Dev s, MleBufs m, double* li
     if (b == nm) { if (slot >= 0) like[slot] = r; }
     else m.mom[b] = r;
   }
+  if (!UPDATE) return;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const int prev = atomicAdd(&m.iter[3], 1);
+    sh_last = (prev == (int)gridDim.x - 1);
+    if (sh_last) { m.iter[3] = 0; __threadfence(); }
+  }
+  __syncthreads();
+  if (sh_last) mle_update_body(s, m, 0);
 }
 
 __global__ void __launch_bounds__(1024) k_mle_reduce_ll(Dev s, MleBufs m, double* like, int slot) {
@@ -289,7 +316,8 @@ __global__ void __launch_bounds__(1024) k_mle_reduce_ll(Dev s, MleBufs m, double
 }
 
 // beta_k, Sigma_k, p_k from the reduced moments (:65-147), then the derived density constants
-__global__ void k_mle_update(Dev s, MleBufs m, int derive_only) {
+// (run by the first K threads of ONE block; every thread of the block must call it)
+__device__ __forceinline__ void mle_update_body(const Dev& s, const MleBufs& m, int derive_only) {
   const int D = s.D, K = s.K, NMF = SQC_NMOM(D);
   __shared__ double tot;
   if (threadIdx.x == 0) { double a = 0.0; for (int k = 0; k < K; ++k) a += m.mom[k * NMF]; tot = a; }
@@ -297,7 +325,7 @@ __global__ void k_mle_update(Dev s, MleBufs m, int derive_only) {
   if (threadIdx.x == 0) m.iter[2] = 0;
   __syncthreads();
   const int k = threadIdx.x;
-  if (k >= K) return;
+  if (k >= K) return;                       // (no barrier below this line)
   if (!derive_only) {
     const double* S = m.mom + k * NMF;
     const double g = S[0];
@@ -332,6 +360,8 @@ __global__ void k_mle_update(Dev s, MleBufs m, int derive_only) {
   if (!(coef > 1e-20 && coef < 1e20)) atomicOr(&m.iter[2], 1);     // outside the range the fast path's exponent arithmetic is safe for
 }
 
+__global__ void k_mle_update(Dev s, MleBufs m, int derive_only) { mle_update_body(s, m, derive_only); }
+
 // p_jk = G_jk / sum_k G_jk (extract_p_jk :248-273), stored where the robust path keeps p_jk
 __global__ void k_mle_pjk(Dev s, MleBufs m) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -343,7 +373,7 @@ __global__ void k_mle_pjk(Dev s, MleBufs m) {
 
 template <int D> size_t mle_smem(int K, int mode) {
   size_t n = (size_t)K * DensK<D>::SZ + (size_t)K * 32 + (size_t)(EST_THREADS / 32) * K * SQC_NMOM(D);
-  if (mode == MLE_A || mode == MLE_B) n += (size_t)K * TileCfg<D>::TILE;
+  if (mode == MLE_A || mode == MLE_B || mode == MLE_B_LAST) n += (size_t)K * TileCfg<D>::TILE;
   return n * sizeof(double);
 }
 template <int D> void mle_launch_pass(const Dev& s, const MleBufs& m, int mode, cudaStream_t st) {
@@ -354,8 +384,14 @@ template <int D> void mle_launch_pass(const Dev& s, const MleBufs& m, int mode, 
       cudaFuncSetAttribute(k_mle_pass<D, MLE_A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
       k_mle_pass<D, MLE_A><<<s.T, EST_THREADS, sm, st>>>(s, m); break;
     case MLE_B:
-      cudaFuncSetAttribute(k_mle_pass<D, MLE_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-      k_mle_pass<D, MLE_B><<<s.T, EST_THREADS, sm, st>>>(s, m); break;
+      if (m.last_store) {
+        cudaFuncSetAttribute(k_mle_pass<D, MLE_B_LAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        k_mle_pass<D, MLE_B_LAST><<<s.T, EST_THREADS, sm, st>>>(s, m);
+      } else {
+        cudaFuncSetAttribute(k_mle_pass<D, MLE_B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        k_mle_pass<D, MLE_B><<<s.T, EST_THREADS, sm, st>>>(s, m);
+      }
+      break;
     default: k_mle_pass<D, MLE_LIKE><<<s.T, EST_THREADS, sm, st>>>(s, m); break;
   }
 }

@@ -44,33 +44,38 @@ void mle_run(sqc_session* S) {
   CK(cudaMemsetAsync(s.z, 0, (size_t)S->N, S->st));
   CK(cudaMemsetAsync(m.g_jk, 0, (size_t)J * K * sizeof(double), S->st));
   if (n_iter == 0) CK(cudaMemsetAsync(m.gamma, 0, (size_t)S->N * K * sizeof(double), S->st));            // gamma_i stays zeros, :291
-  auto reduce = [&](int ll_only, double* like, int slot) {
-    Launch L(S, SQC_KF_UPDATE);
-    if (ll_only) k_mle_reduce_ll<<<1, 1024, 0, S->st>>>(s, m, like, slot);
-    else k_mle_reduce<<<K * SQC_NMOM(D) + 1, 256, 0, S->st>>>(s, m, like, slot);
-    L.done();
-    if (S->world > 1) xchg_allreduce_mle(S, s, m, ll_only, like, slot);
+  const bool multi = S->world > 1;
+  // moments + log-likelihood reduced over the tiles (all-reduced over the GPUs), then the M-step update; on one GPU the
+  // update runs inside the reduction's last block
+  auto reduce_update = [&](double* like, int slot) {
+    { Launch L(S, SQC_KF_UPDATE, nullptr, "reduce_update");
+      if (multi) k_mle_reduce<0><<<K * SQC_NMOM(D) + 1, 256, 0, S->st>>>(s, m, like, slot);
+      else k_mle_reduce<1><<<K * SQC_NMOM(D) + 1, 256, 0, S->st>>>(s, m, like, slot);
+      L.done(); }
+    if (multi) {
+      xchg_allreduce_mle(S, s, m, 0, like, slot);
+      Launch L(S, SQC_KF_UPDATE); k_mle_update<<<1, 32, 0, S->st>>>(s, m, 0); L.done();
+    }
   };
-  auto update = [&]() { Launch L(S, SQC_KF_UPDATE); k_mle_update<<<1, 32, 0, S->st>>>(s, m, 0); L.done(); };
   // beta_k, Sigma_k, p_k from init_gamma_i (:301-303)
   m.last_store = 0;
   do_mle_pass(S, MLE_INIT);
-  reduce(0, s.like1, -1);
-  update();
+  reduce_update(s.like1, -1);
   CK(cudaEventRecord(S->ev_init, S->st));
   for (int i = 0; i < n_iter; ++i) {                                                                    // :307
     do_mle_pass(S, MLE_A);                                                                              // :313
-    { Launch L(S, SQC_KF_UPDATE); k_mle_sample<1><<<(J * 32 + 255) / 256, 256, 0, S->st>>>(s, m); L.done(); }   // :316
-    reduce(1, s.like2, i - 1);                                                                          // like_2 of iteration i-1, :326
+    // :316, and like_2 of iteration i-1 (:326) summed by the launch's extra block
+    { Launch L(S, SQC_KF_UPDATE, nullptr, "sample_alpha"); k_mle_sample<1><<<(J * 32 + 255) / 256 + 1, 256, 0, S->st>>>(s, m, s.like2, i - 1); L.done(); }
+    if (multi) xchg_allreduce_mle(S, s, m, 1, s.like2, i - 1);
     m.last_store = (i == n_iter - 1) ? 1 : 0;
     do_mle_pass(S, MLE_B);                                                                              // :317, :320
-    reduce(0, s.like1, i);
-    update();                                                                                           // :323-325
+    reduce_update(s.like1, i);                                                                          // :323-325
   }
   if (n_iter > 0) {
-    { Launch L(S, SQC_KF_UPDATE); k_mle_sample<0><<<(J * 32 + 255) / 256, 256, 0, S->st>>>(s, m); L.done(); }   // extract_p_jk, :331
+    { Launch L(S, SQC_KF_UPDATE); k_mle_sample<0><<<(J * 32 + 255) / 256, 256, 0, S->st>>>(s, m, nullptr, -1); L.done(); }   // extract_p_jk, :331
     do_mle_pass(S, MLE_LIKE);
-    reduce(1, s.like2, n_iter - 1);
+    { Launch L(S, SQC_KF_UPDATE); k_mle_reduce_ll<<<1, 1024, 0, S->st>>>(s, m, s.like2, n_iter - 1); L.done(); }
+    if (multi) xchg_allreduce_mle(S, s, m, 1, s.like2, n_iter - 1);
   }
   { Launch L(S, SQC_KF_UPDATE); k_mle_pjk<<<(J + 127) / 128, 128, 0, S->st>>>(s, m); L.done(); }
   { Launch L(S, SQC_KF_UPDATE); k_mle_finish<<<1, 32, 0, S->st>>>(s, m, n_iter); L.done(); }

@@ -27,7 +27,17 @@ for _ in range(steps):
     ms += st["loop_ms"] + st["init_ms"]
     for k, v in st["family_ms"].items():
         fam[k] = fam.get(k, 0.0) + v; cnt[k] = cnt.get(k, 0) + st["family_launches"][k]
-out = sess.fetch() if hasattr(sess, "fetch") else None
 sess.close()
+tl = os.environ.get("SQC_TIMELINE")
+if tl and os.path.exists(tl + ".rank0.csv"):                     # per-tag launch durations and the gaps behind them (last run)
+    import csv
+    rows = list(csv.DictReader(open(tl + ".rank0.csv")))
+    agg = {}
+    for a, b in zip(rows, rows[1:] + [None]):
+        d = agg.setdefault(a["tag"] or a["family"], [0, 0.0, 0.0])
+        d[0] += 1; d[1] += float(a["t1_ms"]) - float(a["t0_ms"])
+        if b is not None:
+            d[2] += float(b["t0_ms"]) - float(a["t1_ms"])
+    print(json.dumps({"timeline_us": {k: {"n": v[0], "avg": round(1e3 * v[1] / v[0], 1), "gap_after": round(1e3 * v[2] / v[0], 1)} for k, v in agg.items()}}))
 print(json.dumps({"lib": os.environ.get("SQC_LIB", "in-tree"), "workload": wl, "n_iter": n_iter, "ms_per_fit": ms / steps, "cell_iters_per_s": N * n_iter / (ms / steps / 1e3),
                   "family_ms_per_fit": {k: round(v / steps, 4) for k, v in fam.items() if v}, "avg_launch_us": {k: round(1e3 * fam[k] / cnt[k], 1) for k in fam if cnt[k]}}))
