@@ -352,7 +352,6 @@ void mle_run(sqc_session*);
 void mle_fetch(sqc_session*, sqc_fit_out*);
 void xchg_allreduce_host(sqc_session* S, double* buf, int n);
 void key_stream_setup(sqc_session* S);
-void xchg_allreduce_mle(sqc_session* S, Dev& s, MleBufs& m, int ll_only, double* like, int slot);
 
 // per-launch accounting: count every launch, time it with events when profiling is on
 struct Launch {
@@ -481,10 +480,6 @@ void xchg_iteration(sqc_session* S, Dev& s, int with_like) {
 
 void xchg_allreduce_host(sqc_session* S, double* buf, int n) {
   Launch L(S, SQC_KF_UPDATE); k_xchg_sum_f64<<<1, 256, 0, S->st>>>(S->xc.dev, XCHG_CH_HOST + 0, buf, n, nullptr); L.done();
-}
-void xchg_allreduce_mle(sqc_session* S, Dev& s, MleBufs& m, int ll_only, double* like, int slot) {
-  if (!ll_only) { Launch L(S, SQC_KF_UPDATE); k_xchg_sum_f64<<<1, 256, 0, S->st>>>(S->xc.dev, XCHG_CH_HOST + 2, m.mom, s.K * SQC_NMOM(s.D), nullptr); L.done(); }
-  if (slot >= 0) { Launch L(S, SQC_KF_UPDATE); k_xchg_sum_f64<<<1, 256, 0, S->st>>>(S->xc.dev, XCHG_CH_HOST + 3, like + slot, 1, nullptr); L.done(); }
 }
 
 #define SQC_CASE_ESTEP(DD) case DD: launch_estep<DD>(S, mode); break;

@@ -80,7 +80,7 @@ template <int D> __device__ __noinline__ double mle_dens_slow(const double* xcel
 #endif
 // One CTA per sample-aligned tile.  The densities use the E-step's arithmetic (sqc_kernels.cuh): affine whitening
 // y = L_k^-1 (x - alpha_j) - c_k, exp(-q/2) by table + degree-4 polynomial with the weight p_k (2 pi)^(-D/2) det^(-1/2)
-// folded into the table (constants derived once per M-step by k_mle_update), the reference's own arithmetic for the
+// folded into the table (constants derived once per M-step by mle_update_body), the reference's own arithmetic for the
 // cells the fast path is not safe for.  gamma = density / likelihood is one reciprocal per cell and a product per
 // component.  Per-component moment sums: registers -> recursive-halving warp sums -> one fixed-order sum over the
 // warps per tile (bit-reproducible), tile partials stored tile-minor so that the reductions read them contiguously.
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(256) k_mle_sample(Dev s, MleBufs m, double* li
 // fixed-order reduction over tiles: block b < K * NMOM sums moment b = k * NMOM + e (contiguous over the tiles); block
 // K * NMOM sums the log-likelihood partials into like[slot] (slot < 0: discard)
 __device__ __forceinline__ void mle_update_body(const Dev& s, const MleBufs& m, int derive_only);
-// UPDATE = 1 (single GPU): the block that finishes last goes on to the M-step update (k_mle_update) — one launch less
+// UPDATE = 1 (single GPU): the block that finishes last goes on to the M-step update — one launch less (several GPUs: k_mle_xchg_update)
 template <int UPDATE>
 __global__ void __launch_bounds__(256) k_mle_reduce(Dev s, MleBufs m, double* like, int slot) {
   __shared__ double sh[8];
@@ -359,8 +359,6 @@ __device__ __forceinline__ void mle_update_body(const Dev& s, const MleBufs& m, 
   for (int i = 0; i < 32; ++i) s.dens_tab[k * DENS_TAB + i] = coef * c_exp_tab[i];
   if (!(coef > 1e-20 && coef < 1e20)) atomicOr(&m.iter[2], 1);     // outside the range the fast path's exponent arithmetic is safe for
 }
-
-__global__ void k_mle_update(Dev s, MleBufs m, int derive_only) { mle_update_body(s, m, derive_only); }
 
 // p_jk = G_jk / sum_k G_jk (extract_p_jk :248-273), stored where the robust path keeps p_jk
 __global__ void k_mle_pjk(Dev s, MleBufs m) {

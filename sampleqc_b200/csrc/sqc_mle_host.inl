@@ -8,6 +8,14 @@ __global__ void k_mle_pack_pk(Dev s, MleBufs m, OutPtrs o, double* out_pk) {
   if ((int)threadIdx.x < s.K) out_pk[threadIdx.x] = m.p_k[o.korder[threadIdx.x]];     // reorder_vector, :338
 }
 
+// multi-GPU: the K x NMOM moments summed over the GPUs (rank order: bit-identical everywhere), then the M-step update, in
+// one launch.  The log-likelihoods are outputs only: every rank keeps its partial sums and the two vectors are summed
+// over the GPUs once, after the last iteration — one exchange per iteration instead of three.
+__global__ void __launch_bounds__(256) k_mle_xchg_update(Dev s, MleBufs m, XchgDev x) {
+  xchg_sum_f64(x, XCHG_CH_HOST + 2, m.mom, s.K * SQC_NMOM(s.D));
+  mle_update_body(s, m, 0);
+}
+
 void mle_alloc(sqc_session& S, const sqc_fit_args* a, MleBufs& m) {
   const int D = S.D, J = S.J, K = S.K; const long long N = S.N; const int T = S.dev.T;
   double* g0 = S.alloc<double>((size_t)N * K, false);
@@ -52,10 +60,7 @@ void mle_run(sqc_session* S) {
       if (multi) k_mle_reduce<0><<<K * SQC_NMOM(D) + 1, 256, 0, S->st>>>(s, m, like, slot);
       else k_mle_reduce<1><<<K * SQC_NMOM(D) + 1, 256, 0, S->st>>>(s, m, like, slot);
       L.done(); }
-    if (multi) {
-      xchg_allreduce_mle(S, s, m, 0, like, slot);
-      Launch L(S, SQC_KF_UPDATE); k_mle_update<<<1, 32, 0, S->st>>>(s, m, 0); L.done();
-    }
+    if (multi) { Launch L(S, SQC_KF_UPDATE, nullptr, "xchg_update"); k_mle_xchg_update<<<1, 256, 0, S->st>>>(s, m, S->xc.dev); L.done(); }
   };
   // beta_k, Sigma_k, p_k from init_gamma_i (:301-303)
   m.last_store = 0;
@@ -66,7 +71,6 @@ void mle_run(sqc_session* S) {
     do_mle_pass(S, MLE_A);                                                                              // :313
     // :316, and like_2 of iteration i-1 (:326) summed by the launch's extra block
     { Launch L(S, SQC_KF_UPDATE, nullptr, "sample_alpha"); k_mle_sample<1><<<(J * 32 + 255) / 256 + 1, 256, 0, S->st>>>(s, m, s.like2, i - 1); L.done(); }
-    if (multi) xchg_allreduce_mle(S, s, m, 1, s.like2, i - 1);
     m.last_store = (i == n_iter - 1) ? 1 : 0;
     do_mle_pass(S, MLE_B);                                                                              // :317, :320
     reduce_update(s.like1, i);                                                                          // :323-325
@@ -75,8 +79,13 @@ void mle_run(sqc_session* S) {
     { Launch L(S, SQC_KF_UPDATE); k_mle_sample<0><<<(J * 32 + 255) / 256, 256, 0, S->st>>>(s, m, nullptr, -1); L.done(); }   // extract_p_jk, :331
     do_mle_pass(S, MLE_LIKE);
     { Launch L(S, SQC_KF_UPDATE); k_mle_reduce_ll<<<1, 1024, 0, S->st>>>(s, m, s.like2, n_iter - 1); L.done(); }
-    if (multi) xchg_allreduce_mle(S, s, m, 1, s.like2, n_iter - 1);
   }
+  if (multi)                                                          // like_1 / like_2: partial sums until here
+    for (int i0 = 0; i0 < n_iter; i0 += 4096) {
+      const int n = std::min(4096, n_iter - i0);
+      { Launch L(S, SQC_KF_UPDATE); k_xchg_sum_f64<<<1, 256, 0, S->st>>>(S->xc.dev, XCHG_CH_HOST + 3, s.like1 + i0, n, nullptr); L.done(); }
+      { Launch L(S, SQC_KF_UPDATE); k_xchg_sum_f64<<<1, 256, 0, S->st>>>(S->xc.dev, XCHG_CH_HOST + 3, s.like2 + i0, n, nullptr); L.done(); }
+    }
   { Launch L(S, SQC_KF_UPDATE); k_mle_pjk<<<(J + 127) / 128, 128, 0, S->st>>>(s, m); L.done(); }
   { Launch L(S, SQC_KF_UPDATE); k_mle_finish<<<1, 32, 0, S->st>>>(s, m, n_iter); L.done(); }
   CK(cudaEventRecord(S->ev_loop, S->st));
