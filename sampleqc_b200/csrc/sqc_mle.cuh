@@ -235,23 +235,62 @@ __global__ void __launch_bounds__(EST_THREADS, SQC_MLE_MINB) k_mle_pass(Dev s, M
   }
 }
 
+// lower Cholesky factor and its inverse (small_chol_inv, sqc_common.cuh) with every index static: registers
+template <int D>
+__device__ __forceinline__ bool chol_inv_static(const double (&m)[D * D], double (&L)[D * D], double (&Li)[D * D]) {
+#pragma unroll
+  for (int i = 0; i < D * D; ++i) { L[i] = 0.0; Li[i] = 0.0; }
+  bool ok = true;
+#pragma unroll
+  for (int c = 0; c < D; ++c) {
+    double sdiag = m[c + D * c];
+#pragma unroll
+    for (int k = 0; k < c; ++k) sdiag -= L[c + D * k] * L[c + D * k];
+    ok = ok && (sdiag > 0.0) && (sdiag < CUDART_INF);
+    const double d = sqrt(sdiag); L[c + D * c] = d;
+#pragma unroll
+    for (int r = c + 1; r < D; ++r) {
+      double t = m[r + D * c];
+#pragma unroll
+      for (int k = 0; k < c; ++k) t -= L[r + D * k] * L[c + D * k];
+      L[r + D * c] = t / d;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < D; ++c) {                              // forward substitution for the inverse, column by column
+    Li[c + D * c] = 1.0 / L[c + D * c];
+#pragma unroll
+    for (int r = c + 1; r < D; ++r) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = c; k < r; ++k) t -= L[r + D * k] * Li[k + D * c];
+      Li[r + D * c] = t / L[r + D * r];
+    }
+  }
+  return ok;
+}
+
 // per-sample reduction of the pass-A partials and the alpha_j solve (max_alpha_j_given_others :26-64):
 //   denom_j = sum_k G_jk inv(Sigma_k), numer_j = sum_k inv(Sigma_k) (X_jk - G_jk beta_k)
-// one warp per sample; WITH_ALPHA = 0 only reduces G_jk (extract_p_jk)
+// one warp per sample; WITH_ALPHA = 0 only reduces G_jk (extract_p_jk).  D is a template parameter so that the solve of
+// lane 0 runs in registers (with a run-time D it was 3000 instructions on local memory, most of the kernel).
 // like != NULL: one more block (the last) sums the tiles' log-likelihood partials into like[slot] (slot < 0: discard)
-template <int WITH_ALPHA>
+template <int D, int WITH_ALPHA>
 __global__ void __launch_bounds__(256) k_mle_sample(Dev s, MleBufs m, double* like, int slot) {
   if (like && blockIdx.x == gridDim.x - 1) {
     __shared__ double sh[8];
-    double a = 0.0;
-    for (int t = threadIdx.x; t < s.T; t += 256) a += m.t_ll[t];
-    const double r = block_sum<256>(a, sh);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int t = threadIdx.x;
+    for (; t + 768 < s.T; t += 1024) { a0 += m.t_ll[t]; a1 += m.t_ll[t + 256]; a2 += m.t_ll[t + 512]; a3 += m.t_ll[t + 768]; }
+    for (; t < s.T; t += 256) a0 += m.t_ll[t];
+    const double r = block_sum<256>((a0 + a1) + (a2 + a3), sh);
     if (threadIdx.x == 0 && slot >= 0) like[slot] = r;
     return;
   }
   const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (j >= s.J) return;
-  const int D = s.D, K = s.K, NMF = SQC_NMOM(D);
+  constexpr int NMF = SQC_NMOM(D);
+  const int K = s.K;
   const int t0 = s.sample_tile_begin[j], t1 = s.sample_tile_begin[j + 1];
   for (int e = lane; e < K * (1 + D); e += 32) {
     const int k = e / (1 + D), c = e % (1 + D);
@@ -263,35 +302,59 @@ __global__ void __launch_bounds__(256) k_mle_sample(Dev s, MleBufs m, double* li
   if (!WITH_ALPHA) return;
   __syncwarp();
   if (lane == 0) {
-    double denom[SQC_MAXD * SQC_MAXD], numer[SQC_MAXD], inv[SQC_MAXD * SQC_MAXD];
+    double denom[D * D], numer[D], inv[D * D];
+#pragma unroll
     for (int e = 0; e < D * D; ++e) denom[e] = 0.0;
+#pragma unroll
     for (int d = 0; d < D; ++d) numer[d] = 0.0;
     for (int k = 0; k < K; ++k) {
       const double g = m.g_jk[j * K + k];
       const double* A = s.ainv + k * D * D;
-      double v[SQC_MAXD];
+      double v[D];
+#pragma unroll
       for (int d = 0; d < D; ++d) v[d] = m.x_jk[((long long)j * K + k) * D + d] - g * s.beta[k * D + d];
-      for (int r = 0; r < D; ++r) { double a = 0.0; for (int c = 0; c < D; ++c) a += A[r + D * c] * v[c]; numer[r] += a; }
+#pragma unroll
+      for (int r = 0; r < D; ++r) {
+        double a = 0.0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) a += A[r + D * c] * v[c];
+        numer[r] += a;
+      }
+#pragma unroll
       for (int e = 0; e < D * D; ++e) denom[e] += g * A[e];
     }
-    if (!small_inv(denom, D, inv)) { atomicCAS(&m.iter[1], 0, SQC_D_SINGULAR); return; }   // inv(), :60
-    for (int r = 0; r < D; ++r) { double a = 0.0; for (int c = 0; c < D; ++c) a += inv[r + D * c] * numer[c]; s.alpha[j * D + r] = a; }
+    if (!inv_small<D>(denom, inv)) { atomicCAS(&m.iter[1], 0, SQC_D_SINGULAR); return; }   // inv(), :60
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+      double a = 0.0;
+#pragma unroll
+      for (int c = 0; c < D; ++c) a += inv[r + D * c] * numer[c];
+      s.alpha[j * D + r] = a;
+    }
   }
 }
 
+template <int D> __device__ __forceinline__ void mle_update_body(const Dev& s, const MleBufs& m);
 // fixed-order reduction over tiles: block b < K * NMOM sums moment b = k * NMOM + e (contiguous over the tiles); block
-// K * NMOM sums the log-likelihood partials into like[slot] (slot < 0: discard)
-__device__ __forceinline__ void mle_update_body(const Dev& s, const MleBufs& m, int derive_only);
-// UPDATE = 1 (single GPU): the block that finishes last goes on to the M-step update — one launch less (several GPUs: k_mle_xchg_update)
-template <int UPDATE>
-__global__ void __launch_bounds__(256) k_mle_reduce(Dev s, MleBufs m, double* like, int slot) {
+// K * NMOM sums the log-likelihood partials into like[slot] (slot < 0: discard).
+// UPDATE = 1 (single GPU): the block that finishes last goes on to the M-step update — one launch less (several GPUs:
+// k_mle_xchg_update)
+template <int D, int UPDATE>
+__global__ void __launch_bounds__(256) k_mle_reduce(Dev s, MleBufs m, double* like, int slot) {   // 256 threads: the update's matrices want registers
   __shared__ double sh[8];
   __shared__ int sh_last;
-  const int b = blockIdx.x, nm = s.K * SQC_NMOM(s.D);
+  const int b = blockIdx.x, nm = s.K * SQC_NMOM(D);
   const double* src = (b == nm) ? m.t_ll : m.t_mom + (size_t)b * s.T;
-  double a = 0.0;
-  for (int t = threadIdx.x; t < s.T; t += 256) a += src[t];
-  const double r = block_sum<256>(a, sh);
+  double acc[8];                                             // independent loads in flight: the kernel is nothing but their latency
+#pragma unroll
+  for (int u = 0; u < 8; ++u) acc[u] = 0.0;
+  int t = threadIdx.x;
+  for (; t + 7 * 256 < s.T; t += 8 * 256) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] += src[t + u * 256];
+  }
+  for (; t < s.T; t += 256) acc[0] += src[t];
+  const double r = block_sum<256>(((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7])), sh);
   if (threadIdx.x == 0) {
     if (b == nm) { if (slot >= 0) like[slot] = r; }
     else m.mom[b] = r;
@@ -304,7 +367,7 @@ __global__ void __launch_bounds__(256) k_mle_reduce(Dev s, MleBufs m, double* li
     if (sh_last) { m.iter[3] = 0; __threadfence(); }
   }
   __syncthreads();
-  if (sh_last) mle_update_body(s, m, 0);
+  if (sh_last) mle_update_body<D>(s, m);
 }
 
 __global__ void __launch_bounds__(1024) k_mle_reduce_ll(Dev s, MleBufs m, double* like, int slot) {
@@ -315,49 +378,71 @@ __global__ void __launch_bounds__(1024) k_mle_reduce_ll(Dev s, MleBufs m, double
   if (threadIdx.x == 0 && slot >= 0) like[slot] = r;
 }
 
-// beta_k, Sigma_k, p_k from the reduced moments (:65-147), then the derived density constants
-// (run by the first K threads of ONE block; every thread of the block must call it)
-__device__ __forceinline__ void mle_update_body(const Dev& s, const MleBufs& m, int derive_only) {
-  const int D = s.D, K = s.K, NMF = SQC_NMOM(D);
-  __shared__ double tot;
-  if (threadIdx.x == 0) { double a = 0.0; for (int k = 0; k < K; ++k) a += m.mom[k * NMF]; tot = a; }
-  __syncthreads();
-  if (threadIdx.x == 0) m.iter[2] = 0;
+// beta_k, Sigma_k, p_k from the reduced moments (:65-147), then the derived constants of the passes.  Every thread of ONE
+// block calls it; thread k < K works on component k with the small matrices in registers, then the whole block fills
+// the K x 32 weighted exponential tables.
+template <int D>
+__device__ __forceinline__ void mle_update_body(const Dev& s, const MleBufs& m) {
+  constexpr int NMF = SQC_NMOM(D), TRI = SQC_TRI(D);
+  const int K = s.K;
+  __shared__ double sh_tot;
+  __shared__ double sh_coef[SQC_MAXK];
+  __shared__ int sh_bad;
+  if (threadIdx.x == 0) { double a = 0.0; for (int k = 0; k < K; ++k) a += m.mom[k * NMF]; sh_tot = a; sh_bad = 0; }
   __syncthreads();
   const int k = threadIdx.x;
-  if (k >= K) return;                       // (no barrier below this line)
-  if (!derive_only) {
+  if (k < K) {
     const double* S = m.mom + k * NMF;
-    const double g = S[0];
-    double mm[SQC_MAXD];
-    for (int d = 0; d < D; ++d) mm[d] = S[1 + d] / g;
-    int e = 1 + D;
-    for (int a = 0; a < D; ++a)
-      for (int b = a; b < D; ++b) {
-        const double v = S[e++] / g - mm[a] * mm[b];
-        s.sigma[k * D * D + a + D * b] = v; s.sigma[k * D * D + b + D * a] = v;
+    double mo[NMF];
+#pragma unroll
+    for (int e = 0; e < NMF; ++e) mo[e] = S[e];
+    const double g = mo[0];
+    double mm[D], Sg[D * D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) mm[d] = mo[1 + d] / g;
+    {
+      int e = 1 + D;
+#pragma unroll
+      for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int b = a; b < D; ++b) { const double v = mo[e] / g - mm[a] * mm[b]; Sg[a + D * b] = v; Sg[b + D * a] = v; ++e; }
+    }
+    double bk[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) { bk[d] = s.beta[k * D + d] + mm[d]; s.beta[k * D + d] = bk[d]; }
+#pragma unroll
+    for (int e = 0; e < D * D; ++e) s.sigma[k * D * D + e] = Sg[e];
+    const double pk = g / sh_tot;
+    m.p_k[k] = pk;
+    double L[D * D], Li[D * D], Ai[D * D];
+    bool good = true;
+    if (!inv_small<D>(Sg, Ai)) { atomicCAS(&m.iter[1], 0, SQC_D_SINGULAR); good = false; }
+    else if (!chol_inv_static<D>(Sg, L, Li)) { atomicCAS(&m.iter[1], 0, SQC_D_NOT_SPD); good = false; }
+    double coef = 0.0;
+    if (good) {
+      const double det = small_det(Sg, D);
+#pragma unroll
+      for (int e = 0; e < D * D; ++e) { s.linv[k * D * D + e] = Li[e]; s.ainv[k * D * D + e] = Ai[e]; }
+      const double nrm = 1.0 / sqrt(pow(6.283185307179586476925286766559, (double)D) * det);
+      s.Pk[k] = nrm;
+      coef = pk * nrm;
+      m.coef[k] = coef;
+      // constants of the passes' fast densities (sqc_kernels.cuh): L^-1 packed, c = L^-1 beta
+      double* ck = s.dens_cons + k * (TRI + D);
+#pragma unroll
+      for (int r = 0; r < D; ++r) {
+        double c = 0.0;
+#pragma unroll
+        for (int cc = 0; cc <= r; ++cc) { const double l = Li[r + D * cc]; ck[r * (r + 1) / 2 + cc] = l; c = fma(l, bk[cc], c); }
+        ck[TRI + r] = c;
       }
-    for (int d = 0; d < D; ++d) s.beta[k * D + d] = s.beta[k * D + d] + mm[d];
-    m.p_k[k] = g / tot;
+      if (!(coef > 1e-20 && coef < 1e20)) sh_bad = 1;       // outside the range the fast path's exponent arithmetic is safe for
+    }
+    sh_coef[k] = coef;
   }
-  const double* Sg = s.sigma + k * D * D;
-  double L[SQC_MAXD * SQC_MAXD], Li[SQC_MAXD * SQC_MAXD], Ai[SQC_MAXD * SQC_MAXD];
-  if (!small_inv(Sg, D, Ai)) { atomicCAS(&m.iter[1], 0, SQC_D_SINGULAR); return; }
-  if (!small_chol_inv(Sg, D, L, Li)) { atomicCAS(&m.iter[1], 0, SQC_D_NOT_SPD); return; }
-  const double det = small_det(Sg, D);
-  for (int e2 = 0; e2 < D * D; ++e2) { s.linv[k * D * D + e2] = Li[e2]; s.ainv[k * D * D + e2] = Ai[e2]; }
-  s.Pk[k] = 1.0 / sqrt(pow(6.283185307179586476925286766559, (double)D) * det);
-  const double coef = m.p_k[k] * s.Pk[k];
-  m.coef[k] = coef;
-  // constants of the passes' fast densities (sqc_kernels.cuh): L^-1 packed, c = L^-1 beta, the weight folded into the exp table
-  double* ck = s.dens_cons + k * (SQC_TRI(D) + D);
-  for (int r = 0; r < D; ++r) {
-    double c = 0.0;
-    for (int cc = 0; cc <= r; ++cc) { const double l = Li[r + D * cc]; ck[r * (r + 1) / 2 + cc] = l; c = fma(l, s.beta[k * D + cc], c); }
-    ck[SQC_TRI(D) + r] = c;
-  }
-  for (int i = 0; i < 32; ++i) s.dens_tab[k * DENS_TAB + i] = coef * c_exp_tab[i];
-  if (!(coef > 1e-20 && coef < 1e20)) atomicOr(&m.iter[2], 1);     // outside the range the fast path's exponent arithmetic is safe for
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < K * 32; idx += blockDim.x) s.dens_tab[(idx >> 5) * DENS_TAB + (idx & 31)] = sh_coef[idx >> 5] * c_exp_tab[idx & 31];   // the weight folded into the exp table
+  if (threadIdx.x == 0) m.iter[2] = sh_bad;
 }
 
 // p_jk = G_jk / sum_k G_jk (extract_p_jk :248-273), stored where the robust path keeps p_jk

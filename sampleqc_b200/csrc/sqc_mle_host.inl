@@ -11,9 +11,38 @@ __global__ void k_mle_pack_pk(Dev s, MleBufs m, OutPtrs o, double* out_pk) {
 // multi-GPU: the K x NMOM moments summed over the GPUs (rank order: bit-identical everywhere), then the M-step update, in
 // one launch.  The log-likelihoods are outputs only: every rank keeps its partial sums and the two vectors are summed
 // over the GPUs once, after the last iteration — one exchange per iteration instead of three.
+template <int D>
 __global__ void __launch_bounds__(256) k_mle_xchg_update(Dev s, MleBufs m, XchgDev x) {
-  xchg_sum_f64(x, XCHG_CH_HOST + 2, m.mom, s.K * SQC_NMOM(s.D));
-  mle_update_body(s, m, 0);
+  xchg_sum_f64(x, XCHG_CH_HOST + 2, m.mom, s.K * SQC_NMOM(D));
+  mle_update_body<D>(s, m);
+}
+
+enum { MLE_S_REDUCE_UPDATE = 0, MLE_S_SAMPLE_ALPHA = 1, MLE_S_SAMPLE = 2 };
+// the small kernels between the passes, D compile-time (their solves live in registers)
+template <int D> void mle_launch_small(sqc_session* S, int what, double* like, int slot) {
+  Dev& s = S->dev; MleBufs& m = S->ml;
+  const int J = S->J, K = S->K; const bool multi = S->world > 1;
+  switch (what) {
+    case MLE_S_REDUCE_UPDATE: {
+      // moments + log-likelihood reduced over the tiles, then the M-step update: on one GPU inside the reduction's
+      // last block; on several after the all-reduce of the moments, in that kernel
+      { Launch L(S, SQC_KF_UPDATE, nullptr, "reduce_update");
+        if (multi) k_mle_reduce<D, 0><<<K * SQC_NMOM(D) + 1, 256, 0, S->st>>>(s, m, like, slot);
+        else k_mle_reduce<D, 1><<<K * SQC_NMOM(D) + 1, 256, 0, S->st>>>(s, m, like, slot);
+        L.done(); }
+      if (multi) { Launch L(S, SQC_KF_UPDATE, nullptr, "xchg_update"); k_mle_xchg_update<D><<<1, 256, 0, S->st>>>(s, m, S->xc.dev); L.done(); }
+      break; }
+    case MLE_S_SAMPLE_ALPHA: {
+      Launch L(S, SQC_KF_UPDATE, nullptr, "sample_alpha"); k_mle_sample<D, 1><<<(J * 32 + 255) / 256 + 1, 256, 0, S->st>>>(s, m, like, slot); L.done();
+      break; }
+    default: {
+      Launch L(S, SQC_KF_UPDATE); k_mle_sample<D, 0><<<(J * 32 + 255) / 256, 256, 0, S->st>>>(s, m, nullptr, -1); L.done();
+      break; }
+  }
+}
+#define SQC_CASE_MLE_SMALL(DD) case DD: mle_launch_small<DD>(S, what, like, slot); break;
+void do_mle_small(sqc_session* S, int what, double* like, int slot) {
+  switch (S->D) { SQC_FOR_D(SQC_CASE_MLE_SMALL) default: fail(SQC_ERR_BAD_ARG, "D = %d not compiled in", S->D); }
 }
 
 void mle_alloc(sqc_session& S, const sqc_fit_args* a, MleBufs& m) {
@@ -53,15 +82,7 @@ void mle_run(sqc_session* S) {
   CK(cudaMemsetAsync(m.g_jk, 0, (size_t)J * K * sizeof(double), S->st));
   if (n_iter == 0) CK(cudaMemsetAsync(m.gamma, 0, (size_t)S->N * K * sizeof(double), S->st));            // gamma_i stays zeros, :291
   const bool multi = S->world > 1;
-  // moments + log-likelihood reduced over the tiles (all-reduced over the GPUs), then the M-step update; on one GPU the
-  // update runs inside the reduction's last block
-  auto reduce_update = [&](double* like, int slot) {
-    { Launch L(S, SQC_KF_UPDATE, nullptr, "reduce_update");
-      if (multi) k_mle_reduce<0><<<K * SQC_NMOM(D) + 1, 256, 0, S->st>>>(s, m, like, slot);
-      else k_mle_reduce<1><<<K * SQC_NMOM(D) + 1, 256, 0, S->st>>>(s, m, like, slot);
-      L.done(); }
-    if (multi) { Launch L(S, SQC_KF_UPDATE, nullptr, "xchg_update"); k_mle_xchg_update<<<1, 256, 0, S->st>>>(s, m, S->xc.dev); L.done(); }
-  };
+  auto reduce_update = [&](double* like, int slot) { do_mle_small(S, MLE_S_REDUCE_UPDATE, like, slot); };
   // beta_k, Sigma_k, p_k from init_gamma_i (:301-303)
   m.last_store = 0;
   do_mle_pass(S, MLE_INIT);
@@ -70,13 +91,13 @@ void mle_run(sqc_session* S) {
   for (int i = 0; i < n_iter; ++i) {                                                                    // :307
     do_mle_pass(S, MLE_A);                                                                              // :313
     // :316, and like_2 of iteration i-1 (:326) summed by the launch's extra block
-    { Launch L(S, SQC_KF_UPDATE, nullptr, "sample_alpha"); k_mle_sample<1><<<(J * 32 + 255) / 256 + 1, 256, 0, S->st>>>(s, m, s.like2, i - 1); L.done(); }
+    do_mle_small(S, MLE_S_SAMPLE_ALPHA, s.like2, i - 1);
     m.last_store = (i == n_iter - 1) ? 1 : 0;
     do_mle_pass(S, MLE_B);                                                                              // :317, :320
     reduce_update(s.like1, i);                                                                          // :323-325
   }
   if (n_iter > 0) {
-    { Launch L(S, SQC_KF_UPDATE); k_mle_sample<0><<<(J * 32 + 255) / 256, 256, 0, S->st>>>(s, m, nullptr, -1); L.done(); }   // extract_p_jk, :331
+    do_mle_small(S, MLE_S_SAMPLE, nullptr, -1);                                                         // extract_p_jk, :331
     do_mle_pass(S, MLE_LIKE);
     { Launch L(S, SQC_KF_UPDATE); k_mle_reduce_ll<<<1, 1024, 0, S->st>>>(s, m, s.like2, n_iter - 1); L.done(); }
   }
