@@ -602,54 +602,126 @@ __global__ void k_init_alpha(Dev s) {
 //   position of a sample's first cell of component k inside the cluster-sorted segment), cluster sizes and
 //   segment offsets.  k_partition adds the counts of the earlier tiles of its own sample.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void em_control_block(Dev& s);
-__global__ void __launch_bounds__(1024) k_post_stats(Dev s, int n_sample_blocks, int fuse_ctl) {
-  __shared__ long long sh_scan[33];
+__device__ __forceinline__ void em_control_block(Dev& s, bool with_like = true, bool with_track_alpha = true);
+template <int D> __device__ __forceinline__ void alpha_from_stats(Dev& s, int j);
+// exclusive block scans of up to four long long per thread at once (one per component); *total = block sums
+template <int NT> __device__ __forceinline__ void block_excl_scan4(long long (&v)[4], long long (*sh)[NT / 32 + 1], long long (&total)[4]) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  long long inc[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    inc[q] = v[q];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { long long t = __shfl_up_sync(0xffffffffu, inc[q], o); if (lane >= o) inc[q] += t; }
+  }
+  __syncthreads();
+  if (lane == 31) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sh[q][w] = inc[q];
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) { long long run = 0; for (int i = 0; i < NT / 32; ++i) { long long t = sh[threadIdx.x][i]; sh[threadIdx.x][i] = run; run += t; } sh[threadIdx.x][NT / 32] = run; }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { total[q] = sh[q][NT / 32]; v[q] = sh[q][w] + inc[q] - v[q]; }
+}
+// flags: bit 0 (single GPU) = the end-of-iteration bookkeeping rides along (:511-521; one launch less): one extra block
+//        sums the tile log-likelihoods beside the sample blocks, the block that finishes last closes the iteration;
+//        bit 1 (with bit 0) = alpha_j of the NEXT iteration (update_alpha_j, :496) rides along too: the warp that has just
+//        reduced sample j's statistics solves for its alpha_j when the loop goes on — the loop condition of :490 is
+//        known at entry (z_delta of the E-step before, the iteration count, the status).
+//        (D <= POST_ALPHA_MAXD: beyond it the D x D solve does not fit the 64 registers of a 1024-thread block).
+constexpr int POST_ALPHA_MAXD = 4;
+template <int D>
+__global__ void __launch_bounds__(1024) k_post_stats(Dev s, int n_sample_blocks, int flags) {
+  __shared__ long long sh_scan[4][33];
+  __shared__ double sh_like[32];
   __shared__ int sh_last;
   if (!s.ctl->cont) return;
   const int tid = threadIdx.x, lane = tid & 31, K = s.K;
-  {
+  const bool fuse_ctl = flags & 1, fuse_alpha = (D <= POST_ALPHA_MAXD) && (flags & 3) == 3;
+  const int it = s.ctl->iter;
+  const bool goes_on = (s.ctl->z_delta > 0) && (it + 1 < s.em_iters) && (s.ctl->status == 0);       // what em_control_block will find
+  const int n_blocks = n_sample_blocks + (fuse_ctl ? 1 : 0);
+  if ((int)blockIdx.x == n_sample_blocks) {                    // the likelihood block (same sums, same order as em_control_block)
+    double a1 = 0.0, a2 = 0.0;
+    for (int t = tid; t < s.T; t += 1024) { a1 += s.t_ll1[t]; a2 += s.t_ll2[t]; }
+    const double r1 = block_sum<1024>(a1, sh_like);
+    const double r2 = block_sum<1024>(a2, sh_like);
+    if (tid == 0) { s.like1[it] = r1; s.like2[it] = r2; }
+  } else {
     const int j = blockIdx.x * 32 + (tid >> 5);
     if (j < s.J) {
       const int t0 = s.sample_tile_begin[j], t1 = s.sample_tile_begin[j + 1];
-      const int ne = K * (s.D + 1);
+      const int ne = K * (D + 1);
+      // eight tiles' partials in flight at a time (the t_rel stores would otherwise order the t_nk loads one behind the
+      // other); the sums run in tile order as before
       for (int e = lane; e < ne; e += 32) {
-        const int k = e / (s.D + 1), c = e % (s.D + 1);
-        if (c == 0) { int a = 0; for (int t = t0; t < t1; ++t) { s.t_rel[t * K + k] = a; a += s.t_nk[t * K + k]; } s.n_jk[j * K + k] = a; }
-        else { double a = 0.0; for (int t = t0; t < t1; ++t) a += s.t_sk[((long long)t * K + k) * s.D + (c - 1)]; s.s_jk[((long long)j * K + k) * s.D + (c - 1)] = a; }
+        const int k = e / (D + 1), c = e % (D + 1);
+        if (c == 0) {
+          int a = 0;
+          for (int tb = t0; tb < t1; tb += 8) {
+            int v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (tb + u < t1) ? __ldcg(s.t_nk + (tb + u) * K + k) : 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (tb + u < t1) { s.t_rel[(tb + u) * K + k] = a; a += v[u]; }
+          }
+          s.n_jk[j * K + k] = a;
+        } else {
+          double a = 0.0;
+          for (int tb = t0; tb < t1; tb += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (tb + u < t1) ? __ldcg(s.t_sk + ((long long)(tb + u) * K + k) * D + (c - 1)) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) if (tb + u < t1) a += v[u];
+          }
+          s.s_jk[((long long)j * K + k) * D + (c - 1)] = a;
+        }
+      }
+      if constexpr (D <= POST_ALPHA_MAXD) if (fuse_alpha) {
+        if (s.track && it < s.em_iters && lane < D) s.track_alpha[(long long)it * s.J * D + j + s.J * lane] = s.alpha[j * D + lane];
+        __syncwarp();                                          // the statistics above were written by this warp's lanes
+        if (goes_on && lane == 0) alpha_from_stats<D>(s, j);
       }
     }
   }
   __threadfence();
   __syncthreads();
-  if (tid == 0) sh_last = (atomicAdd(s.done_ctr, 1u) == (unsigned)n_sample_blocks - 1u) ? 1 : 0;
+  if (tid == 0) sh_last = (atomicAdd(s.done_ctr, 1u) == (unsigned)n_blocks - 1u) ? 1 : 0;
   __syncthreads();
   if (!sh_last) return;
   __threadfence();
-  // exclusive scan over the samples, one block scan per component (thread t owns a contiguous run of samples)
+  // exclusive scan over the samples for four components at a time (thread t owns a contiguous run of samples)
   const int per = (s.J + 1023) / 1024;
   const int j0 = min(tid * per, s.J), j1 = min(j0 + per, s.J);
-  long long off_run = 0;
-  for (int k = 0; k < K; ++k) {
-    long long mine = 0;
-    for (int j = j0; j < j1; ++j) mine += __ldcg(s.n_jk + j * K + k);
-    long long total;
-    long long run = block_excl_scan<1024>(mine, sh_scan, &total);
-    for (int j = j0; j < j1; ++j) { s.s_base[j * K + k] = (int)run; run += __ldcg(s.n_jk + j * K + k); }
-    if (tid == 0) { s.clu_n[k] = total; s.clu_off[k] = off_run; }
-    off_run += (total + 31) & ~31ll;        // 256-byte aligned cluster segments
+  long long off_run = 0, key_run = 0;
+  for (int k0 = 0; k0 < K; k0 += 4) {
+    long long run[4], total[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      run[q] = 0;
+      if (k0 + q < K) for (int j = j0; j < j1; ++j) run[q] += __ldcg(s.n_jk + j * K + k0 + q);
+    }
+    block_excl_scan4<1024>(run, sh_scan, total);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (k0 + q < K) {
+        long long r = run[q];
+        for (int j = j0; j < j1; ++j) { s.s_base[j * K + k0 + q] = (int)r; r += __ldcg(s.n_jk + j * K + k0 + q); }
+        // single GPU: the key stream of one update_beta_scale_k call runs over the clusters in order (SURVEY Appendix
+        // A3); the multi-GPU exchange overwrites clu_n_glob / clu_prefix with the global values
+        if (tid == 0) { s.clu_n[k0 + q] = total[q]; s.clu_off[k0 + q] = off_run; s.clu_n_glob[k0 + q] = total[q]; s.clu_prefix[k0 + q] = key_run; }
+        off_run += (total[q] + 31) & ~31ll;        // 256-byte aligned cluster segments
+        key_run += total[q];
+      }
+    }
     __syncthreads();
   }
-  // single GPU: the key stream of one update_beta_scale_k call runs over the clusters in order
-  // (SURVEY Appendix A3); the multi-GPU exchange overwrites these with the global values
-  if (tid == 0) {
-    long long run = 0;
-    for (int k = 0; k < K; ++k) { s.clu_n_glob[k] = s.clu_n[k]; s.clu_prefix[k] = run; run += s.clu_n[k]; }
-    *s.done_ctr = 0u;
-  }
-  // single GPU: the end-of-iteration bookkeeping rides along (one launch less); every other block of this launch
-  // has passed its loop-flag test by now
-  if (fuse_ctl) { __syncthreads(); em_control_block(s); }
+  if (tid == 0) *s.done_ctr = 0u;
+  // every other block of this launch has passed its loop-flag test (and read iter / z_delta / status) by now
+  if (fuse_ctl) { __syncthreads(); em_control_block(s, false, !fuse_alpha); }
 }
 
 // alpha_j from the (j,k) statistics: update_alpha_j :116-157 with the per-cell sums factored out
@@ -694,10 +766,7 @@ __device__ __forceinline__ bool inv_small(const double (&m)[D * D], double (&inv
   return ok;
 }
 template <int D>
-__global__ void k_update_alpha(Dev s) {
-  if (!s.ctl->cont) return;
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= s.J) return;
+__device__ __forceinline__ void alpha_from_stats(Dev& s, int j) {
   const int K = s.K;
   double denom[D * D], numer[D], inv[D * D];
 #pragma unroll
@@ -729,6 +798,13 @@ __global__ void k_update_alpha(Dev s) {
     s.alpha[j * D + r] = a;
   }
 }
+template <int D>
+__global__ void k_update_alpha(Dev s) {
+  if (!s.ctl->cont) return;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= s.J) return;
+  alpha_from_stats<D>(s, j);
+}
 // p_jk = (1 + n_jk) / (K + n_j), update_p_jk :322-341
 __global__ void k_update_p(Dev s) {
   if (!s.ctl->cont) return;
@@ -744,23 +820,26 @@ __global__ void k_update_p(Dev s) {
 
 // end-of-iteration bookkeeping (:499,:506,:511-521): deterministic sums of the tile log-likelihoods,
 // loop condition, optional tracking.  single block.
-__device__ __forceinline__ void em_control_block(Dev& s) {       // one block of 1024 threads
+__device__ __forceinline__ void em_control_block(Dev& s, bool with_like, bool with_track_alpha) {       // one block of 1024 threads
   __shared__ double sh[32];
   Control* c = s.ctl;
   const int it = c->iter;
-  double a1 = 0.0, a2 = 0.0;
-  for (int t = threadIdx.x; t < s.T; t += 1024) { a1 += s.t_ll1[t]; a2 += s.t_ll2[t]; }
-  double r1 = block_sum<1024>(a1, sh);
-  double r2 = block_sum<1024>(a2, sh);
+  double r1 = 0.0, r2 = 0.0;
+  if (with_like) {                                 // (otherwise like1[it] / like2[it] were written by the likelihood block of k_post_stats)
+    double a1 = 0.0, a2 = 0.0;
+    for (int t = threadIdx.x; t < s.T; t += 1024) { a1 += s.t_ll1[t]; a2 += s.t_ll2[t]; }
+    r1 = block_sum<1024>(a1, sh);
+    r2 = block_sum<1024>(a2, sh);
+  }
   if (s.track && it < s.em_iters) {
-    for (int e = threadIdx.x; e < s.J * s.D; e += 1024) { int j = e / s.D, d = e % s.D; s.track_alpha[(long long)it * s.J * s.D + j + s.J * d] = s.alpha[e]; }
+    if (with_track_alpha) for (int e = threadIdx.x; e < s.J * s.D; e += 1024) { int j = e / s.D, d = e % s.D; s.track_alpha[(long long)it * s.J * s.D + j + s.J * d] = s.alpha[e]; }
     for (int e = threadIdx.x; e < s.K * s.D; e += 1024) { int k = e / s.D, d = e % s.D; s.track_beta[(long long)it * s.K * s.D + k + s.K * d] = s.beta[e]; }
     for (int e = threadIdx.x; e < s.K * s.D * s.D; e += 1024) s.track_sigma[(long long)it * s.K * s.D * s.D + e] = s.sigma[e];
     for (int e = threadIdx.x; e < s.J * s.K; e += 1024) { int j = e / s.K, k = e % s.K; s.track_p[(long long)it * s.J * s.K + j + s.J * k] = s.p_jk[e]; }
   }
   if (threadIdx.x == 0) {
     // multi-GPU: like sums and z_delta are made global by the host-side exchange before this point
-    s.like1[it] = r1; s.like2[it] = r2;
+    if (with_like) { s.like1[it] = r1; s.like2[it] = r2; }
     c->iter = it + 1;
     __threadfence();
     c->cont = (c->z_delta > 0) && (it + 1 < s.em_iters) && (c->status == 0);    // :490

@@ -498,6 +498,13 @@ void do_update_alpha(sqc_session* S) {
   switch (S->D) { SQC_FOR_D(SQC_CASE_ALPHA) default: fail(SQC_ERR_BAD_ARG, "D = %d not compiled in", S->D); }
   L.done();
 }
+#define SQC_CASE_POST(DD) case DD: k_post_stats<DD><<<nsb + (flags & 1), 1024, 0, S->st>>>(S->dev, nsb, flags); break;
+void do_post_stats(sqc_session* S, int flags) {
+  const int nsb = (S->J + 31) / 32;
+  Launch L(S, SQC_KF_UPDATE, nullptr, "post_stats");
+  switch (S->D) { SQC_FOR_D(SQC_CASE_POST) default: fail(SQC_ERR_BAD_ARG, "D = %d not compiled in", S->D); }
+  L.done();
+}
 #define SQC_CASE_AFTER(DD) case DD: k_after_mstep<DD><<<(S->J + 7) / 8, 256, 0, S->st>>>(S->dev, with_p); break;
 void do_after_mstep(sqc_session* S, int with_p) {
   Launch L(S, SQC_KF_UPDATE);
@@ -833,10 +840,10 @@ void run_robust(sqc_session* S) {
     }
     enqueue_keys(S, 0, nullptr);
   }
-  const int nsb = (J + 31) / 32;
-  auto post_stats = [&](int fuse_ctl) {
-    Launch L(S, SQC_KF_UPDATE); k_post_stats<<<nsb, 1024, 0, S->st>>>(s, nsb, fuse_ctl); L.done();
-  };
+  // single GPU: the end-of-iteration bookkeeping and the next iteration's alpha_j ride in k_post_stats (SQC_FUSE_ALPHA=0: own launch)
+  static const bool fuse_alpha_env = !(getenv("SQC_FUSE_ALPHA") && atoi(getenv("SQC_FUSE_ALPHA")) == 0);
+  const int loop_flags = S->world > 1 ? 0 : ((fuse_alpha_env && S->D <= POST_ALPHA_MAXD) ? 3 : 1);
+  auto post_stats = [&](int flags) { do_post_stats(S, flags); };
   auto m_step = [&](int call, int like) {
     do_partition(S, like);
     use_keys(S, call);
@@ -857,10 +864,10 @@ void run_robust(sqc_session* S) {
   { Launch L(S, SQC_KF_UPDATE); k_ctl_start_loop<<<1, 32, 0, S->st>>>(s); L.done(); }
   CK(cudaEventRecord(S->ev_init, S->st));
   for (int it = 0; it < S->em_iters; ++it) {                                            // :490
-    do_update_alpha(S);                                                                 // :496
+    if (it == 0 || !(loop_flags & 2)) do_update_alpha(S);                               // :496 (later iterations: inside the k_post_stats before)
     m_step(it + 1, 1);                                                                  // like_1 :499, M-step :502, p_jk :504
     do_estep(S, 0);                                                                     // :506, :509, :519
-    post_stats(S->world > 1 ? 0 : 1);                                                  // single GPU: :511-521 fused in
+    post_stats(loop_flags);                                                             // single GPU: :511-521 and the next :496 fused in
     if (S->key_q && it + 2 <= S->em_iters) CK(cudaStreamWaitEvent(S->st, S->ev_key_ready[(it + 2) & 1], 0));   // keys of the next call (fence, see above)
     if (S->world > 1) xchg_iteration(S, s, 1);     // cluster layout of the next M-step + like / z_delta / status + loop control
   }
