@@ -776,6 +776,7 @@ sqc_session* session_create(const sqc_fit_args* a, int variant, InprocGroup* grp
     mb.xc = S->xc.dev;
     mb.epoch = S->alloc<unsigned int>(2 * SQC_MAXK + 4); mb.arrive = mb.epoch + SQC_MAXK; mb.status = (int*)(mb.epoch + 2 * SQC_MAXK);
     s.mcd_sync = mb.epoch;
+    mb.join = getenv("SQC_MCD_JOIN") ? atoi(getenv("SQC_MCD_JOIN")) : 0;     // 1: worker classes join (faster tail, sums reproducible to rounding only)
     mb.trace_leader = getenv("SQC_MCD_TRACE") ? atoi(getenv("SQC_MCD_TRACE")) : 0;
     mb.trace = getenv("SQC_MCD_TRACE") ? S->alloc<long long>(16 * 512) : nullptr;
     if (S->rng_mode == SQC_RNG_R_COMPAT) {

@@ -34,7 +34,7 @@
 // of the big ones at C3), and with one pool its renewed epoch has to wait until every worker has finished the share of
 // a big cluster it is in the middle of (non-preemptive, ~17 us of a ~33 us round).  So while big AND small clusters are
 // active, a fixed share of the workers (SQC_MCD_SMALL_WORKERS) serves only the small clusters (n_k <= N /
-// SQC_MCD_SMALL_DIV) and the others only the big ones; when one class has finished, its workers join the other.  Who
+// SQC_MCD_SMALL_DIV) and the others only the big ones (SQC_MCD_JOIN=1: when one class has finished, its workers join the other).  Who
 // serves an epoch is decided by the leader and published in the epoch word ({number, done, all}), so the arrival count
 // it waits for and the set of per-CTA partials / candidate regions it reads are known exactly; the chunk dealing, hence
 // every reduction order, is a function of that set only: results stay bit-reproducible.
@@ -138,7 +138,9 @@ struct McdBufs {
   unsigned long long call_mix;         // counter-mode key mix for this call
   long long stream_base;               // call * N_total: index of this call's first draw
   McdPred* pred;                       // K: threshold history of the previous calls (band prediction)
-  int call, pad_call;                  // index of this update_beta_scale_k call (0 = initial labelling)
+  int call;                            // index of this update_beta_scale_k call (0 = initial labelling)
+  int join;                            // worker classes: 1 = the workers of a class whose clusters are all done join the other class (the
+                                       // moment they do depends on timing: results reproducible to rounding only); 0 = never (default)
   unsigned int* epoch;                 // K: state version of every cluster (0 at launch; the leader publishes 1, 2, ...)
   unsigned int* arrive;                // K: worker arrivals (0 at launch)
   int* status;                         // in-kernel error word (0 at launch): identical on every rank, derived from exchanged data only
@@ -390,8 +392,13 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
     auto publish = [&](int epoch_no) {
       if (tid == 0) {
         int all = 1;
-        if (split) {                                               // the other class joins once all of ITS clusters are done
-          for (int k2 = 0; k2 < K; ++k2) if (sh_small[k2] != my_small && !(ld_acquire_u32(&mb.epoch[k2]) & 2u)) all = 0;
+        if (split) {
+          // Who serves an epoch fixes the chunk dealing and with it the order of every floating-point sum.  By default the
+          // classes stay apart for the whole launch, so that order is a function of the data alone: two runs give the
+          // same bits ("seeds are replicable", tests/testthat/test-03_fit_sampleqc.R:81-88).  mb.join: the other class
+          // joins once all of ITS clusters are done — WHEN this leader notices is a matter of timing.
+          if (!mb.join) all = 0;
+          else for (int k2 = 0; k2 < K; ++k2) if (sh_small[k2] != my_small && !(ld_acquire_u32(&mb.epoch[k2]) & 2u)) all = 0;
         }
         sh_clu.serve_all = all;
       }

@@ -9,7 +9,7 @@ python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_${TAG}_
 export SQC_BENCH_PROFILING=1
 CMD="python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-extra"
 $CMD > gpurun_out/plain_$TAG.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -s 700 -c 560 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_list_$TAG.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -s 560 -c 560 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_list_$TAG.log 2>&1
 $CMD > gpurun_out/plain2_$TAG.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:'k_mcd|k_estep|k_partition|k_mt_jump|k_mt_gen' -s 150 -c 6 -o /tmp/prof_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
 tail -2 gpurun_out/ncu_full_$TAG.log

@@ -95,3 +95,29 @@ def test_c5_shape_k5_robust_and_mle(oracle):
         scale = np.max(np.abs(ref[key]))
         np.testing.assert_allclose(got[key], ref[key], rtol=1e-8, atol=1e-8 * scale, err_msg=key)
     np.testing.assert_array_equal(got["z"], ref["z"])
+
+
+def test_large_fit_is_bit_reproducible():
+    """"seeds are replicable" (reference tests/testthat/test-03_fit_sampleqc.R:81-88) at a size where k_mcd runs with its two
+    worker classes (one component under N / 8 beside three big ones, as in C3) and the launches overlap the key stream:
+    re-runs of a resident session and fresh fits give the same bits — nothing may depend on timing.  (With
+    SQC_MCD_JOIN=1 the worker classes merge at a moment that timing decides and this test fails now and then:
+    scripts/determinism_probe.py, profiles/r2z_determinism.md.)"""
+    from sampleqc_b200 import api
+    from sampleqc_b200.simulate import simulate_qcs
+    sim = simulate_qcs(2_400_000, 240, 4, 3, seed=77)
+    keep = (sim.z_true != 3) | (np.random.default_rng(5).random(sim.z_true.size) < 0.15)      # thin one component out
+    x, g, iz = np.asfortranarray(sim.x[keep]), sim.groups[keep], sim.z_true[keep].astype(np.int32)
+    N, J, K, D = int(keep.sum()), 240, 4, 3
+    assert np.unique(g).size == J and np.bincount(iz, minlength=K).min() * 8 <= N          # a "small" cluster: both worker classes in use
+    em = 12
+    keys = ("mu_0", "alpha_j", "beta_k", "sigma_k", "p_jk", "like_1", "like_2", "z")
+    for rng_mode in (0, 1):
+        with api.Session(x, g, D, J, K, N, em, init_z=iz, mcd_alpha=0.5, mcd_iters=50, seed=0, rng_mode=rng_mode) as s:
+            s.run(); a = s.fetch()
+            s.run(); s.run(); b = s.fetch()
+        fits = [api.fit_sampleqc_robust_cpp(x, iz, g, D, J, K, N, em, 0.5, 50, 0, rng_mode=rng_mode) for _ in range(3)]
+        for other in [b] + fits:
+            assert other["n_iter"] == a["n_iter"]
+            for key in keys:
+                np.testing.assert_array_equal(other[key], a[key], err_msg=key)
