@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
         // candidate counts of this thread's regions: same L2 round trip as the partials and the fine histogram
         unsigned int cn[MCD_RPT];
 #pragma unroll
-        for (int i = 0; i < MCD_RPT; ++i) { const int rg = i * MCD_THREADS + tid; cn[i] = (rg >= cta_lo * MCD_WARPS && rg < cta_hi * MCD_WARPS) ? ccnt[rg] : 0u; }   // regions dealt round-robin over the threads
+        for (int i = 0; i < MCD_RPT; ++i) { const int rg = tid * MCD_RPT + i; cn[i] = (rg >= cta_lo * MCD_WARPS && rg < cta_hi * MCD_WARPS) ? ccnt[rg] : 0u; }   // thread t: regions t * MCD_RPT ..
         // 1. fine histogram of the candidates: built by the workers with atomics on mb.fhist
         {
           constexpr int FPT = (MCD_NF + 4 + MCD_THREADS - 1) / MCD_THREADS;
@@ -592,50 +592,62 @@ __global__ void __launch_bounds__(MCD_THREADS, 1) k_mcd(Dev s, McdBufs mb) {
           double cs[D];
 #pragma unroll
           for (int d = 0; d < D; ++d) cs[d] = cl.cshift[d];
-          // every thread walks its own candidate regions (region i * threads + tid), slot by slot; the record loads of a
-          // trip (one slot of up to MCD_PB regions) are all in flight together — the pass is bound by L2 round trips.  The
-          // order a thread adds its members in depends on the regions' contents only: reproducible.
-          unsigned int mx = 0;
+          // The candidates are numbered flat — regions in index order, slots in order — and dealt round-robin over the
+          // threads: thread t takes candidates t, t + threads, ...  (a prefix of the region counts in shared memory, a
+          // binary search per candidate).  However the candidates spread over the regions, the pass takes
+          // ceil(candidates / (threads x FB)) L2 round trips (one for a few hundred candidates); walking each region
+          // slot by slot took as many as the fullest region had slots.  Which thread adds which member depends on the
+          // regions' contents only: reproducible.
+          unsigned int mine_c = 0;
 #pragma unroll
-          for (int i = 0; i < MCD_RPT; ++i) { cn[i] = min(cn[i], (unsigned)MCD_CAPW); mx = max(mx, cn[i]); }
-          constexpr int MCD_PB = (D <= 4) ? 4 : 2;
-          static_assert(MCD_RPT % MCD_PB == 0, "regions per thread in whole batches");
-          for (unsigned int sl = 0; sl < mx; ++sl) {
+          for (int i = 0; i < MCD_RPT; ++i) { cn[i] = min(cn[i], (unsigned)MCD_CAPW); mine_c += cn[i]; }
+          long long total_c;
+          const long long base_c = block_excl_scan<MCD_THREADS>((long long)mine_c, sh_scan, &total_c);
+          unsigned int* sh_pref = sh_hist;                           // the fine histogram has been consumed (fbin, fbelow, overflow are in registers / sh_u64)
+          {
+            unsigned int run_c = (unsigned int)base_c;
 #pragma unroll
-            for (int i0 = 0; i0 < MCD_RPT; i0 += MCD_PB) {
-              bool live[MCD_PB]; bool any = false;
+            for (int i = 0; i < MCD_RPT; ++i) { sh_pref[tid * MCD_RPT + i] = run_c; run_c += cn[i]; }
+          }
+          static_assert(MCD_THREADS * MCD_RPT <= MCD_NB, "region prefixes fit the histogram buffer");
+          if (tid == 0) sh_pref[MCD_THREADS * MCD_RPT] = (unsigned int)total_c;
+          __syncthreads();
+          const int ntot = (int)total_c;
+          constexpr int FB = (D <= 4) ? 4 : 2;                       // records in flight per thread
+          for (int f0 = tid; f0 < ntot; f0 += FB * MCD_THREADS) {
+            unsigned long long wv[FB][2 + D]; int rgs[FB], sls[FB]; bool live[FB];
 #pragma unroll
-              for (int q = 0; q < MCD_PB; ++q) { live[q] = sl < cn[i0 + q]; any = any || live[q]; }
-              if (!any) continue;
-              unsigned long long wv[MCD_PB][2 + D];
-#pragma unroll
-              for (int q = 0; q < MCD_PB; ++q) {
-                const int rg = (i0 + q) * MCD_THREADS + tid;
-                const unsigned long long* rec = mb.cand_rec + (((long long)k * regions + rg) * MCD_CAPW + sl) * (2 + D);
-#pragma unroll
-                for (int e = 0; e < 2 + D; ++e) wv[q][e] = live[q] ? __ldcg(rec + e) : 0ull;
+            for (int q = 0; q < FB; ++q) {
+              const int f = f0 + q * MCD_THREADS;
+              live[q] = f < ntot;
+              int lo = 0, hi = MCD_THREADS * MCD_RPT;               // largest region with prefix <= f (regions without candidates share their successor's prefix)
+              if (live[q]) {
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sh_pref[mid] <= (unsigned int)f) lo = mid; else hi = mid; }
               }
+              rgs[q] = lo; sls[q] = live[q] ? f - (int)sh_pref[lo] : 0;
+              const unsigned long long* rec = mb.cand_rec + (((long long)k * regions + lo) * MCD_CAPW + sls[q]) * (2 + D);
 #pragma unroll
-              for (int q = 0; q < MCD_PB; ++q) {
-                if (!live[q]) continue;
-                const int rg = (i0 + q) * MCD_THREADS + tid;
-                const unsigned long long bits = wv[q][0];
-                const int fb = (int)((bits - blo) >> fshift);
-                if (fb < fbin) {
-                  if (need_mom) {
-                    double r[D];
+              for (int e = 0; e < 2 + D; ++e) wv[q][e] = live[q] ? __ldcg(rec + e) : 0ull;
+            }
 #pragma unroll
-                    for (int d = 0; d < D; ++d) r[d] = __longlong_as_double((long long)wv[q][2 + d]);
-                    Mom<D>::add(tot, r, cs, true);
-                  }
-                } else if (fb == fbin) {
-                  const int t = atomicAdd(&sh_flag[4], 1);
-                  if (t < MCD_TINY) {
-                    sh_tkey[t] = bits; sh_tpos[t] = (unsigned int)wv[q][1]; sh_tref[t] = (unsigned int)(rg * MCD_CAPW + (int)sl); sh_trank[t] = (unsigned)myrank;
-                    if (t < MCD_TCACHE) {
+            for (int q = 0; q < FB; ++q) {
+              if (!live[q]) continue;
+              const unsigned long long bits = wv[q][0];
+              const int fb = (int)((bits - blo) >> fshift);
+              if (fb < fbin) {
+                if (need_mom) {
+                  double r[D];
 #pragma unroll
-                      for (int d = 0; d < D; ++d) sh_tr[t * D + d] = __longlong_as_double((long long)wv[q][2 + d]);
-                    }
+                  for (int d = 0; d < D; ++d) r[d] = __longlong_as_double((long long)wv[q][2 + d]);
+                  Mom<D>::add(tot, r, cs, true);
+                }
+              } else if (fb == fbin) {
+                const int t = atomicAdd(&sh_flag[4], 1);
+                if (t < MCD_TINY) {
+                  sh_tkey[t] = bits; sh_tpos[t] = (unsigned int)wv[q][1]; sh_tref[t] = (unsigned int)(rgs[q] * MCD_CAPW + sls[q]); sh_trank[t] = (unsigned)myrank;
+                  if (t < MCD_TCACHE) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) sh_tr[t * D + d] = __longlong_as_double((long long)wv[q][2 + d]);
                   }
                 }
               }
