@@ -14,7 +14,7 @@ KERNELS = [("k_mcd<3, false>", "_ZN3sqc5k_mcdILi3ELb0EEEvNS_3DevENS_7McdBufsE"),
            ("k_mt_gen", "_ZN3sqc8k_mt_genEPKjPjS1_S1_PixiPKNS_7ControlE")]
 print("# SASS opcode histograms (static), sm_100a, `cuobjdump -sass` of sampleqc_b200/libsampleqc_cuda.so\n")
 print("Static counts: loops execute their bodies many times (the per-launch dynamic mix of the E-step / partition kernels is in "
-      "`r2final_ncu_summary.md`).  Data movement is through `LDG` (128-bit where the layout allows: `LDG.E.NA.128.CONSTANT` = `ld.global.nc.L1::no_allocate.v2.f64` in the streaming loop of `k_mcd`) and `STG`; "
+      "`r2z_ncu_summary.md`).  Data movement is through `LDG` (128-bit where the layout allows: `LDG.E.NA.128.CONSTANT` = `ld.global.nc.L1::no_allocate.v2.f64` in the streaming loop of `k_mcd`) and `STG`; "
       "no `UBLKCP` / `UTMALDG` — a TMA-staged variant of the two per-cell passes was built and measured slower (DESIGN.md section 8).\n")
 names = subprocess.run(["cuobjdump", "-elf", SO], capture_output=True, text=True).stdout
 for title, sym in KERNELS:
