@@ -653,7 +653,7 @@ def main():
     if rank != 0:
         return
     out = {"metric": METRIC, "value": m["value"], "unit": "cell-iters/s", "n_gpus": world, "steps": a.steps, "warmup": n_warm,
-           "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak" if (weak or world == 1) else "strong", "vs_baseline": None, "dtype": "f64",
+           "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak" if weak else ("strong" if world > 1 else a.scaling), "vs_baseline": None, "dtype": "f64",
            "data": "synthetic", "config": config, "em_iterations_per_step": m["n_iter"], "clocks": m["clocks"], "e2e": m["e2e"],
            "gpu_launches": m["launches"], "roofline": m["roofline"], "checks": checks}
     if extra:
